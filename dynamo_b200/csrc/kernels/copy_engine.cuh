@@ -1,0 +1,371 @@
+// The warp-level TMA ring that every KV transfer kernel in this library is built from.
+//
+// One warp owns `S` shared-memory slots of `tile` bytes and walks its share of the work items:
+//
+//     HBM (paged source) --cp.async.bulk--> smem slot --cp.async.bulk--> HBM / NVLink peer (1..N)
+//
+// Lane 0 drives both directions asynchronously (loads complete on per-slot mbarriers, stores are
+// tracked by bulk async-groups); the other lanes only work for pieces that cannot use TMA (pointer
+// or size not a multiple of 16 B -> vectorised SIMT ladder) and for the fused fp8<->bf16 cast.
+// A CTA is W such warps, each with a private ring, so a single SM keeps W*(S-1) tiles in flight.
+#pragma once
+#include "ptx.cuh"
+
+namespace kvbm {
+
+constexpr int kMaxDst = 8;
+constexpr int kMaxStages = 16;
+
+// One unit of work: `bytes` (of source) from `src` to each of dst[0..ndst).
+struct Piece {
+  const uint8_t* src;
+  uint8_t* dst[kMaxDst];
+  uint32_t bytes;  // source bytes
+  int ndst;
+  int layer;  // for layer-streaming flags (0 when unused)
+};
+
+// ------------------------------------------------------------------------------------------
+// SIMT ladder for pieces TMA cannot take.  Same alignment contract as the reference K1 kernel
+// (/root/reference/lib/kvbm-kernels/cuda/tensor_kernels.cu:511-540): the widest vector both
+// pointers allow, byte tail.  Whole warp cooperates, 4 independent 16 B loads in flight per lane.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_copy_simt(uint8_t* dst, const uint8_t* src, uint32_t bytes,
+                                               int lane)
+{
+  const uintptr_t both = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src);
+  uint32_t done = 0;
+  if ((both & 15) == 0) {
+    const uint32_t n = bytes >> 4;
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    uint32_t i = lane;
+    for (; i + 96 < n; i += 128) {
+      uint4 a = ptx::ld_stream_v4(s + i), b = ptx::ld_stream_v4(s + i + 32);
+      uint4 c = ptx::ld_stream_v4(s + i + 64), e = ptx::ld_stream_v4(s + i + 96);
+      ptx::st_stream_v4(d + i, a);
+      ptx::st_stream_v4(d + i + 32, b);
+      ptx::st_stream_v4(d + i + 64, c);
+      ptx::st_stream_v4(d + i + 96, e);
+    }
+    for (; i < n; i += 32) ptx::st_stream_v4(d + i, ptx::ld_stream_v4(s + i));
+    done = n << 4;
+  } else if ((both & 7) == 0) {
+    const uint32_t n = bytes >> 3;
+    const uint2* s = reinterpret_cast<const uint2*>(src);
+    uint2* d = reinterpret_cast<uint2*>(dst);
+#pragma unroll 4
+    for (uint32_t i = lane; i < n; i += 32) d[i] = s[i];
+    done = n << 3;
+  } else if ((both & 3) == 0) {
+    const uint32_t n = bytes >> 2;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll 4
+    for (uint32_t i = lane; i < n; i += 32) d[i] = s[i];
+    done = n << 2;
+  }
+#pragma unroll 4
+  for (uint32_t i = done + lane; i < bytes; i += 32) dst[i] = src[i];
+}
+
+__device__ __forceinline__ bool piece_tma_ok(const Piece& p)
+{
+  uintptr_t m = reinterpret_cast<uintptr_t>(p.src) | p.bytes;
+#pragma unroll
+  for (int d = 0; d < kMaxDst; ++d)
+    if (d < p.ndst) m |= reinterpret_cast<uintptr_t>(p.dst[d]);
+  return (m & 15) == 0 && p.bytes != 0;
+}
+
+// Layer-streaming hooks shared by the rings.  All members may be null.
+struct StreamSync {
+  const uint32_t* layer_ready;  // wait until layer_ready[l] >= epoch before reading layer l
+  uint32_t* workspace;          // [num_layers + 1] zeroed counters (last = whole transfer)
+  uint32_t* done_flag[kMaxDst];
+  uint32_t* layer_done[kMaxDst];
+  uint32_t epoch;
+  uint32_t total_warps;
+  int ndst;
+  int num_layers;  // counters per layer live at workspace[l]; whole-transfer counter at [num_layers]
+  int layer_begin, layer_end;
+  bool any;        // false -> every hook below is skipped
+};
+
+__device__ __forceinline__ void wait_layer_ready(const StreamSync& ss, int layer, int lane)
+{
+  if (ss.layer_ready == nullptr) return;
+  if (lane == 0) {
+    while (ptx::ld_acquire_sys(ss.layer_ready + layer) < ss.epoch) __nanosleep(64);
+  }
+  __syncwarp();
+}
+
+// This warp has *completed* (stores landed) everything it owns in layers [from, to).
+__device__ __forceinline__ void arrive_layers(const StreamSync& ss, int from, int to, int lane)
+{
+  if (lane != 0 || ss.workspace == nullptr) return;
+  bool want_layers = false;
+#pragma unroll
+  for (int d = 0; d < kMaxDst; ++d)
+    if (d < ss.ndst && ss.layer_done[d] != nullptr) want_layers = true;
+  if (!want_layers) return;
+  for (int l = from; l < to; ++l) {
+    uint32_t old = ptx::atom_add_acq_rel_gpu(ss.workspace + l, 1u);
+    if (old == ss.total_warps - 1) {
+      ss.workspace[l] = 0;  // leave the workspace zeroed for the next launch
+      __threadfence_system();
+#pragma unroll
+      for (int d = 0; d < kMaxDst; ++d)
+        if (d < ss.ndst && ss.layer_done[d] != nullptr) ptx::st_release_sys(ss.layer_done[d] + l, ss.epoch);
+    }
+  }
+}
+
+__device__ __forceinline__ void arrive_transfer(const StreamSync& ss, int lane)
+{
+  if (lane != 0 || ss.workspace == nullptr) return;
+  uint32_t old = ptx::atom_add_acq_rel_gpu(ss.workspace + ss.num_layers, 1u);
+  if (old == ss.total_warps - 1) {
+    ss.workspace[ss.num_layers] = 0;
+    __threadfence_system();
+#pragma unroll
+    for (int d = 0; d < kMaxDst; ++d)
+      if (d < ss.ndst && ss.done_flag[d] != nullptr) ptx::st_release_sys(ss.done_flag[d], ss.epoch);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Byte-exact ring.  Gen::get(item, Piece&) must be warp-uniform.
+//   first/stride/total : this warp's arithmetic progression of item indices
+//   slots              : S * tile bytes of shared memory private to this warp (16 B aligned)
+//   bars               : S mbarriers private to this warp (already initialised, count 1)
+// ------------------------------------------------------------------------------------------
+template <class Gen>
+__device__ __forceinline__ void warp_copy_ring(const Gen& gen, uint32_t first, uint32_t stride,
+                                               uint32_t total, uint8_t* slots, uint64_t* bars,
+                                               int S, uint32_t tile, bool allow_tma,
+                                               const StreamSync& ss)
+{
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_my = total > first ? (total - first + stride - 1) / stride : 0;
+  const uint32_t slot0 = ptx::smem_addr(slots);
+  const uint32_t bar0 = ptx::smem_addr(bars);
+  uint32_t phase = 0;  // bit s = parity the next wait on slot s expects
+
+  int ready_layer = ss.layer_begin - 1;  // highest layer whose ready flag we have observed
+  int open_layer = ss.layer_begin;       // lowest layer this warp has not yet arrived for
+
+  auto issue_load = [&](uint32_t q) {
+    Piece p;
+    gen.get(first + q * stride, p);
+    if (ss.any && p.layer > ready_layer) {
+      wait_layer_ready(ss, p.layer, lane);
+      ready_layer = p.layer;
+    }
+    if (allow_tma && piece_tma_ok(p) && lane == 0) {
+      const int s = q % S;
+      ptx::mbar_arrive_expect_tx(bar0 + 8 * s, p.bytes);
+      ptx::bulk_g2s(slot0 + s * tile, p.src, p.bytes, bar0 + 8 * s);
+    }
+  };
+
+  const uint32_t depth = static_cast<uint32_t>(S - 1) < n_my ? static_cast<uint32_t>(S - 1) : n_my;
+  for (uint32_t q = 0; q < depth; ++q) issue_load(q);
+
+  for (uint32_t q = 0; q < n_my; ++q) {
+    Piece p;
+    gen.get(first + q * stride, p);
+    if (ss.any && p.layer > open_layer) {
+      // everything this warp owns below p.layer has been issued: drain, then publish those layers
+      if (lane == 0) {
+        ptx::bulk_wait<0>();
+        ptx::fence_proxy_async_global();
+        __threadfence_system();
+      }
+      __syncwarp();
+      arrive_layers(ss, open_layer, p.layer, lane);
+      open_layer = p.layer;
+    }
+    const int s = q % S;
+    if (allow_tma && piece_tma_ok(p)) {
+      if (lane == 0) {
+        ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);
+#pragma unroll
+        for (int d = 0; d < kMaxDst; ++d)
+          if (d < p.ndst) ptx::bulk_s2g(p.dst[d], slot0 + s * tile, p.bytes);
+      }
+      phase ^= 1u << s;
+    } else {
+      for (int d = 0; d < p.ndst; ++d) warp_copy_simt(p.dst[d], p.src, p.bytes, lane);
+    }
+    if (lane == 0) {
+      ptx::bulk_commit();       // always one group per item (possibly empty) so the count below holds
+      ptx::bulk_wait_read<1>(); // store q-1 has left its slot -> slot (q-1)%S == (q+S-1)%S is free
+    }
+    if (q + S - 1 < n_my) issue_load(q + S - 1);
+  }
+
+  if (lane == 0) {
+    ptx::bulk_wait<0>();
+    ptx::fence_proxy_async_global();
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (ss.any) {
+    arrive_layers(ss, open_layer, ss.layer_end, lane);
+    arrive_transfer(ss, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Casting ring.  UP: fp8 e4m3 -> bf16 (dst bytes = 2 x src bytes); !UP: bf16 -> fp8 (dst = src/2).
+//   in slots : S * tile_in ; out slots : 2 * tile_out (double buffered).
+// ------------------------------------------------------------------------------------------
+template <bool UP>
+__device__ __forceinline__ void convert_smem(uint32_t in_smem, uint32_t out_smem, uint32_t src_bytes,
+                                             int lane)
+{
+  if (UP) {
+    // 16 fp8 in (16 B) -> 16 bf16 out (32 B) per lane-iteration
+    for (uint32_t off = lane * 16; off < src_bytes; off += 32 * 16) {
+      uint4 v;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(in_smem + off));
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t o[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        o[2 * k] = ptx::e4m3x2_to_bf16x2(static_cast<uint16_t>(w[k] & 0xffff));
+        o[2 * k + 1] = ptx::e4m3x2_to_bf16x2(static_cast<uint16_t>(w[k] >> 16));
+      }
+      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(out_smem + 2 * off), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(out_smem + 2 * off + 16), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+    }
+  } else {
+    // 16 bf16 in (32 B) -> 16 fp8 out (16 B)
+    for (uint32_t off = lane * 32; off < src_bytes; off += 32 * 32) {
+      uint4 a, b;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(in_smem + off));
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(in_smem + off + 16));
+      uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        o[k] = static_cast<uint32_t>(ptx::bf16x2_to_e4m3x2(w[2 * k])) |
+               (static_cast<uint32_t>(ptx::bf16x2_to_e4m3x2(w[2 * k + 1])) << 16);
+      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(out_smem + off / 2), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+    }
+  }
+}
+
+// SIMT conversion straight from global to global for pieces TMA cannot take (any alignment).
+template <bool UP>
+__device__ __forceinline__ void warp_cast_simt(uint8_t* dst, const uint8_t* src, uint32_t src_bytes,
+                                               int lane)
+{
+  if (UP) {
+    uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+    const uint32_t pairs = src_bytes >> 1;
+    for (uint32_t i = lane; i < pairs; i += 32) {
+      uint16_t two = static_cast<uint16_t>(src[2 * i]) | (static_cast<uint16_t>(src[2 * i + 1]) << 8);
+      uint32_t r = ptx::e4m3x2_to_bf16x2(two);
+      d[2 * i] = static_cast<uint16_t>(r & 0xffff);
+      d[2 * i + 1] = static_cast<uint16_t>(r >> 16);
+    }
+    if ((src_bytes & 1) && lane == 0)
+      d[src_bytes - 1] = static_cast<uint16_t>(ptx::e4m3x2_to_bf16x2(src[src_bytes - 1]) & 0xffff);
+  } else {
+    const uint16_t* s = reinterpret_cast<const uint16_t*>(src);
+    const uint32_t elems = src_bytes >> 1;
+    for (uint32_t i = lane; i < elems; i += 32)
+      dst[i] = static_cast<uint8_t>(ptx::bf16x2_to_e4m3x2(s[i]) & 0xff);
+  }
+}
+
+template <bool UP, class Gen>
+__device__ __forceinline__ void warp_cast_ring(const Gen& gen, uint32_t first, uint32_t stride,
+                                               uint32_t total, uint8_t* in_slots, uint8_t* out_slots,
+                                               uint64_t* bars, int S, uint32_t tile_in,
+                                               bool allow_tma, const StreamSync& ss)
+{
+  const int lane = threadIdx.x & 31;
+  const uint32_t tile_out = UP ? tile_in * 2 : tile_in / 2;
+  const uint32_t n_my = total > first ? (total - first + stride - 1) / stride : 0;
+  const uint32_t in0 = ptx::smem_addr(in_slots);
+  const uint32_t out0 = ptx::smem_addr(out_slots);
+  const uint32_t bar0 = ptx::smem_addr(bars);
+  uint32_t phase = 0;
+  int ready_layer = ss.layer_begin - 1;
+  int open_layer = ss.layer_begin;
+
+  auto elig = [&](const Piece& p) {
+    // source bytes must also be a multiple of 32 so that both sides are whole 16 B vectors
+    return allow_tma && piece_tma_ok(p) && (p.bytes & 31) == 0;
+  };
+  auto issue_load = [&](uint32_t q) {
+    Piece p;
+    gen.get(first + q * stride, p);
+    if (ss.any && p.layer > ready_layer) {
+      wait_layer_ready(ss, p.layer, lane);
+      ready_layer = p.layer;
+    }
+    if (elig(p) && lane == 0) {
+      const int s = q % S;
+      ptx::mbar_arrive_expect_tx(bar0 + 8 * s, p.bytes);
+      ptx::bulk_g2s(in0 + s * tile_in, p.src, p.bytes, bar0 + 8 * s);
+    }
+  };
+
+  const uint32_t depth = static_cast<uint32_t>(S) < n_my ? static_cast<uint32_t>(S) : n_my;
+  for (uint32_t q = 0; q < depth; ++q) issue_load(q);
+
+  for (uint32_t q = 0; q < n_my; ++q) {
+    Piece p;
+    gen.get(first + q * stride, p);
+    if (ss.any && p.layer > open_layer) {
+      if (lane == 0) {
+        ptx::bulk_wait<0>();
+        ptx::fence_proxy_async_global();
+        __threadfence_system();
+      }
+      __syncwarp();
+      arrive_layers(ss, open_layer, p.layer, lane);
+      open_layer = p.layer;
+    }
+    const int s = q % S;
+    const uint32_t dst_bytes = UP ? p.bytes * 2 : p.bytes / 2;
+    if (elig(p)) {
+      const uint32_t ob = out0 + (q & 1) * tile_out;
+      if (lane == 0) ptx::bulk_wait_read<1>();  // store q-2 (same out buffer) has been read out
+      __syncwarp();
+      ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);  // every lane reads the slot
+      phase ^= 1u << s;
+      convert_smem<UP>(in0 + s * tile_in, ob, p.bytes, lane);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < kMaxDst; ++d)
+          if (d < p.ndst) ptx::bulk_s2g(p.dst[d], ob, dst_bytes);
+      }
+    } else {
+      for (int d = 0; d < p.ndst; ++d) warp_cast_simt<UP>(p.dst[d], p.src, p.bytes, lane);
+    }
+    if (lane == 0) ptx::bulk_commit();
+    // the input slot was consumed synchronously by this warp: refill it right away
+    if (q + S < n_my) issue_load(q + S);
+  }
+
+  if (lane == 0) {
+    ptx::bulk_wait<0>();
+    ptx::fence_proxy_async_global();
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (ss.any) {
+    arrive_layers(ss, open_layer, ss.layer_end, lane);
+    arrive_transfer(ss, lane);
+  }
+}
+
+}  // namespace kvbm

@@ -1,0 +1,153 @@
+/*
+ * kvbm_kernels.h -- C ABI of libkvbm_kernels.so, the B200-native (sm_100a) replacement for
+ * Dynamo's lib/kvbm-kernels.
+ *
+ * Part 1 are the six symbols the reference exports and its Rust FFI binds
+ *   (/root/reference/lib/kvbm-kernels/cuda/tensor_kernels.cu:306,332,360,389,477,551;
+ *    Rust declarations lib/kvbm-kernels/src/tensor_kernels.rs:46-74,89-109).
+ * Signatures, enum values, return codes and edge-case behaviour are identical, so this library is a
+ * drop-in via LD_LIBRARY_PATH exactly as lib/kvbm-kernels/cuda/stubs.c:4-7 documents.
+ *
+ * Part 2 are the v2 extensions: the block-table ("paged") gather -> push -> scatter kernel with
+ * address arithmetic on the device, multi-destination fan-out over NVLink peer mappings, the fused
+ * fp8<->bf16 cast and in-kernel completion / layer-streaming flags.  They replace the host loop +
+ * pointer-table upload + host sync of lib/kvbm-physical/src/transfer/executor/cuda.rs:234-327 and
+ * the grouped ncclBcast of lib/kvbm-engine/src/collectives/nccl.rs:321-356.
+ *
+ * No torch types; plain pointers and sizes.  All functions are thread-safe and hold no global state
+ * (device attribute queries are cached per device).  Nothing here ever falls back to a CPU copy.
+ */
+#ifndef KVBM_KERNELS_H
+#define KVBM_KERNELS_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDA_RUNTIME_API_H__) || defined(__DRIVER_TYPES_H__)
+/* cudaError_t / cudaStream_t come from the CUDA headers */
+#else
+typedef int cudaError_t;    /* cudaSuccess == 0, as lib/kvbm-kernels/cuda/stubs.c:14-18 */
+typedef void* cudaStream_t; /* opaque */
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ============================ Part 1: reference ABI (exact) ============================ */
+
+/* tensor_kernels.cu:59-69 */
+enum { KVBM_DTYPE_F16 = 0, KVBM_DTYPE_BF16 = 1, KVBM_DTYPE_F32 = 2, KVBM_DTYPE_F64 = 3 };
+enum { KVBM_BLOCK_LAYOUT_NHD = 0, KVBM_BLOCK_LAYOUT_HND = 1 };
+/* tensor_kernels.cu:371-375 */
+enum {
+  KVBM_MEMCPY_BATCHED_WITH_FALLBACK = 0,
+  KVBM_MEMCPY_FALLBACK_ONLY = 1,
+  KVBM_MEMCPY_BATCH_WITHOUT_FALLBACK = 2,
+};
+
+/* Replaces tensor_kernels.cu:551-571 (K1).  src_ptrs/dst_ptrs are DEVICE-ACCESSIBLE tables (device
+ * or pinned host) of num_pairs pointers; every pair copies copy_size_bytes; any alignment; src/dst
+ * may be device, peer-device or pinned-host memory.  num_pairs==0 || copy_size_bytes==0 ->
+ * cudaSuccess before the NULL checks; NULL table -> cudaErrorInvalidValue. */
+cudaError_t kvbm_kernels_launch_vectorized_copy(void** src_ptrs, void** dst_ptrs,
+                                                size_t copy_size_bytes, int num_pairs,
+                                                cudaStream_t stream);
+
+/* Replaces tensor_kernels.cu:389-473 (K4).  HOST pointer tables, consumed before return. */
+cudaError_t kvbm_kernels_memcpy_batch(const void* const* src_ptrs, void* const* dst_ptrs,
+                                      size_t size_per_copy, size_t num_copies, int mode,
+                                      cudaStream_t stream);
+
+/* Replaces tensor_kernels.cu:306-330 (K2): block stacks [nl*no chunks of NHD|HND] -> universal
+ * [nh,nl,no,nt,hd].  Tables are device-accessible. Unknown dtype -> cudaErrorInvalidValue. */
+cudaError_t kvbm_kernels_launch_universal_from_block(void* const* universal_ptrs,
+                                                     const void* const* block_ptrs,
+                                                     size_t num_blocks, size_t nh, size_t nl,
+                                                     size_t no, size_t nt, size_t hd, int dtype,
+                                                     int layout, cudaStream_t stream);
+
+/* Replaces tensor_kernels.cu:332-356 (K3): the inverse. */
+cudaError_t kvbm_kernels_launch_block_from_universal(const void* const* universal_ptrs,
+                                                     void* const* block_ptrs, size_t num_blocks,
+                                                     size_t nh, size_t nl, size_t no, size_t nt,
+                                                     size_t hd, int dtype, int layout,
+                                                     cudaStream_t stream);
+
+/* tensor_kernels.cu:360-368 */
+bool kvbm_kernels_has_memcpy_batch_async(void);
+/* tensor_kernels.cu:477-481: always false -- this is a real CUDA build. */
+bool kvbm_kernels_is_stub_build(void);
+
+/* ============================ Part 2: v2 extensions ============================ */
+
+#define KVBM_MAX_DESTINATIONS 8
+
+/* Geometry of one KV pool as the kernel sees it.  It is the device form of
+ * Layout::memory_region (lib/kvbm-physical/src/layout/mod.rs:73-78):
+ *   addr(block, layer, outer) = layer_base[layer] + block*block_stride + outer*outer_stride
+ * FullyContiguous pools (fully_contiguous.rs:158-162) set layer_base[l] = base + l*layer_stride;
+ * LayerSeparate pools (layer_separate.rs:171-184) pass their per-layer allocations directly.
+ * layer_base is a DEVICE-ACCESSIBLE array of num_layers addresses (uploaded once per pool). */
+typedef struct kvbm_paged_layout {
+  const uint64_t* layer_base;
+  uint64_t block_stride;
+  uint64_t outer_stride;
+  uint32_t region_bytes; /* page_size * inner_dim * dtype_width_bytes */
+  uint32_t num_layers;
+  uint32_t outer_dim;
+  uint32_t num_blocks;
+} kvbm_paged_layout;
+
+/* One destination of a transfer: its pool, the block table pair and optional in-band signals.
+ * block id arrays are DEVICE-ACCESSIBLE int32[num_blocks]. */
+typedef struct kvbm_paged_dst {
+  kvbm_paged_layout layout;      /* layer_base may hold PEER addresses (NVLink-mapped) */
+  const int32_t* src_block_ids;  /* blocks to gather from the source pool */
+  const int32_t* dst_block_ids;  /* where they are scattered in this destination */
+  uint32_t* done_flag;           /* nullable; set to `epoch` (st.release.sys) once every byte landed */
+  uint32_t* layer_done_flags;    /* nullable; [num_layers]; entry l set to `epoch` when layer l landed */
+} kvbm_paged_dst;
+
+enum {
+  KVBM_CAST_NONE = 0,
+  KVBM_CAST_FP8E4M3_TO_BF16 = 1, /* exact; NaN codes -> 0x7fc0 */
+  KVBM_CAST_BF16_TO_FP8E4M3 = 2, /* round-to-nearest-even, saturate-to-finite */
+};
+
+typedef struct kvbm_paged_copy_opts {
+  uint32_t epoch;                 /* value written to done flags / compared with ready flags (>=) */
+  const uint32_t* layer_ready_flags; /* nullable; [num_layers]; layer l is read only after flag >= epoch */
+  uint32_t* sync_workspace;       /* device u32[num_layers + 1], zeroed; required iff any flag is used */
+  int max_ctas;                   /* 0 = one CTA per SM; smaller values leave SMs to the attention kernel */
+  int warps_per_cta;              /* 0 = default */
+  int stages;                     /* 0 = default */
+  int tile_bytes;                 /* 0 = default */
+  int force_simt;                 /* 1 = never use the TMA path (diagnostics) */
+} kvbm_paged_copy_opts;
+
+/* Gather `num_blocks` non-contiguous blocks x layers [layer_begin, layer_end) x outer from `src`,
+ * push them to `num_dsts` destinations and scatter them into their block tables, optionally casting.
+ * One launch, one-sided (no receiver kernel), stream-ordered, never blocks the host.
+ * When all destinations share one src_block_ids pointer the payload is read from HBM once and stored
+ * num_dsts times (replicate); otherwise each destination's blocks are gathered separately. */
+cudaError_t kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* dsts,
+                                       int num_dsts, int num_blocks, int layer_begin,
+                                       int layer_end, int cast_mode,
+                                       const kvbm_paged_copy_opts* opts, cudaStream_t stream);
+
+/* Small helpers so hosts without a CUDA binding (ctypes, cgo, JNI) can drive the flags. */
+cudaError_t kvbm_kernels_set_flags(uint32_t* flags, int first, int count, uint32_t value,
+                                   cudaStream_t stream);
+cudaError_t kvbm_kernels_wait_flag(const uint32_t* flag, uint32_t value, cudaStream_t stream);
+
+/* Number of kernel launches issued by this library since load (bench accounting). */
+uint64_t kvbm_kernels_launch_count(void);
+/* "sm_100a" build tag + whether the TMA path is compiled in. */
+const char* kvbm_kernels_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVBM_KERNELS_H */

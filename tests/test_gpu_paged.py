@@ -1,0 +1,269 @@
+"""GPU parity tests for the v2 block-table kernel (kvbm_kernels_paged_copy_v2) against the CPU oracle.
+
+The cases are the reference's transfer tests (lib/kvbm-physical/src/transfer/tests/local_transfers.rs):
+layout matrix FC/LW x FC/LW, layer ranges, guard blocks, layer composition -- with Device storage on
+both sides, checked by per-block BLAKE3 (transfer/checksum.rs:91-158) and whole-pool equality.
+"""
+import itertools
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dynamo_b200 import kernels as K
+from oracle import oracle as O
+from tests.gpu_util import DevicePool, dev_u8, ids_dev, make_layout, paged_dst, randomize, stream_ptr
+
+pytestmark = pytest.mark.gpu
+
+KINDS = [("FC", dict(kind=O.FC)), ("LWf", dict(kind=O.LW, block_dim=O.BLOCK_IS_FIRST_DIM)),
+         ("LWs", dict(kind=O.LW, block_dim=O.BLOCK_IS_SECOND_DIM))]
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def run_paged(src_pool, dst_pools, sid_list, did_list, layers=None, cast=0, opts=None, replicate=False):
+    nl = src_pool.host.num_layers
+    lb, le = (layers.start, layers.stop) if layers is not None else (0, nl)
+    shared = ids_dev(sid_list[0]) if replicate else None
+    keep, dsts = [], []
+    for pool, sid, did in zip(dst_pools, sid_list, did_list):
+        s = shared if replicate else ids_dev(sid)
+        d = ids_dev(did)
+        keep += [s, d]
+        dsts.append(paged_dst(pool, s, d))
+    rc = K.paged_copy(src_pool.desc, dsts, len(sid_list[0]), lb, le, cast, opts, stream_ptr())
+    torch.cuda.synchronize()
+    return rc
+
+
+def check_against_oracle(src_h, dst_h, dst_pool, sid, did, layers=None, cast=0):
+    """Run the oracle on the host twins, then require the device pool to equal it byte for byte."""
+    O.execute_memcpy_transfer(src_h, dst_h, sid, did, layers, cast_mode=cast)
+    want_sums = dst_h.block_checksums(did, layers)
+    want = [b.copy() for b in dst_h.buffers]
+    got = dst_pool.snapshot()
+    for w, g in zip(want, got):
+        assert np.array_equal(w, g)
+    dst_pool.download()
+    assert dst_h.block_checksums(did, layers) == want_sums
+
+
+@pytest.mark.parametrize("src_kw,dst_kw", list(itertools.product([k[1] for k in KINDS], repeat=2)),
+                         ids=[f"{a[0]}-{b[0]}" for a, b in itertools.product(KINDS, repeat=2)])
+@pytest.mark.parametrize("layers", [None, range(0, 1), range(1, 2)], ids=["full", "layer0", "layer1"])
+def test_p2p_layout_matrix(src_kw, dst_kw, layers):
+    # local_transfers.rs:108-171 (+ TransferMode layer0/layer1 of tests/mod.rs:100-113), Device -> Device
+    src_h, dst_h = make_layout(nb=6, **src_kw), make_layout(nb=6, fill=0, **dst_kw)
+    src_h.fill_blocks([0, 1], -1)
+    dst_h.fill_blocks([2, 5], 0xFF)               # guard blocks (local_transfers.rs:498-505)
+    src_p, dst_p = DevicePool(src_h), DevicePool(dst_h)
+    assert run_paged(src_p, [dst_p], [[0, 1]], [[3, 4]], layers) == 0
+    check_against_oracle(src_h, dst_h, dst_p, [0, 1], [3, 4], layers)
+    assert (dst_h.region_bytes(2, 0, 0) == 0xFF).all() and (dst_h.region_bytes(5, 1, 1) == 0xFF).all()
+
+
+@pytest.mark.parametrize("src_kw,dst_kw", list(itertools.product([k[1] for k in KINDS], repeat=2)))
+def test_layer_composition_equals_full_block(src_kw, dst_kw):
+    # local_transfers.rs:922-...
+    src_h = make_layout(nb=4, **src_kw)
+    src_h.fill_blocks([0, 1], -1)
+    full_h, lay_h = make_layout(nb=4, **dst_kw), make_layout(nb=4, **dst_kw)
+    src_p, full_p, lay_p = DevicePool(src_h), DevicePool(full_h), DevicePool(lay_h)
+    assert run_paged(src_p, [full_p], [[0, 1]], [[2, 3]]) == 0
+    assert run_paged(src_p, [lay_p], [[0, 1]], [[2, 3]], range(0, 1)) == 0
+    assert run_paged(src_p, [lay_p], [[0, 1]], [[2, 3]], range(1, 2)) == 0
+    for a, b in zip(full_p.snapshot(), lay_p.snapshot()):
+        assert np.array_equal(a, b)
+    full_p.download()
+    assert full_h.block_checksums([2, 3]) == {2: src_h.block_checksum(0), 3: src_h.block_checksum(1)}
+
+
+@pytest.mark.parametrize("geom", [
+    dict(nl=4, no=2, page=16, inner=1024, dt=2),     # Llama-3-8B bf16: 32 KiB regions (2 tiles each)
+    dict(nl=5, no=2, page=16, inner=256, dt=2),      # Llama-3-70B TP4: 8 KiB regions
+    dict(nl=3, no=1, page=16, inner=576, dt=2),      # MLA-style outer_dim=1, 18 KiB regions (tile tail)
+    dict(nl=2, no=2, page=3, inner=37, dt=2),        # 222 B regions: not a multiple of 16 -> SIMT ladder
+    dict(nl=2, no=2, page=16, inner=100, dt=4),      # 6400 B
+], ids=["8b", "70b-tp4", "mla", "odd222", "f32"])
+@pytest.mark.parametrize("force_simt", [0, 1], ids=["tma", "simt"])
+def test_random_block_tables_vllm_layout(geom, force_simt):
+    # SURVEY §8(d) cfg2 in miniature: LW/BlockIsSecondDim pools, random non-contiguous ids, random bytes
+    nb, n = 48, 20
+    mk = lambda: make_layout(O.LW, nb, block_dim=O.BLOCK_IS_SECOND_DIM, **geom)
+    src_h, dst_h = mk(), mk()
+    randomize(src_h, 1234)
+    randomize(dst_h, 99)
+    sid = np.random.default_rng(0).permutation(nb)[:n]
+    did = np.random.default_rng(1).permutation(nb)[:n]
+    src_p, dst_p = DevicePool(src_h), DevicePool(dst_h)
+    opts = K.PagedCopyOpts(force_simt=force_simt)
+    assert run_paged(src_p, [dst_p], [sid], [did], opts=opts) == 0
+    check_against_oracle(src_h, dst_h, dst_p, sid, did)
+
+
+@pytest.mark.parametrize("warps,stages,tile", [(1, 2, 4096), (2, 5, 8192), (4, 3, 16384), (8, 2, 2048), (3, 16, 512)])
+def test_ring_geometries(warps, stages, tile):
+    nb, n = 32, 16
+    mk = lambda: make_layout(O.LW, nb, nl=3, no=2, page=16, inner=512, dt=2, block_dim=O.BLOCK_IS_SECOND_DIM)
+    src_h, dst_h = mk(), mk()
+    randomize(src_h, 7)
+    sid, did = np.arange(n)[::-1].copy(), np.arange(n) + 10
+    src_p, dst_p = DevicePool(src_h), DevicePool(dst_h)
+    opts = K.PagedCopyOpts(warps_per_cta=warps, stages=stages, tile_bytes=tile, max_ctas=7)
+    assert run_paged(src_p, [dst_p], [sid], [did], opts=opts) == 0
+    check_against_oracle(src_h, dst_h, dst_p, sid, did)
+
+
+@pytest.mark.parametrize("replicate", [False, True], ids=["distinct", "replicate"])
+@pytest.mark.parametrize("ndst", [2, 4, 7])
+def test_fan_out_to_many_destinations(ndst, replicate):
+    # 1 -> N, here N pools on one device (peer mappings are plain pointers to the kernel)
+    nb, n = 40, 12
+    mk = lambda: make_layout(O.LW, nb, nl=3, no=2, page=16, inner=256, dt=2, block_dim=O.BLOCK_IS_SECOND_DIM)
+    src_h = mk()
+    randomize(src_h, 21)
+    dst_hs = [mk() for _ in range(ndst)]
+    for i, d in enumerate(dst_hs):
+        randomize(d, 100 + i)
+    rng = np.random.default_rng(5)
+    sids = [rng.permutation(nb)[:n] for _ in range(ndst)]
+    if replicate:
+        sids = [sids[0]] * ndst
+    dids = [np.random.default_rng(50 + i).permutation(nb)[:n] for i in range(ndst)]
+    src_p, dst_ps = DevicePool(src_h), [DevicePool(d) for d in dst_hs]
+    assert run_paged(src_p, dst_ps, sids, dids, replicate=replicate) == 0
+    for d_h, d_p, sid, did in zip(dst_hs, dst_ps, sids, dids):
+        check_against_oracle(src_h, d_h, d_p, sid, did)
+
+
+@pytest.mark.parametrize("force_simt", [0, 1], ids=["tma", "simt"])
+def test_fused_cast_fp8_to_bf16_all_codes(force_simt):
+    # BASELINE configs[2] in miniature; source bytes cover all 256 e4m3 codes
+    nb, n = 24, 10
+    src_h = make_layout(O.LW, nb, nl=3, no=2, page=16, inner=256, dt=1, block_dim=O.BLOCK_IS_SECOND_DIM, allow_fp8=True)
+    dst_h = make_layout(O.LW, nb, nl=3, no=2, page=16, inner=256, dt=2, block_dim=O.BLOCK_IS_SECOND_DIM)
+    randomize(src_h, 3)
+    src_h.buffers[0][:256] = np.arange(256, dtype=np.uint8)
+    sid = np.array([0] + list(np.random.default_rng(2).permutation(np.arange(1, nb))[:n - 1]))
+    did = np.random.default_rng(4).permutation(nb)[:n]
+    src_p, dst_p = DevicePool(src_h), DevicePool(dst_h)
+    opts = K.PagedCopyOpts(force_simt=force_simt)
+    assert run_paged(src_p, [dst_p], [sid], [did], cast=K.CastMode.FP8E4M3_TO_BF16, opts=opts) == 0
+    check_against_oracle(src_h, dst_h, dst_p, sid, did, cast=1)
+    # and directly against the torch-generated golden table
+    table = np.load(os.path.join(GOLD, "fp8_e4m3_to_bf16_torch.npy"))
+    got = dst_h.region_bytes(int(did[0]), 0, 0).view(np.uint16)[:256]
+    assert np.array_equal(got, table)
+
+
+@pytest.mark.parametrize("force_simt", [0, 1], ids=["tma", "simt"])
+def test_fused_cast_bf16_to_fp8_all_bit_patterns(force_simt):
+    # 65 536 bf16 patterns = 128 KiB = exactly 4 regions of 32 KiB
+    nb = 8
+    src_h = make_layout(O.LW, nb, nl=2, no=2, page=16, inner=1024, dt=2, block_dim=O.BLOCK_IS_SECOND_DIM)
+    dst_h = make_layout(O.LW, nb, nl=2, no=2, page=16, inner=1024, dt=1, block_dim=O.BLOCK_IS_SECOND_DIM, allow_fp8=True)
+    randomize(src_h, 8)
+    allbits = np.arange(65536, dtype=np.uint16)
+    src_h.region_bytes(3, 0, 0).view(np.uint16)[:] = allbits[:16384]
+    src_h.region_bytes(3, 0, 1).view(np.uint16)[:] = allbits[16384:32768]
+    src_h.region_bytes(3, 1, 0).view(np.uint16)[:] = allbits[32768:49152]
+    src_h.region_bytes(3, 1, 1).view(np.uint16)[:] = allbits[49152:]
+    sid, did = [3, 5, 1], [0, 7, 2]
+    src_p, dst_p = DevicePool(src_h), DevicePool(dst_h)
+    opts = K.PagedCopyOpts(force_simt=force_simt)
+    assert run_paged(src_p, [dst_p], [sid], [did], cast=K.CastMode.BF16_TO_FP8E4M3, opts=opts) == 0
+    check_against_oracle(src_h, dst_h, dst_p, sid, did, cast=2)
+
+
+def test_argument_validation():
+    h = make_layout(O.LW, 8, block_dim=O.BLOCK_IS_SECOND_DIM)
+    other = make_layout(O.LW, 8, nl=3, block_dim=O.BLOCK_IS_SECOND_DIM)
+    small = make_layout(O.LW, 8, inner=64, block_dim=O.BLOCK_IS_SECOND_DIM)
+    p, q, r = DevicePool(h), DevicePool(other), DevicePool(small)
+    ids = ids_dev([0, 1])
+    sp = stream_ptr()
+    ok = paged_dst(p, ids, ids)
+    assert K.paged_copy(p.desc, [ok], 0, 0, 2, 0, None, sp) == 0                      # empty -> no-op
+    assert K.paged_copy(p.desc, [ok], 2, 1, 1, 0, None, sp) == 0                      # empty layer range
+    assert K.paged_copy(p.desc, [ok], 2, 0, 3, 0, None, sp) == K.CUDA_ERROR_INVALID_VALUE   # layer range too long
+    assert K.paged_copy(p.desc, [paged_dst(q, ids, ids)], 2, 0, 2, 0, None, sp) == K.CUDA_ERROR_INVALID_VALUE  # cuda.rs:52-58
+    assert K.paged_copy(p.desc, [paged_dst(r, ids, ids)], 2, 0, 2, 0, None, sp) == K.CUDA_ERROR_INVALID_VALUE  # memcpy.rs:143
+    assert K.paged_copy(p.desc, [ok] * 9, 2, 0, 2, 0, None, sp) == K.CUDA_ERROR_INVALID_VALUE
+    assert K.paged_copy(p.desc, [ok], 2, 0, 2, 7, None, sp) == K.CUDA_ERROR_INVALID_VALUE
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    need_ws = K.PagedDst(p.desc, ids.data_ptr(), ids.data_ptr(), flag.data_ptr(), 0)
+    assert K.paged_copy(p.desc, [need_ws], 2, 0, 2, 0, None, sp) == K.CUDA_ERROR_INVALID_VALUE  # flag without workspace
+
+
+def test_completion_and_layer_flags():
+    nb, n, nl = 32, 16, 6
+    mk = lambda: make_layout(O.LW, nb, nl=nl, no=2, page=16, inner=256, dt=2, block_dim=O.BLOCK_IS_SECOND_DIM)
+    src_h, d0_h, d1_h = mk(), mk(), mk()
+    randomize(src_h, 31)
+    sid, did0, did1 = np.arange(n), np.arange(n) + 8, np.arange(n)[::-1].copy() + 3
+    src_p, d0_p, d1_p = DevicePool(src_h), DevicePool(d0_h), DevicePool(d1_h)
+    flags = torch.zeros(2, dtype=torch.int32, device="cuda")
+    layer_flags = torch.zeros(2, nl, dtype=torch.int32, device="cuda")
+    ws = torch.zeros(nl + 1, dtype=torch.int32, device="cuda")
+    ready = torch.zeros(nl, dtype=torch.int32, device="cuda")
+    s_ids = ids_dev(sid)
+    a, b = ids_dev(did0), ids_dev(did1)
+    dsts = [K.PagedDst(d0_p.desc, s_ids.data_ptr(), a.data_ptr(), flags[0:].data_ptr(), layer_flags[0].data_ptr()),
+            K.PagedDst(d1_p.desc, s_ids.data_ptr(), b.data_ptr(), flags[1:].data_ptr(), layer_flags[1].data_ptr())]
+    side = torch.cuda.Stream()
+    for epoch in (1, 2):      # run twice: the kernel must leave the workspace zeroed
+        opts = K.PagedCopyOpts(epoch=epoch, layer_ready_flags=ready.data_ptr(), sync_workspace=ws.data_ptr(), max_ctas=8)
+        torch.cuda.synchronize()
+        assert K.paged_copy(src_p.desc, dsts, n, 0, nl, 0, opts, stream_ptr(side)) == 0
+        # the transfer kernel is now spinning on ready[0]; release the layers one at a time from another stream
+        for l in range(nl):
+            assert K.set_flags(ready.data_ptr(), l, 1, epoch, stream_ptr()) == 0
+        assert K.wait_flag(flags[1:].data_ptr(), epoch, stream_ptr()) == 0     # device-side wait on the done flag
+        torch.cuda.synchronize()
+        assert flags.tolist() == [epoch, epoch]
+        assert layer_flags.tolist() == [[epoch] * nl, [epoch] * nl]
+        assert ws.tolist() == [0] * (nl + 1)
+    check_against_oracle(src_h, d0_h, d0_p, sid, did0)
+    check_against_oracle(src_h, d1_h, d1_p, sid, did1)
+
+
+def test_full_size_config2_roundtrip_property():
+    # BASELINE configs[1] at full size on one device: 256 blocks x 32 layers x K/V x 32 KiB = 512 MiB.
+    # Size-independent property: gather->scatter with a permutation, then the inverse permutation,
+    # restores the source pool exactly; plus a BLAKE3 spot check of one block against the oracle formula.
+    nb_pool, n, nl = 320, 256, 32
+    region = 16 * 1024 * 2
+    def pool():
+        bufs = [torch.empty(2 * nb_pool * region, dtype=torch.uint8, device="cuda") for _ in range(nl)]
+        base = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+        return bufs, base, K.PagedLayout(base.data_ptr(), region, region * nb_pool, region, nl, 2, nb_pool)
+    a_bufs, a_base, a = pool()
+    b_bufs, b_base, b = pool()
+    c_bufs, c_base, c = pool()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in a_bufs:
+        t.copy_(torch.randint(0, 256, t.shape, dtype=torch.uint8, device="cuda", generator=g))
+    for t in b_bufs + c_bufs:
+        t.zero_()
+    sid = np.random.default_rng(0).permutation(nb_pool)[:n]
+    did = np.random.default_rng(1).permutation(nb_pool)[:n]
+    s, d = ids_dev(sid), ids_dev(did)
+    sp = stream_ptr()
+    assert K.paged_copy(a, [K.PagedDst(b, s.data_ptr(), d.data_ptr(), 0, 0)], n, 0, nl, 0, None, sp) == 0
+    assert K.paged_copy(b, [K.PagedDst(c, d.data_ptr(), s.data_ptr(), 0, 0)], n, 0, nl, 0, None, sp) == 0
+    torch.cuda.synchronize()
+    moved = torch.zeros(nb_pool, dtype=torch.bool, device="cuda")
+    moved[torch.from_numpy(sid).cuda()] = True
+    for l in range(nl):
+        av = a_bufs[l].view(2, nb_pool, region)
+        cv = c_bufs[l].view(2, nb_pool, region)
+        assert torch.equal(cv[:, moved], av[:, moved])
+        assert not cv[:, ~moved].any()
+    import blake3
+    h1, h2 = blake3.blake3(), blake3.blake3()
+    for l in range(nl):
+        for o in range(2):
+            h1.update(a_bufs[l].view(2, nb_pool, region)[o, int(sid[5])].cpu().numpy().tobytes())
+            h2.update(b_bufs[l].view(2, nb_pool, region)[o, int(did[5])].cpu().numpy().tobytes())
+    assert h1.hexdigest() == h2.hexdigest()
