@@ -1,0 +1,778 @@
+// libkvbm_physical.so -- host half of the KV transfer path (C++ restatement of Dynamo's kvbm-physical crate
+// for this path; see include/kvbm_physical.h for the reference lines every entry point replaces).
+#include <cuda_runtime_api.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include <sched.h>
+#include <unistd.h>
+
+#include "layout.hpp"
+
+namespace kvbm_host {
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg)
+{
+  g_last_error = msg;
+  return code;
+}
+static int fail_cuda(cudaError_t e, const char* what)
+{
+  g_last_error = std::string(what) + " failed: " + cudaGetErrorName(e) + " (" + std::to_string(static_cast<int>(e)) + ")";
+  (void)cudaGetLastError();
+  return KVBM_ERR_CUDA;
+}
+#define CU(call)                                   \
+  do {                                             \
+    cudaError_t e__ = (call);                      \
+    if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// validation.rs
+// ---------------------------------------------------------------------------------------------------
+static int validate_block_transfer(const size_t* src_ids, size_t n_src, const size_t* dst_ids, size_t n_dst,
+                                   size_t src_blocks, size_t dst_blocks, bool same_layout)
+{
+  if (n_src != n_dst)  // validation.rs:177-183
+    return fail(KVBM_ERR_LENGTH_MISMATCH, "Block ID lists have mismatched lengths: src=" + std::to_string(n_src) +
+                                              ", dst=" + std::to_string(n_dst) + ", bounce=None");
+  std::unordered_set<size_t> seen;
+  seen.reserve(n_dst * 2);
+  for (size_t i = 0; i < n_dst; ++i)  // validate_dst_unique, validation.rs:55-70
+    if (!seen.insert(dst_ids[i]).second)
+      return fail(KVBM_ERR_DUPLICATE_DST, "Destination block IDs are not unique: duplicates = [" + std::to_string(dst_ids[i]) + "]");
+  if (same_layout) {  // validate_disjoint_same_layout, validation.rs:112-136
+    for (size_t i = 0; i < n_src; ++i)
+      if (seen.count(src_ids[i]))
+        return fail(KVBM_ERR_OVERLAP, "Source and destination blocks overlap (same layout): overlapping = [" + std::to_string(src_ids[i]) + "]");
+  }
+  for (size_t i = 0; i < n_src; ++i) {  // validate_block_ids_in_range, validation.rs:139-158
+    if (src_ids[i] >= src_blocks)
+      return fail(KVBM_ERR_RANGE, "Block ID " + std::to_string(src_ids[i]) + " out of range for source (max=" + std::to_string(src_blocks) + ")");
+    if (dst_ids[i] >= dst_blocks)
+      return fail(KVBM_ERR_RANGE, "Block ID " + std::to_string(dst_ids[i]) + " out of range for destination (max=" + std::to_string(dst_blocks) + ")");
+  }
+  return KVBM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// strategy.rs:138-210 (local-to-local rows).  Device index is ignored exactly like strategy.rs:168.
+// ---------------------------------------------------------------------------------------------------
+static int select_direct_strategy(int src, int dst, const kvbm_transfer_capabilities* caps, kvbm_transfer_plan* out)
+{
+  auto direct = [&](int s) {
+    *out = kvbm_transfer_plan{0, s, 0, KVBM_STRATEGY_INVALID};
+    return KVBM_OK;
+  };
+  auto two_hop = [&](int first, int second) {
+    *out = kvbm_transfer_plan{1, first, KVBM_STORAGE_PINNED, second};
+    return KVBM_OK;
+  };
+  const bool gds = caps && caps->allow_gds;
+  const bool host_s = src == KVBM_STORAGE_SYSTEM || src == KVBM_STORAGE_PINNED;
+  const bool host_d = dst == KVBM_STORAGE_SYSTEM || dst == KVBM_STORAGE_PINNED;
+  if (src < 0 || src > KVBM_STORAGE_DISK || dst < 0 || dst > KVBM_STORAGE_DISK) return fail(KVBM_ERR, "unknown StorageKind");
+  if (host_s && host_d) return direct(KVBM_STRATEGY_MEMCPY);
+  if (src == KVBM_STORAGE_SYSTEM && dst == KVBM_STORAGE_DEVICE) return fail(KVBM_ERR_UNSUPPORTED, "System to Device transfers are not supported");
+  if (src == KVBM_STORAGE_PINNED && dst == KVBM_STORAGE_DEVICE) return direct(KVBM_STRATEGY_CUDA_ASYNC_H2D);
+  if (src == KVBM_STORAGE_DEVICE && dst == KVBM_STORAGE_SYSTEM) return fail(KVBM_ERR_UNSUPPORTED, "Device to System transfers are not supported");
+  if (src == KVBM_STORAGE_DEVICE && dst == KVBM_STORAGE_PINNED) return direct(KVBM_STRATEGY_CUDA_ASYNC_D2H);
+  if (src == KVBM_STORAGE_DEVICE && dst == KVBM_STORAGE_DEVICE) return direct(KVBM_STRATEGY_CUDA_ASYNC_D2D);
+  if (host_s && dst == KVBM_STORAGE_DISK) return direct(KVBM_STRATEGY_NIXL_WRITE);
+  if (src == KVBM_STORAGE_DISK && host_d) return direct(KVBM_STRATEGY_NIXL_READ_FLIPPED);
+  if (src == KVBM_STORAGE_DISK && dst == KVBM_STORAGE_DISK) return two_hop(KVBM_STRATEGY_NIXL_READ_FLIPPED, KVBM_STRATEGY_NIXL_WRITE);
+  if (src == KVBM_STORAGE_DEVICE && dst == KVBM_STORAGE_DISK)
+    return gds ? direct(KVBM_STRATEGY_NIXL_WRITE) : two_hop(KVBM_STRATEGY_CUDA_ASYNC_D2H, KVBM_STRATEGY_NIXL_WRITE);
+  if (src == KVBM_STORAGE_DISK && dst == KVBM_STORAGE_DEVICE)
+    return gds ? direct(KVBM_STRATEGY_NIXL_READ) : two_hop(KVBM_STRATEGY_NIXL_READ_FLIPPED, KVBM_STRATEGY_CUDA_ASYNC_H2D);
+  return fail(KVBM_ERR, "unreachable strategy");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TransferManager
+// ---------------------------------------------------------------------------------------------------
+constexpr int kSlots = 64;     // in-flight transfers before the host has to wait for the oldest
+constexpr int kStreams = 4;    // context.rs:286-292: 4 h2d + 4 d2h streams, round-robin
+
+struct Slot {
+  int32_t* pinned_ids = nullptr;  // staging for the narrowed block tables (H2D source)
+  int32_t* dev_ids = nullptr;
+  size_t cap = 0;                 // capacity in int32 entries
+  uint32_t* host_flag = nullptr;  // mapped pinned word the kernel's last warp writes
+  uint32_t* dev_ws = nullptr;     // sync workspace (zeroed, kernel leaves it zeroed)
+  size_t ws_cap = 0;
+  cudaEvent_t ev = nullptr;
+  uint64_t seq = 0;               // owner
+  bool in_flight = false;
+};
+
+#pragma pack(push, 1)
+struct BlobHeader {
+  char magic[8];
+  uint32_t version;
+  uint32_t fully_contiguous;
+  uint32_t block_dim;
+  uint32_t storage;
+  int32_t device_id;
+  uint32_t n_allocs;
+  uint64_t worker_id;
+  uint64_t pid;
+  uint64_t cfg[9];
+};
+struct BlobAlloc {
+  uint64_t addr;
+  uint64_t size;
+  uint64_t offset_in_ipc;   // addr - base of the cudaMalloc allocation the IPC handle names
+  uint32_t has_ipc;
+  unsigned char ipc[64];
+};
+#pragma pack(pop)
+constexpr uint32_t kBlobVersion = 1;
+static const char kMagic[8] = {'K', 'V', 'B', 'M', 'L', 'A', 'Y', '1'};
+
+}  // namespace kvbm_host
+
+using namespace kvbm_host;
+
+struct kvbm_transfer_manager {
+  int device = -1;       // < 0: host-only
+  uint64_t worker_id = 0;
+  std::mutex mu;
+  std::unordered_map<uint64_t, std::unique_ptr<Layout>> layouts;
+  uint16_t next_layout_id = 1;
+  cudaStream_t h2d[kStreams] = {};
+  cudaStream_t d2h[kStreams] = {};
+  std::atomic<uint32_t> rr_h2d{0}, rr_d2h{0};
+  Slot slots[kSlots];
+  uint64_t next_seq = 1;
+  std::atomic<uint64_t> bytes_moved{0}, h2d_bytes{0};
+
+  Layout* find(kvbm_layout_handle h)
+  {
+    auto it = layouts.find(h);
+    return it == layouts.end() ? nullptr : it->second.get();
+  }
+};
+
+namespace kvbm_host {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool active = false;
+  explicit DeviceGuard(int dev)
+  {
+    if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+      active = cudaSetDevice(dev) == cudaSuccess;
+    }
+  }
+  ~DeviceGuard()
+  {
+    if (active) cudaSetDevice(prev);
+  }
+};
+
+static int upload_layer_base(kvbm_transfer_manager* m, Layout* L)
+{
+  if (m->device < 0) return KVBM_OK;
+  DeviceGuard g(m->device);
+  CU(cudaMalloc(reinterpret_cast<void**>(&L->dev_layer_base), L->layer_base.size() * sizeof(uint64_t)));
+  CU(cudaMemcpy(L->dev_layer_base, L->layer_base.data(), L->layer_base.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  return KVBM_OK;
+}
+
+static kvbm_layout_handle add_layout(kvbm_transfer_manager* m, Layout&& L)
+{
+  std::lock_guard<std::mutex> lk(m->mu);
+  const uint16_t id = m->next_layout_id++;
+  const kvbm_layout_handle h = (m->worker_id << 16) | id;
+  m->layouts[h] = std::make_unique<Layout>(std::move(L));
+  return h;
+}
+
+static kvbm_paged_layout descriptor(const Layout& L)
+{
+  kvbm_paged_layout d{};
+  d.layer_base = L.dev_layer_base;
+  d.block_stride = L.block_stride;
+  d.outer_stride = L.outer_stride;
+  d.region_bytes = static_cast<uint32_t>(L.region);
+  d.num_layers = static_cast<uint32_t>(L.cfg.num_layers);
+  d.outer_dim = static_cast<uint32_t>(L.cfg.outer_dim);
+  d.num_blocks = static_cast<uint32_t>(L.cfg.num_blocks);
+  return d;
+}
+
+// memcpy.rs:98-165
+static int host_memcpy_transfer(const Layout& S, const Layout& D, const size_t* sid, const size_t* did, size_t n,
+                                bool has_range, size_t lb, size_t le)
+{
+  const bool full = !has_range || (lb == 0 && le == S.cfg.num_layers);
+  std::string why;
+  if (full && S.fully_contiguous && D.fully_contiguous) {  // can_use_whole_block_transfer, transfer/mod.rs:150-173
+    const size_t bytes = bytes_per_block(S.cfg);
+    for (size_t i = 0; i < n; ++i) {
+      uintptr_t s, d;
+      int rc;
+      if ((rc = S.memory_region(sid[i], 0, 0, &s, nullptr, &why))) return fail(rc, why);
+      if ((rc = D.memory_region(did[i], 0, 0, &d, nullptr, &why))) return fail(rc, why);
+      std::memcpy(reinterpret_cast<void*>(d), reinterpret_cast<const void*>(s), bytes);
+    }
+    return KVBM_OK;
+  }
+  for (size_t i = 0; i < n; ++i)
+    for (size_t l = lb; l < le; ++l)
+      for (size_t o = 0; o < S.cfg.outer_dim; ++o) {
+        uintptr_t s, d;
+        size_t ss, ds;
+        int rc;
+        if ((rc = S.memory_region(sid[i], l, o, &s, &ss, &why))) return fail(rc, why);
+        if ((rc = D.memory_region(did[i], l, o, &d, &ds, &why))) return fail(rc, why);
+        if (ss != ds)
+          return fail(KVBM_ERR_INCOMPATIBLE, "Memory region size mismatch at block=(" + std::to_string(sid[i]) + "," + std::to_string(did[i]) +
+                                                 "), layer=" + std::to_string(l) + ", outer=" + std::to_string(o) + ": src=" + std::to_string(ss) +
+                                                 ", dst=" + std::to_string(ds));
+        std::memcpy(reinterpret_cast<void*>(d), reinterpret_cast<const void*>(s), ss);
+      }
+  return KVBM_OK;
+}
+
+// Acquire a slot whose previous transfer has completed (waits for the oldest if all are busy).
+static int acquire_slot(kvbm_transfer_manager* m, size_t ids_needed, size_t ws_needed, Slot** out, uint64_t* seq)
+{
+  const uint64_t s = m->next_seq++;
+  Slot& sl = m->slots[(s - 1) % kSlots];
+  if (sl.in_flight) {
+    CU(cudaEventSynchronize(sl.ev));
+    sl.in_flight = false;
+  }
+  if (!sl.ev) CU(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+  if (!sl.host_flag) {
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&sl.host_flag), 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    *sl.host_flag = 0;
+  }
+  if (sl.cap < ids_needed) {
+    if (sl.pinned_ids) cudaFreeHost(sl.pinned_ids);
+    if (sl.dev_ids) cudaFree(sl.dev_ids);
+    sl.pinned_ids = nullptr;
+    sl.dev_ids = nullptr;
+    size_t cap = 1024;
+    while (cap < ids_needed) cap *= 2;
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&sl.pinned_ids), cap * sizeof(int32_t), cudaHostAllocPortable));
+    CU(cudaMalloc(reinterpret_cast<void**>(&sl.dev_ids), cap * sizeof(int32_t)));
+    sl.cap = cap;
+  }
+  if (sl.ws_cap < ws_needed) {
+    if (sl.dev_ws) cudaFree(sl.dev_ws);
+    size_t cap = 128;
+    while (cap < ws_needed) cap *= 2;
+    CU(cudaMalloc(reinterpret_cast<void**>(&sl.dev_ws), cap * sizeof(uint32_t)));
+    CU(cudaMemset(sl.dev_ws, 0, cap * sizeof(uint32_t)));
+    sl.ws_cap = cap;
+  }
+  sl.seq = s;
+  *out = &sl;
+  *seq = s;
+  return KVBM_OK;
+}
+
+static int check_compat(const Layout& S, const Layout& D, int cast)
+{
+  if (S.cfg.num_layers != D.cfg.num_layers)  // executor/cuda.rs:52-58, memcpy.rs:49-55
+    return fail(KVBM_ERR_INCOMPATIBLE, "Layouts have incompatible layer counts: src=" + std::to_string(S.cfg.num_layers) +
+                                           ", dst=" + std::to_string(D.cfg.num_layers));
+  if (S.cfg.outer_dim != D.cfg.outer_dim)  // cuda.rs:60-66
+    return fail(KVBM_ERR_INCOMPATIBLE, "Layouts have incompatible outer dimensions: src=" + std::to_string(S.cfg.outer_dim) +
+                                           ", dst=" + std::to_string(D.cfg.outer_dim));
+  const size_t num = cast == KVBM_CAST_FP8E4M3_TO_BF16 ? 2 : 1, den = cast == KVBM_CAST_BF16_TO_FP8E4M3 ? 2 : 1;
+  if (S.region * num != D.region * den)
+    return fail(KVBM_ERR_INCOMPATIBLE, "Memory region size mismatch: src=" + std::to_string(S.region) + ", dst=" + std::to_string(D.region));
+  if (cast == KVBM_CAST_FP8E4M3_TO_BF16 && (S.cfg.dtype_width_bytes != 1 || D.cfg.dtype_width_bytes != 2))
+    return fail(KVBM_ERR_INCOMPATIBLE, "fp8->bf16 cast needs dtype widths 1 -> 2");
+  if (cast == KVBM_CAST_BF16_TO_FP8E4M3 && (S.cfg.dtype_width_bytes != 2 || D.cfg.dtype_width_bytes != 1))
+    return fail(KVBM_ERR_INCOMPATIBLE, "bf16->fp8 cast needs dtype widths 2 -> 1");
+  return KVBM_OK;
+}
+
+static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, const kvbm_layout_handle* dst_h,
+                   const size_t* const* src_ids, const size_t* const* dst_ids, size_t n, bool replicate,
+                   const kvbm_transfer_options* opts_in, kvbm_notification* out)
+{
+  kvbm_transfer_options o{};
+  if (opts_in) o = *opts_in;
+  if (out) *out = 0;
+  if (nd < 1 || nd > KVBM_MAX_DESTINATIONS) return fail(KVBM_ERR, "number of destinations must be in 1..=8");
+  std::lock_guard<std::mutex> lk(m->mu);
+  Layout* S = m->find(src_h);
+  if (!S) return fail(KVBM_ERR_HANDLE, "invalid source handle");
+  std::vector<Layout*> D(nd);
+  for (int d = 0; d < nd; ++d) {
+    D[d] = m->find(dst_h[d]);
+    if (!D[d]) return fail(KVBM_ERR_HANDLE, "invalid destination handle");
+    int rc = check_compat(*S, *D[d], o.cast_mode);
+    if (rc) return rc;
+    if (n && (!src_ids || !dst_ids || !src_ids[d] || !dst_ids[d])) return fail(KVBM_ERR, "null block id list");
+    rc = validate_block_transfer(src_ids[d], n, dst_ids[d], n, S->cfg.num_blocks, D[d]->cfg.num_blocks, src_h == dst_h[d]);
+    if (rc) return rc;
+  }
+  size_t lb = 0, le = S->cfg.num_layers;
+  if (o.has_layer_range) {
+    lb = o.layer_begin;
+    le = o.layer_end;
+    if (lb > le || le > S->cfg.num_layers)
+      return fail(KVBM_ERR_RANGE, "Layer range " + std::to_string(lb) + ".." + std::to_string(le) + " exceeds num_layers " + std::to_string(S->cfg.num_layers));
+  }
+  if (n == 0 || lb == le) return KVBM_OK;
+
+  // select_strategy (strategy.rs:78-108): every layout handled here is local or peer-mapped
+  kvbm_transfer_plan plan{};
+  for (int d = 0; d < nd; ++d) {
+    kvbm_transfer_plan p{};
+    int rc = select_direct_strategy(S->storage, D[d]->storage, nullptr, &p);
+    if (rc) return rc;
+    if (d && (p.first != plan.first || p.two_hop != plan.two_hop)) return fail(KVBM_ERR_UNSUPPORTED, "destinations need different strategies");
+    plan = p;
+  }
+  if (plan.two_hop) return fail(KVBM_ERR_UNSUPPORTED, "two-hop (disk) plans are outside this library");
+
+  if (plan.first == KVBM_STRATEGY_MEMCPY) {
+    if (o.cast_mode != KVBM_CAST_NONE) return fail(KVBM_ERR_UNSUPPORTED, "the fused cast exists only on the CUDA strategies");
+    for (int d = 0; d < nd; ++d) {
+      int rc = host_memcpy_transfer(*S, *D[d], src_ids[d], dst_ids[d], n, o.has_layer_range != 0, lb, le);
+      if (rc) return rc;
+      m->bytes_moved += n * (le - lb) * S->cfg.outer_dim * D[d]->region;
+    }
+    return KVBM_OK;  // synchronous: TransferCompleteNotification::completed() (memcpy.rs:91-92)
+  }
+  if (plan.first != KVBM_STRATEGY_CUDA_ASYNC_H2D && plan.first != KVBM_STRATEGY_CUDA_ASYNC_D2H && plan.first != KVBM_STRATEGY_CUDA_ASYNC_D2D)
+    return fail(KVBM_ERR_UNSUPPORTED, "NIXL strategies are outside this library (the NVLink peer path replaces them)");
+  if (m->device < 0) return fail(KVBM_ERR_CUDA, "this TransferManager was created without a CUDA device; CUDA strategies have no CPU fallback");
+
+  DeviceGuard g(m->device);
+  // stream: caller's, or round-robin from the pool (cuda.rs:82-90: D2H pool for D2H, H2D pool otherwise)
+  cudaStream_t stream;
+  if (o.use_caller_stream)
+    stream = o.cuda_stream;
+  else if (plan.first == KVBM_STRATEGY_CUDA_ASYNC_D2H)
+    stream = m->d2h[m->rr_d2h++ % kStreams];
+  else
+    stream = m->h2d[m->rr_h2d++ % kStreams];
+
+  // block tables: narrow to int32 into pinned staging, async upload on the transfer's stream (no host sync;
+  // the reference blocks on pointers_transfered_event.synchronize(), cuda.rs:324)
+  const size_t lists = replicate ? static_cast<size_t>(nd) + 1 : 2 * static_cast<size_t>(nd);
+  Slot* sl;
+  uint64_t seq;
+  int rc = acquire_slot(m, lists * n, S->cfg.num_layers + 1, &sl, &seq);
+  if (rc) return rc;
+  auto narrow = [&](const size_t* ids, int32_t* dstp) { for (size_t i = 0; i < n; ++i) dstp[i] = static_cast<int32_t>(ids[i]); };
+  std::vector<const int32_t*> dev_src(nd), dev_dst(nd);
+  size_t k = 0;
+  if (replicate) {
+    narrow(src_ids[0], sl->pinned_ids);
+    for (int d = 0; d < nd; ++d) dev_src[d] = sl->dev_ids;
+    k = 1;
+  }
+  for (int d = 0; d < nd; ++d) {
+    if (!replicate) {
+      narrow(src_ids[d], sl->pinned_ids + k * n);
+      dev_src[d] = sl->dev_ids + k * n;
+      ++k;
+    }
+    narrow(dst_ids[d], sl->pinned_ids + k * n);
+    dev_dst[d] = sl->dev_ids + k * n;
+    ++k;
+  }
+  CU(cudaMemcpyAsync(sl->dev_ids, sl->pinned_ids, k * n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  m->h2d_bytes += k * n * sizeof(int32_t);
+
+  kvbm_paged_layout sdesc = descriptor(*S);
+  kvbm_paged_dst dd[KVBM_MAX_DESTINATIONS] = {};
+  for (int d = 0; d < nd; ++d) {
+    dd[d].layout = descriptor(*D[d]);
+    dd[d].src_block_ids = dev_src[d];
+    dd[d].dst_block_ids = dev_dst[d];
+    dd[d].done_flag = nullptr;
+    dd[d].layer_done_flags = (d == 0) ? o.layer_done_flags : nullptr;
+  }
+  kvbm_paged_copy_opts ko{};
+  ko.epoch = o.epoch;
+  ko.layer_ready_flags = o.layer_ready_flags;
+  ko.sync_workspace = sl->dev_ws;
+  ko.max_ctas = o.max_ctas;
+  ko.completion_flag = sl->host_flag;
+  ko.completion_value = static_cast<uint32_t>(seq);
+  cudaError_t e = kvbm_kernels_paged_copy_v2(&sdesc, dd, nd, static_cast<int>(n), static_cast<int>(lb), static_cast<int>(le), o.cast_mode, &ko, stream);
+  if (e != cudaSuccess) return fail_cuda(e, "kvbm_kernels_paged_copy_v2");
+  CU(cudaEventRecord(sl->ev, stream));
+  sl->in_flight = true;
+  for (int d = 0; d < nd; ++d) m->bytes_moved += n * (le - lb) * S->cfg.outer_dim * D[d]->region;
+  // caller-provided stream: caller manages sync, completed() is returned (cuda.rs:139-141)
+  if (out) *out = o.use_caller_stream ? 0 : seq;
+  return KVBM_OK;
+}
+
+}  // namespace kvbm_host
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" const char* kvbm_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int kvbm_layout_config_validate(const kvbm_layout_config* cfg)
+{
+  if (!cfg) return fail(KVBM_ERR, "null config");
+  std::string why;
+  int rc = validate_config(*cfg, &why);
+  return rc ? fail(rc, why) : KVBM_OK;
+}
+extern "C" size_t kvbm_layout_required_bytes(const kvbm_layout_config* cfg) { return cfg ? required_bytes(*cfg) : 0; }
+extern "C" size_t kvbm_layout_bytes_per_block(const kvbm_layout_config* cfg) { return cfg ? bytes_per_block(*cfg) : 0; }
+
+extern "C" int kvbm_select_direct_strategy(int src_kind, int dst_kind, const kvbm_transfer_capabilities* caps, kvbm_transfer_plan* out)
+{
+  if (!out) return fail(KVBM_ERR, "null plan");
+  return select_direct_strategy(src_kind, dst_kind, caps, out);
+}
+
+extern "C" int kvbm_validate_block_transfer(const size_t* src_ids, size_t n_src, const size_t* dst_ids, size_t n_dst,
+                                            size_t src_num_blocks, size_t dst_num_blocks, int same_layout)
+{
+  return validate_block_transfer(src_ids, n_src, dst_ids, n_dst, src_num_blocks, dst_num_blocks, same_layout != 0);
+}
+
+extern "C" int kvbm_manager_create(int cuda_device_id, uint64_t worker_id, kvbm_transfer_manager** out)
+{
+  if (!out) return fail(KVBM_ERR, "null out");
+  auto m = std::make_unique<kvbm_transfer_manager>();
+  m->device = cuda_device_id;
+  m->worker_id = worker_id & 0xffffffffffffull;
+  if (cuda_device_id >= 0) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
+    if (cuda_device_id >= count) return fail(KVBM_ERR_CUDA, "CUDA device " + std::to_string(cuda_device_id) + " does not exist");
+    DeviceGuard g(cuda_device_id);
+    for (int i = 0; i < kStreams; ++i) {
+      CU(cudaStreamCreateWithFlags(&m->h2d[i], cudaStreamNonBlocking));
+      CU(cudaStreamCreateWithFlags(&m->d2h[i], cudaStreamNonBlocking));
+    }
+  }
+  *out = m.release();
+  return KVBM_OK;
+}
+
+extern "C" void kvbm_manager_destroy(kvbm_transfer_manager* m)
+{
+  if (!m) return;
+  if (m->device >= 0) {
+    DeviceGuard g(m->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : m->layouts) {
+      if (kv.second->dev_layer_base) cudaFree(kv.second->dev_layer_base);
+      for (void* p : kv.second->ipc_mappings) cudaIpcCloseMemHandle(p);
+    }
+    for (auto& s : m->slots) {
+      if (s.ev) cudaEventDestroy(s.ev);
+      if (s.pinned_ids) cudaFreeHost(s.pinned_ids);
+      if (s.dev_ids) cudaFree(s.dev_ids);
+      if (s.host_flag) cudaFreeHost(s.host_flag);
+      if (s.dev_ws) cudaFree(s.dev_ws);
+    }
+    for (int i = 0; i < kStreams; ++i) {
+      if (m->h2d[i]) cudaStreamDestroy(m->h2d[i]);
+      if (m->d2h[i]) cudaStreamDestroy(m->d2h[i]);
+    }
+  }
+  delete m;
+}
+
+static int finish_register(kvbm_transfer_manager* m, Layout&& L, int storage_kind, int device_id, kvbm_layout_handle* out)
+{
+  if (storage_kind < KVBM_STORAGE_SYSTEM || storage_kind > KVBM_STORAGE_DISK) return fail(KVBM_ERR, "unknown StorageKind");
+  if (L.region >= (1ull << 32)) return fail(KVBM_ERR_CONFIG, "a (block, layer, outer) region must be < 4 GiB");
+  L.storage = storage_kind;
+  L.device_id = device_id;
+  int rc = upload_layer_base(m, &L);
+  if (rc) return rc;
+  *out = add_layout(m, std::move(L));
+  return KVBM_OK;
+}
+
+extern "C" int kvbm_manager_register_fully_contiguous(kvbm_transfer_manager* m, const kvbm_layout_config* cfg, void* base, size_t size,
+                                                      int storage_kind, int device_id, kvbm_layout_handle* out)
+{
+  if (!m || !cfg || !out) return fail(KVBM_ERR, "null argument");
+  Layout L;
+  std::string why;
+  int rc = make_fully_contiguous(*cfg, reinterpret_cast<uintptr_t>(base), size, &L, &why);
+  if (rc) return fail(rc, why);
+  return finish_register(m, std::move(L), storage_kind, device_id, out);
+}
+
+extern "C" int kvbm_manager_register_layer_separate(kvbm_transfer_manager* m, const kvbm_layout_config* cfg, void* const* layer_bases,
+                                                    const size_t* layer_sizes, int block_dim, int storage_kind, int device_id,
+                                                    kvbm_layout_handle* out)
+{
+  if (!m || !cfg || !out || !layer_bases || !layer_sizes) return fail(KVBM_ERR, "null argument");
+  std::vector<uintptr_t> bases(cfg->num_layers);
+  for (size_t i = 0; i < cfg->num_layers; ++i) bases[i] = reinterpret_cast<uintptr_t>(layer_bases[i]);
+  Layout L;
+  std::string why;
+  int rc = make_layer_separate(*cfg, bases.data(), layer_sizes, cfg->num_layers, block_dim, &L, &why);
+  if (rc) return fail(rc, why);
+  return finish_register(m, std::move(L), storage_kind, device_id, out);
+}
+
+extern "C" int kvbm_manager_unregister(kvbm_transfer_manager* m, kvbm_layout_handle h)
+{
+  if (!m) return fail(KVBM_ERR, "null manager");
+  std::lock_guard<std::mutex> lk(m->mu);
+  auto it = m->layouts.find(h);
+  if (it == m->layouts.end()) return fail(KVBM_ERR_HANDLE, "invalid handle");
+  if (m->device >= 0) {
+    DeviceGuard g(m->device);
+    for (auto& s : m->slots)
+      if (s.in_flight) {
+        cudaEventSynchronize(s.ev);
+        s.in_flight = false;
+      }
+    if (it->second->dev_layer_base) cudaFree(it->second->dev_layer_base);
+    for (void* p : it->second->ipc_mappings) cudaIpcCloseMemHandle(p);
+  }
+  m->layouts.erase(it);
+  return KVBM_OK;
+}
+
+extern "C" int kvbm_layout_memory_region(kvbm_transfer_manager* m, kvbm_layout_handle h, size_t block, size_t layer, size_t outer,
+                                         uintptr_t* addr, size_t* size)
+{
+  if (!m || !addr) return fail(KVBM_ERR, "null argument");
+  std::lock_guard<std::mutex> lk(m->mu);
+  Layout* L = m->find(h);
+  if (!L) return fail(KVBM_ERR_HANDLE, "invalid handle");
+  std::string why;
+  int rc = L->memory_region(block, layer, outer, addr, size, &why);
+  return rc ? fail(rc, why) : KVBM_OK;
+}
+
+extern "C" int kvbm_layout_is_fully_contiguous(kvbm_transfer_manager* m, kvbm_layout_handle h)
+{
+  if (!m) return -1;
+  std::lock_guard<std::mutex> lk(m->mu);
+  Layout* L = m->find(h);
+  return L ? (L->fully_contiguous ? 1 : 0) : -1;
+}
+
+extern "C" int kvbm_manager_enable_peer_access(kvbm_transfer_manager* m, int peer_device)
+{
+  if (!m || m->device < 0) return fail(KVBM_ERR_CUDA, "manager has no CUDA device");
+  if (peer_device == m->device) return KVBM_OK;
+  DeviceGuard g(m->device);
+  int can = 0;
+  CU(cudaDeviceCanAccessPeer(&can, m->device, peer_device));
+  if (!can) return fail(KVBM_ERR_UNSUPPORTED, "device " + std::to_string(m->device) + " cannot map device " + std::to_string(peer_device) + " (no NVLink/P2P path)");
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    (void)cudaGetLastError();
+    return KVBM_OK;
+  }
+  if (e != cudaSuccess) return fail_cuda(e, "cudaDeviceEnablePeerAccess");
+  return KVBM_OK;
+}
+
+// base address + size of the cudaMalloc allocation containing p (driver entry point, no -lcuda needed)
+static int allocation_range(uintptr_t p, uintptr_t* base, size_t* size)
+{
+  typedef int (*fn_t)(unsigned long long*, size_t*, unsigned long long);
+  static fn_t fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q);
+    if (e != cudaSuccess || !f) return fail_cuda(e, "cudaGetDriverEntryPoint(cuMemGetAddressRange)");
+    fn = reinterpret_cast<fn_t>(f);
+  }
+  unsigned long long b = 0;
+  size_t s = 0;
+  int r = fn(&b, &s, static_cast<unsigned long long>(p));
+  if (r != 0) return fail(KVBM_ERR_CUDA, "cuMemGetAddressRange failed: " + std::to_string(r));
+  *base = static_cast<uintptr_t>(b);
+  *size = s;
+  return KVBM_OK;
+}
+
+extern "C" int kvbm_manager_export_metadata(kvbm_transfer_manager* m, kvbm_layout_handle h, void* buf, size_t cap, size_t* len)
+{
+  if (!m || !len) return fail(KVBM_ERR, "null argument");
+  std::lock_guard<std::mutex> lk(m->mu);
+  Layout* L = m->find(h);
+  if (!L) return fail(KVBM_ERR_HANDLE, "invalid handle");
+  const size_t need = sizeof(BlobHeader) + L->allocs.size() * sizeof(BlobAlloc);
+  *len = need;
+  if (!buf) return KVBM_OK;
+  if (cap < need) return fail(KVBM_ERR, "buffer too small for metadata");
+  BlobHeader hd{};
+  std::memcpy(hd.magic, kMagic, 8);
+  hd.version = kBlobVersion;
+  hd.fully_contiguous = L->fully_contiguous;
+  hd.block_dim = static_cast<uint32_t>(L->block_dim);
+  hd.storage = static_cast<uint32_t>(L->storage);
+  hd.device_id = L->device_id;
+  hd.n_allocs = static_cast<uint32_t>(L->allocs.size());
+  hd.worker_id = m->worker_id;
+  hd.pid = static_cast<uint64_t>(getpid());
+  const kvbm_layout_config& c = L->cfg;
+  const uint64_t cfg[9] = {c.num_blocks, c.num_layers, c.outer_dim, c.page_size, c.inner_dim, c.alignment, c.dtype_width_bytes, c.num_heads,
+                           static_cast<uint64_t>(c.allow_fp8)};
+  std::memcpy(hd.cfg, cfg, sizeof(cfg));
+  auto* p = static_cast<unsigned char*>(buf);
+  std::memcpy(p, &hd, sizeof(hd));
+  p += sizeof(hd);
+  DeviceGuard g(L->storage == KVBM_STORAGE_DEVICE ? L->device_id : -1);
+  for (const Allocation& a : L->allocs) {
+    BlobAlloc ba{};
+    ba.addr = a.addr;
+    ba.size = a.size;
+    if (L->storage == KVBM_STORAGE_DEVICE && !L->remote) {
+      uintptr_t base;
+      size_t sz;
+      int rc = allocation_range(a.addr, &base, &sz);
+      if (rc) return rc;
+      cudaIpcMemHandle_t ih;
+      cudaError_t e = cudaIpcGetMemHandle(&ih, reinterpret_cast<void*>(base));
+      if (e != cudaSuccess) return fail_cuda(e, "cudaIpcGetMemHandle");
+      static_assert(sizeof(ih) == 64, "cudaIpcMemHandle_t is 64 bytes");
+      std::memcpy(ba.ipc, &ih, 64);
+      ba.has_ipc = 1;
+      ba.offset_in_ipc = a.addr - base;
+    }
+    std::memcpy(p, &ba, sizeof(ba));
+    p += sizeof(ba);
+  }
+  return KVBM_OK;
+}
+
+extern "C" int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void* buf, size_t len, kvbm_layout_handle* out)
+{
+  if (!m || !buf || !out) return fail(KVBM_ERR, "null argument");
+  if (len < sizeof(BlobHeader)) return fail(KVBM_ERR, "metadata blob truncated");
+  BlobHeader hd;
+  std::memcpy(&hd, buf, sizeof(hd));
+  if (std::memcmp(hd.magic, kMagic, 8) != 0) return fail(KVBM_ERR, "not a KVBM layout blob");
+  if (hd.version != kBlobVersion)  // layout/serialize.rs version check
+    return fail(KVBM_ERR_VERSION, "Unsupported layout descriptor version " + std::to_string(hd.version) + " (expected " + std::to_string(kBlobVersion) + ")");
+  if (len < sizeof(BlobHeader) + hd.n_allocs * sizeof(BlobAlloc)) return fail(KVBM_ERR, "metadata blob truncated");
+  kvbm_layout_config cfg{};
+  cfg.num_blocks = hd.cfg[0];
+  cfg.num_layers = hd.cfg[1];
+  cfg.outer_dim = hd.cfg[2];
+  cfg.page_size = hd.cfg[3];
+  cfg.inner_dim = hd.cfg[4];
+  cfg.alignment = hd.cfg[5];
+  cfg.dtype_width_bytes = hd.cfg[6];
+  cfg.num_heads = hd.cfg[7];
+  cfg.allow_fp8 = static_cast<int>(hd.cfg[8]);
+  const bool same_process = hd.pid == static_cast<uint64_t>(getpid());
+  std::vector<uintptr_t> bases(hd.n_allocs);
+  std::vector<size_t> sizes(hd.n_allocs);
+  std::vector<void*> mappings;
+  const auto* pa = static_cast<const unsigned char*>(buf) + sizeof(BlobHeader);
+  DeviceGuard g(m->device);
+  for (uint32_t i = 0; i < hd.n_allocs; ++i) {
+    BlobAlloc ba;
+    std::memcpy(&ba, pa + i * sizeof(BlobAlloc), sizeof(ba));
+    sizes[i] = ba.size;
+    if (same_process || !ba.has_ipc) {
+      bases[i] = ba.addr;  // same address space (peer access is enabled with kvbm_manager_enable_peer_access)
+    } else {
+      if (m->device < 0) return fail(KVBM_ERR_CUDA, "importing a device layout needs a CUDA manager");
+      cudaIpcMemHandle_t ih;
+      std::memcpy(&ih, ba.ipc, 64);
+      void* mapped = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&mapped, ih, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        for (void* q : mappings) cudaIpcCloseMemHandle(q);
+        return fail_cuda(e, "cudaIpcOpenMemHandle");
+      }
+      mappings.push_back(mapped);
+      bases[i] = reinterpret_cast<uintptr_t>(mapped) + ba.offset_in_ipc;
+    }
+  }
+  Layout L;
+  std::string why;
+  int rc = hd.fully_contiguous ? make_fully_contiguous(cfg, bases.empty() ? 0 : bases[0], sizes.empty() ? 0 : sizes[0], &L, &why)
+                               : make_layer_separate(cfg, bases.data(), sizes.data(), hd.n_allocs, static_cast<int>(hd.block_dim), &L, &why);
+  if (rc) {
+    for (void* q : mappings) cudaIpcCloseMemHandle(q);
+    return fail(rc, why);
+  }
+  L.remote = !same_process;
+  L.ipc_mappings = std::move(mappings);
+  return finish_register(m, std::move(L), static_cast<int>(hd.storage), hd.device_id, out);
+}
+
+extern "C" int kvbm_manager_execute_transfer(kvbm_transfer_manager* m, kvbm_layout_handle src, const size_t* src_ids, kvbm_layout_handle dst,
+                                             const size_t* dst_ids, size_t n, const kvbm_transfer_options* opts, kvbm_notification* out)
+{
+  if (!m) return fail(KVBM_ERR, "null manager");
+  const size_t* s[1] = {src_ids};
+  const size_t* d[1] = {dst_ids};
+  return execute(m, src, 1, &dst, s, d, n, true, opts, out);
+}
+
+extern "C" int kvbm_manager_execute_fanout(kvbm_transfer_manager* m, kvbm_layout_handle src, int num_dsts, const kvbm_layout_handle* dsts,
+                                           const size_t* const* src_ids, const size_t* const* dst_ids, size_t n, int replicate,
+                                           const kvbm_transfer_options* opts, kvbm_notification* out)
+{
+  if (!m || !dsts) return fail(KVBM_ERR, "null argument");
+  bool rep = replicate != 0;
+  if (!rep && src_ids) {
+    rep = true;
+    for (int d = 1; d < num_dsts; ++d)
+      if (src_ids[d] != src_ids[0]) rep = false;
+  }
+  return execute(m, src, num_dsts, dsts, src_ids, dst_ids, n, rep, opts, out);
+}
+
+extern "C" int kvbm_notification_is_complete(kvbm_transfer_manager* m, kvbm_notification n)
+{
+  if (!m) return -1;
+  if (n == 0) return 1;
+  Slot& sl = m->slots[(n - 1) % kSlots];
+  if (sl.seq != n) return sl.seq > n ? 1 : -1;  // slot recycled by a later transfer => ours completed
+  const uint32_t v = *reinterpret_cast<volatile uint32_t*>(sl.host_flag);
+  return v == static_cast<uint32_t>(n) ? 1 : 0;
+}
+
+extern "C" int kvbm_notification_wait(kvbm_transfer_manager* m, kvbm_notification n, int64_t timeout_us)
+{
+  if (!m) return fail(KVBM_ERR, "null manager");
+  const auto t0 = std::chrono::steady_clock::now();
+  unsigned spins = 0;
+  for (;;) {
+    int c = kvbm_notification_is_complete(m, n);
+    if (c == 1) return KVBM_OK;
+    if (c < 0) return fail(KVBM_ERR_HANDLE, "unknown notification");
+    if ((++spins & 63) == 0) {
+      if (timeout_us >= 0 &&
+          std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() > timeout_us)
+        return fail(KVBM_ERR_TIMEOUT, "transfer did not complete in time");
+      sched_yield();
+    }
+  }
+}
+
+extern "C" uint64_t kvbm_manager_bytes_moved(kvbm_transfer_manager* m) { return m ? m->bytes_moved.load() : 0; }
+extern "C" uint64_t kvbm_manager_h2d_bytes(kvbm_transfer_manager* m) { return m ? m->h2d_bytes.load() : 0; }

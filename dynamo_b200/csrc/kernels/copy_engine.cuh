@@ -84,6 +84,8 @@ struct StreamSync {
   uint32_t* workspace;          // [num_layers + 1] zeroed counters (last = whole transfer)
   uint32_t* done_flag[kMaxDst];
   uint32_t* layer_done[kMaxDst];
+  uint32_t* completion_flag;    // extra whole-transfer flag (host-mapped memory allowed)
+  uint32_t completion_value;
   uint32_t epoch;
   uint32_t total_warps;
   int ndst;
@@ -132,6 +134,7 @@ __device__ __forceinline__ void arrive_transfer(const StreamSync& ss, int lane)
 #pragma unroll
     for (int d = 0; d < kMaxDst; ++d)
       if (d < ss.ndst && ss.done_flag[d] != nullptr) ptx::st_release_sys(ss.done_flag[d], ss.epoch);
+    if (ss.completion_flag != nullptr) ptx::st_release_sys(ss.completion_flag, ss.completion_value);
   }
 }
 

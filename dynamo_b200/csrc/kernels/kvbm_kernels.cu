@@ -244,6 +244,8 @@ struct PagedSyncArgs {
   uint32_t* workspace;
   uint32_t* done_flag[kMaxDst];
   uint32_t* layer_done[kMaxDst];
+  uint32_t* completion_flag;
+  uint32_t completion_value;
   uint32_t epoch;
   int any;
   int num_layers_total;
@@ -256,6 +258,8 @@ __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const Pa
   ss.layer_ready = s.layer_ready;
   ss.workspace = s.workspace;
   ss.epoch = s.epoch;
+  ss.completion_flag = s.completion_flag;
+  ss.completion_value = s.completion_value;
   ss.total_warps = gridDim.x * W;
   ss.ndst = a.ndst;
   ss.num_layers = s.num_layers_total;
@@ -580,12 +584,14 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
     if (D.done_flag || D.layer_done_flags) sync.any = 1;
   }
   if (num_dsts == 1) gen.a.replicate = 1;
-  if (o.layer_ready_flags) sync.any = 1;
+  if (o.layer_ready_flags || o.completion_flag) sync.any = 1;
+  sync.completion_flag = o.completion_flag;
+  sync.completion_value = o.completion_value;
   sync.layer_ready = o.layer_ready_flags;
   sync.workspace = o.sync_workspace;
   sync.epoch = o.epoch;
   sync.num_layers_total = static_cast<int>(src->num_layers);
-  bool needs_ws = false;
+  bool needs_ws = o.completion_flag != nullptr;
   for (int d = 0; d < num_dsts; ++d)
     if (dsts[d].done_flag || dsts[d].layer_done_flags) needs_ws = true;
   if (needs_ws && !o.sync_workspace) return cudaErrorInvalidValue;

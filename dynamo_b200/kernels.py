@@ -94,6 +94,8 @@ class PagedCopyOpts(C.Structure):
         ("stages", C.c_int),
         ("tile_bytes", C.c_int),
         ("force_simt", C.c_int),
+        ("completion_flag", C.c_void_p),
+        ("completion_value", C.c_uint32),
     ]
 
 

@@ -1,0 +1,365 @@
+"""ctypes mirror of the reference's host-side transfer API (lib/kvbm-physical), over libkvbm_physical.so.
+
+Names and argument meaning follow the Rust crate so tests read like the reference's own:
+  LayoutConfig                    lib/kvbm-physical/src/layout/config.rs:14-56
+  StorageKind / BlockDimension    lib/memory/src/lib.rs, layout/config.rs:151-163
+  TransferOptions                 transfer/options.rs:27-81
+  TransferManager.register_layout / export_metadata / import_metadata / execute_transfer
+                                  manager/mod.rs:101,112,130,227
+  select_direct_strategy          transfer/strategy.rs:138-210
+  validate_block_transfer         transfer/validation.rs:168-225
+  TransferCompleteNotification    transfer/context.rs:438-470
+
+All bytes move in native code (CUDA kernels for device storage, the reference's own memcpy strategy for
+host<->host); this module only marshals arguments.  Missing native library => exception, never a fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+from . import _lib, kernels
+
+
+class KvbmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{ErrorCode(code).name if code in ErrorCode._value2member_map_ else code}] {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class ErrorCode(enum.IntEnum):
+    OK = 0
+    ERR = 1
+    CONFIG = 2
+    RANGE = 3
+    LENGTH_MISMATCH = 4
+    DUPLICATE_DST = 5
+    OVERLAP = 6
+    INCOMPATIBLE = 7
+    UNSUPPORTED = 8
+    CUDA = 9
+    HANDLE = 10
+    TIMEOUT = 11
+    VERSION = 12
+
+
+class StorageKind(enum.IntEnum):
+    System = 0
+    Pinned = 1
+    Device = 2
+    Disk = 3
+
+
+class BlockDimension(enum.IntEnum):
+    BlockIsFirstDim = 0
+    BlockIsSecondDim = 1
+
+
+class TransferStrategy(enum.IntEnum):
+    Memcpy = 0
+    CudaAsyncH2D = 1
+    CudaAsyncD2H = 2
+    CudaAsyncD2D = 3
+    NixlRead = 4
+    NixlWrite = 5
+    NixlReadFlipped = 6
+    Invalid = 7
+
+
+class _CConfig(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in ("num_blocks", "num_layers", "outer_dim", "page_size", "inner_dim",
+                                          "alignment", "dtype_width_bytes", "num_heads")] + [("allow_fp8", C.c_int)]
+
+
+class _CPlan(C.Structure):
+    _fields_ = [("two_hop", C.c_int), ("first", C.c_int), ("bounce_location", C.c_int), ("second", C.c_int)]
+
+
+class _CCaps(C.Structure):
+    _fields_ = [("allow_gds", C.c_int), ("allow_gpu_rdma", C.c_int)]
+
+
+class _COptions(C.Structure):
+    _fields_ = [
+        ("has_layer_range", C.c_int),
+        ("layer_begin", C.c_size_t),
+        ("layer_end", C.c_size_t),
+        ("cuda_stream", C.c_void_p),
+        ("use_caller_stream", C.c_int),
+        ("cast_mode", C.c_int),
+        ("max_ctas", C.c_int),
+        ("layer_ready_flags", C.c_void_p),
+        ("layer_done_flags", C.c_void_p),
+        ("epoch", C.c_uint32),
+    ]
+
+
+@dataclass
+class LayoutConfig:
+    num_blocks: int
+    num_layers: int
+    outer_dim: int
+    page_size: int
+    inner_dim: int
+    alignment: int = 1
+    dtype_width_bytes: int = 2
+    num_heads: Optional[int] = None
+    allow_fp8: bool = False
+
+    def _c(self) -> _CConfig:
+        return _CConfig(self.num_blocks, self.num_layers, self.outer_dim, self.page_size, self.inner_dim,
+                        self.alignment, self.dtype_width_bytes, self.num_heads or 0, int(self.allow_fp8))
+
+    def validate(self) -> None:
+        _check(lib().kvbm_layout_config_validate(C.byref(self._c())))
+
+    def required_bytes(self) -> int:
+        return lib().kvbm_layout_required_bytes(C.byref(self._c()))
+
+    def bytes_per_block(self) -> int:
+        return lib().kvbm_layout_bytes_per_block(C.byref(self._c()))
+
+    def region_size(self) -> int:
+        return self.page_size * self.inner_dim * self.dtype_width_bytes
+
+
+@dataclass
+class TransferOptions:
+    layer_range: Optional[range] = None
+    cuda_stream: Optional[int] = None     # raw cudaStream_t; when set the caller manages synchronisation
+    cast_mode: int = 0
+    max_ctas: int = 0
+    layer_ready_flags: int = 0
+    layer_done_flags: int = 0
+    epoch: int = 0
+
+    @staticmethod
+    def from_layer_range(layer_range: Optional[range]) -> "TransferOptions":
+        return TransferOptions(layer_range=layer_range)
+
+    def _c(self) -> _COptions:
+        lr = self.layer_range
+        return _COptions(int(lr is not None), lr.start if lr is not None else 0, lr.stop if lr is not None else 0,
+                         self.cuda_stream or 0, int(self.cuda_stream is not None), int(self.cast_mode), self.max_ctas,
+                         self.layer_ready_flags, self.layer_done_flags, self.epoch)
+
+
+@dataclass
+class TransferPlan:
+    two_hop: bool
+    first: TransferStrategy
+    bounce_location: Optional[StorageKind] = None
+    second: Optional[TransferStrategy] = None
+
+
+_configured = False
+
+EXPORTED_SYMBOLS = [
+    "kvbm_last_error", "kvbm_layout_config_validate", "kvbm_layout_required_bytes", "kvbm_layout_bytes_per_block",
+    "kvbm_select_direct_strategy", "kvbm_validate_block_transfer", "kvbm_manager_create", "kvbm_manager_destroy",
+    "kvbm_manager_register_fully_contiguous", "kvbm_manager_register_layer_separate", "kvbm_manager_unregister",
+    "kvbm_layout_memory_region", "kvbm_layout_is_fully_contiguous", "kvbm_manager_enable_peer_access",
+    "kvbm_manager_export_metadata", "kvbm_manager_import_metadata", "kvbm_manager_execute_transfer",
+    "kvbm_manager_execute_fanout", "kvbm_notification_is_complete", "kvbm_notification_wait",
+    "kvbm_manager_bytes_moved", "kvbm_manager_h2d_bytes",
+]
+
+
+def lib() -> C.CDLL:
+    global _configured
+    kernels.lib()  # dependency (resolved through $ORIGIN rpath as well)
+    L = _lib.load(_lib.PHYSICAL_SO)
+    if not _configured:
+        vp, sz, i, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+        P = C.POINTER
+        L.kvbm_last_error.restype = C.c_char_p
+        L.kvbm_layout_config_validate.argtypes = [P(_CConfig)]
+        L.kvbm_layout_required_bytes.argtypes = [P(_CConfig)]
+        L.kvbm_layout_required_bytes.restype = sz
+        L.kvbm_layout_bytes_per_block.argtypes = [P(_CConfig)]
+        L.kvbm_layout_bytes_per_block.restype = sz
+        L.kvbm_select_direct_strategy.argtypes = [i, i, P(_CCaps), P(_CPlan)]
+        L.kvbm_validate_block_transfer.argtypes = [P(sz), sz, P(sz), sz, sz, sz, i]
+        L.kvbm_manager_create.argtypes = [i, u64, P(vp)]
+        L.kvbm_manager_destroy.argtypes = [vp]
+        L.kvbm_manager_destroy.restype = None
+        L.kvbm_manager_register_fully_contiguous.argtypes = [vp, P(_CConfig), vp, sz, i, i, P(u64)]
+        L.kvbm_manager_register_layer_separate.argtypes = [vp, P(_CConfig), P(vp), P(sz), i, i, i, P(u64)]
+        L.kvbm_manager_unregister.argtypes = [vp, u64]
+        L.kvbm_layout_memory_region.argtypes = [vp, u64, sz, sz, sz, P(sz), P(sz)]
+        L.kvbm_layout_is_fully_contiguous.argtypes = [vp, u64]
+        L.kvbm_manager_enable_peer_access.argtypes = [vp, i]
+        L.kvbm_manager_export_metadata.argtypes = [vp, u64, vp, sz, P(sz)]
+        L.kvbm_manager_import_metadata.argtypes = [vp, vp, sz, P(u64)]
+        L.kvbm_manager_execute_transfer.argtypes = [vp, u64, P(sz), u64, P(sz), sz, P(_COptions), P(u64)]
+        L.kvbm_manager_execute_fanout.argtypes = [vp, u64, i, P(u64), P(P(sz)), P(P(sz)), sz, i, P(_COptions), P(u64)]
+        L.kvbm_notification_is_complete.argtypes = [vp, u64]
+        L.kvbm_notification_wait.argtypes = [vp, u64, C.c_int64]
+        L.kvbm_manager_bytes_moved.argtypes = [vp]
+        L.kvbm_manager_bytes_moved.restype = u64
+        L.kvbm_manager_h2d_bytes.argtypes = [vp]
+        L.kvbm_manager_h2d_bytes.restype = u64
+        _configured = True
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise KvbmError(rc, lib().kvbm_last_error().decode(errors="replace"))
+
+
+def _size_array(ids: Sequence[int]):
+    n = len(ids)
+    return (C.c_size_t * max(1, n))(*[int(x) for x in ids]), n
+
+
+def select_direct_strategy(src: StorageKind, dst: StorageKind, allow_gds: bool = False,
+                           allow_gpu_rdma: bool = False) -> TransferPlan:
+    plan = _CPlan()
+    caps = _CCaps(int(allow_gds), int(allow_gpu_rdma))
+    _check(lib().kvbm_select_direct_strategy(int(src), int(dst), C.byref(caps), C.byref(plan)))
+    if plan.two_hop:
+        return TransferPlan(True, TransferStrategy(plan.first), StorageKind(plan.bounce_location),
+                            TransferStrategy(plan.second))
+    return TransferPlan(False, TransferStrategy(plan.first))
+
+
+def validate_block_transfer(src_ids: Sequence[int], dst_ids: Sequence[int], src_num_blocks: int,
+                            dst_num_blocks: int, same_layout: bool = False) -> None:
+    s, ns = _size_array(src_ids)
+    d, nd = _size_array(dst_ids)
+    _check(lib().kvbm_validate_block_transfer(s, ns, d, nd, src_num_blocks, dst_num_blocks, int(same_layout)))
+
+
+class TransferCompleteNotification:
+    def __init__(self, mgr: "TransferManager", token: int):
+        self._mgr, self.token = mgr, token
+
+    def is_complete(self) -> bool:
+        rc = lib().kvbm_notification_is_complete(self._mgr._h, self.token)
+        if rc < 0:
+            raise KvbmError(ErrorCode.HANDLE, "unknown notification")
+        return rc == 1
+
+    def wait(self, timeout_s: Optional[float] = 30.0) -> None:
+        us = -1 if timeout_s is None else int(timeout_s * 1e6)
+        _check(lib().kvbm_notification_wait(self._mgr._h, self.token, us))
+
+
+class TransferManager:
+    """TransferManager over one CUDA device (device < 0: host-only, Memcpy strategy only)."""
+
+    def __init__(self, device: int = 0, worker_id: int = 0):
+        h = C.c_void_p()
+        _check(lib().kvbm_manager_create(device, worker_id, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self) -> None:
+        if self._h:
+            lib().kvbm_manager_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- layouts ------------------------------------------------------------------------------------
+    def register_fully_contiguous(self, config: LayoutConfig, base: int, size: int, storage: StorageKind,
+                                  device_id: int = 0) -> int:
+        out = C.c_uint64()
+        _check(lib().kvbm_manager_register_fully_contiguous(self._h, C.byref(config._c()), base, size, int(storage),
+                                                            device_id, C.byref(out)))
+        return out.value
+
+    def register_layer_separate(self, config: LayoutConfig, layer_bases: Sequence[int], layer_sizes: Sequence[int],
+                                block_dim: BlockDimension, storage: StorageKind, device_id: int = 0) -> int:
+        n = len(layer_bases)
+        if n != config.num_layers or len(layer_sizes) != n:
+            raise KvbmError(ErrorCode.CONFIG, f"Memory region count ({n}) must match num_layers ({config.num_layers})")
+        bases = (C.c_void_p * max(1, n))(*[int(b) for b in layer_bases])
+        sizes = (C.c_size_t * max(1, n))(*[int(s) for s in layer_sizes])
+        out = C.c_uint64()
+        _check(lib().kvbm_manager_register_layer_separate(self._h, C.byref(config._c()), bases, sizes, int(block_dim),
+                                                          int(storage), device_id, C.byref(out)))
+        return out.value
+
+    def unregister(self, handle: int) -> None:
+        _check(lib().kvbm_manager_unregister(self._h, handle))
+
+    def memory_region(self, handle: int, block: int, layer: int, outer: int) -> tuple[int, int]:
+        a, s = C.c_size_t(), C.c_size_t()
+        _check(lib().kvbm_layout_memory_region(self._h, handle, block, layer, outer, C.byref(a), C.byref(s)))
+        return a.value, s.value
+
+    def is_fully_contiguous(self, handle: int) -> bool:
+        rc = lib().kvbm_layout_is_fully_contiguous(self._h, handle)
+        if rc < 0:
+            raise KvbmError(ErrorCode.HANDLE, "invalid handle")
+        return bool(rc)
+
+    def enable_peer_access(self, peer_device: int) -> None:
+        _check(lib().kvbm_manager_enable_peer_access(self._h, peer_device))
+
+    def export_metadata(self, handle: int) -> bytes:
+        n = C.c_size_t()
+        _check(lib().kvbm_manager_export_metadata(self._h, handle, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _check(lib().kvbm_manager_export_metadata(self._h, handle, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def import_metadata(self, blob: bytes) -> int:
+        out = C.c_uint64()
+        buf = C.create_string_buffer(blob, len(blob))
+        _check(lib().kvbm_manager_import_metadata(self._h, buf, len(blob), C.byref(out)))
+        return out.value
+
+    # -- transfers ----------------------------------------------------------------------------------
+    def execute_transfer(self, src: int, src_block_ids: Sequence[int], dst: int, dst_block_ids: Sequence[int],
+                         options: Optional[TransferOptions] = None) -> TransferCompleteNotification:
+        if len(src_block_ids) != len(dst_block_ids):
+            # executor/memcpy.rs:38-44: length mismatch is rejected before anything else
+            raise KvbmError(ErrorCode.LENGTH_MISMATCH,
+                            f"Block ID lists have mismatched lengths: src={len(src_block_ids)}, dst={len(dst_block_ids)}, bounce=None")
+        s, n = _size_array(src_block_ids)
+        d, _ = _size_array(dst_block_ids)
+        tok = C.c_uint64()
+        o = (options or TransferOptions())._c()
+        _check(lib().kvbm_manager_execute_transfer(self._h, src, s, dst, d, n, C.byref(o), C.byref(tok)))
+        return TransferCompleteNotification(self, tok.value)
+
+    def execute_fanout(self, src: int, dsts: Sequence[int], src_block_ids: Sequence[Sequence[int]],
+                       dst_block_ids: Sequence[Sequence[int]], replicate: bool = False,
+                       options: Optional[TransferOptions] = None) -> TransferCompleteNotification:
+        nd = len(dsts)
+        n = len(dst_block_ids[0])
+        if any(len(x) != n for x in dst_block_ids) or any(len(x) != n for x in src_block_ids):
+            raise KvbmError(ErrorCode.LENGTH_MISMATCH, "Block ID lists have mismatched lengths")
+        hs = (C.c_uint64 * nd)(*dsts)
+        s_arrays = [_size_array(x)[0] for x in (src_block_ids if not replicate else [src_block_ids[0]] * nd)]
+        d_arrays = [_size_array(x)[0] for x in dst_block_ids]
+        PP = C.POINTER(C.c_size_t)
+        sp = (PP * nd)(*[C.cast(a, PP) for a in s_arrays])
+        dp = (PP * nd)(*[C.cast(a, PP) for a in d_arrays])
+        tok = C.c_uint64()
+        o = (options or TransferOptions())._c()
+        _check(lib().kvbm_manager_execute_fanout(self._h, src, nd, hs, sp, dp, n, int(replicate), C.byref(o), C.byref(tok)))
+        return TransferCompleteNotification(self, tok.value)
+
+    def broadcast(self, src: int, dsts: Sequence[int], src_block_ids: Sequence[int],
+                  dst_block_ids: Sequence[int], layer_range: Optional[range] = None) -> TransferCompleteNotification:
+        """CollectiveOps::broadcast (lib/kvbm-engine/src/collectives/mod.rs:99-106): same blocks, same destination
+        ids on every rank -- here one replicate launch over peer mappings instead of grouped ncclBcast."""
+        return self.execute_fanout(src, dsts, [src_block_ids] * len(dsts), [dst_block_ids] * len(dsts), replicate=True,
+                                   options=TransferOptions(layer_range=layer_range))
+
+    def bytes_moved(self) -> int:
+        return lib().kvbm_manager_bytes_moved(self._h)
+
+    def h2d_bytes(self) -> int:
+        return lib().kvbm_manager_h2d_bytes(self._h)

@@ -119,12 +119,16 @@ enum {
 typedef struct kvbm_paged_copy_opts {
   uint32_t epoch;                 /* value written to done flags / compared with ready flags (>=) */
   const uint32_t* layer_ready_flags; /* nullable; [num_layers]; layer l is read only after flag >= epoch */
-  uint32_t* sync_workspace;       /* device u32[num_layers + 1], zeroed; required iff any flag is used */
+  uint32_t* sync_workspace;       /* device u32[num_layers + 1], zeroed; required iff any done/completion flag is used */
   int max_ctas;                   /* 0 = one CTA per SM; smaller values leave SMs to the attention kernel */
   int warps_per_cta;              /* 0 = default */
   int stages;                     /* 0 = default */
   int tile_bytes;                 /* 0 = default */
   int force_simt;                 /* 1 = never use the TMA path (diagnostics) */
+  uint32_t* completion_flag;      /* nullable; device-visible (e.g. mapped pinned host) word set to
+                                     completion_value once EVERY destination has landed: lets the host
+                                     observe completion without cudaEventQuery polling */
+  uint32_t completion_value;
 } kvbm_paged_copy_opts;
 
 /* Gather `num_blocks` non-contiguous blocks x layers [layer_begin, layer_end) x outer from `src`,

@@ -1,0 +1,176 @@
+/*
+ * kvbm_physical.h -- C ABI of libkvbm_physical.so: the host half of the KV transfer path.
+ *
+ * It restates, in C++ behind plain-C entry points, what Dynamo's Rust crate lib/kvbm-physical does for
+ * this path (no Rust toolchain exists in the build image; see INTEGRATION.md for the Rust `extern "C"`
+ * block a maintainer would add):
+ *
+ *   LayoutConfig + validation            lib/kvbm-physical/src/layout/config.rs:14-56,165-180
+ *   FullyContiguous / LayerSeparate      layout/fully_contiguous.rs:141-185, layout/layer_separate.rs:155-210
+ *   Layout::memory_region                layout/mod.rs:73-78
+ *   validate_block_transfer              transfer/validation.rs:55-225
+ *   select_strategy / direct strategy    transfer/strategy.rs:78-108,138-210
+ *   TransferOptions                      transfer/options.rs:27-81
+ *   TransferManager::{register_layout, export_metadata, import_metadata, execute_transfer}
+ *                                        manager/mod.rs:101,112,130,227
+ *   TransferCompleteNotification         transfer/context.rs:438-470 (event -> 1 ms poller) -- replaced by an
+ *                                        in-band completion flag the kernel writes to pinned host memory
+ *   layer-wise onboard                   lib/kvbm-engine/src/worker/physical.rs:277-346
+ *   CollectiveOps::broadcast             lib/kvbm-engine/src/collectives/mod.rs:75-106 (ncclBcast per region)
+ *                                        -- replaced by one replicate launch over NVLink peer mappings
+ *
+ * Error style: every call returns KVBM_OK (0) or an error code; kvbm_last_error() gives the thread's last
+ * message (house style of lib/bindings/c/src/lib.rs:74-78: OK=0, ERR!=0).  Nothing aborts or throws.
+ */
+#ifndef KVBM_PHYSICAL_H
+#define KVBM_PHYSICAL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "kvbm_kernels.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  KVBM_OK = 0,
+  KVBM_ERR = 1,                 /* generic */
+  KVBM_ERR_CONFIG = 2,          /* LayoutConfig validation failed / memory too small */
+  KVBM_ERR_RANGE = 3,           /* block / layer / outer id out of range */
+  KVBM_ERR_LENGTH_MISMATCH = 4, /* BlockValidationError::LengthMismatch */
+  KVBM_ERR_DUPLICATE_DST = 5,   /* BlockValidationError::DuplicateDestinationBlocks */
+  KVBM_ERR_OVERLAP = 6,         /* BlockValidationError::OverlappingBlocks */
+  KVBM_ERR_INCOMPATIBLE = 7,    /* layer count / outer dim / region size mismatch */
+  KVBM_ERR_UNSUPPORTED = 8,     /* strategy this library does not implement (NIXL, disk, System<->Device) */
+  KVBM_ERR_CUDA = 9,            /* a CUDA call failed (message carries the cudaError_t) */
+  KVBM_ERR_HANDLE = 10,         /* unknown layout handle / notification */
+  KVBM_ERR_TIMEOUT = 11,
+  KVBM_ERR_VERSION = 12,        /* metadata blob version mismatch (layout/serialize.rs version check) */
+};
+
+/* dynamo_memory::StorageKind (lib/memory/src/lib.rs) */
+enum { KVBM_STORAGE_SYSTEM = 0, KVBM_STORAGE_PINNED = 1, KVBM_STORAGE_DEVICE = 2, KVBM_STORAGE_DISK = 3 };
+/* BlockDimension (layout/config.rs:151-163) */
+enum { KVBM_BLOCK_IS_FIRST_DIM = 0, KVBM_BLOCK_IS_SECOND_DIM = 1 };
+/* TransferStrategy (transfer/strategy.rs:20-58) */
+enum {
+  KVBM_STRATEGY_MEMCPY = 0,
+  KVBM_STRATEGY_CUDA_ASYNC_H2D = 1,
+  KVBM_STRATEGY_CUDA_ASYNC_D2H = 2,
+  KVBM_STRATEGY_CUDA_ASYNC_D2D = 3,
+  KVBM_STRATEGY_NIXL_READ = 4,
+  KVBM_STRATEGY_NIXL_WRITE = 5,
+  KVBM_STRATEGY_NIXL_READ_FLIPPED = 6,
+  KVBM_STRATEGY_INVALID = 7,
+};
+
+typedef struct kvbm_layout_config {
+  size_t num_blocks;
+  size_t num_layers;
+  size_t outer_dim;         /* 1 or 2 */
+  size_t page_size;
+  size_t inner_dim;
+  size_t alignment;         /* power of two; 0 is read as 1 (the builder default) */
+  size_t dtype_width_bytes; /* 2,4,8 as the reference; 1 accepted only with allow_fp8 */
+  size_t num_heads;         /* 0 = None */
+  int allow_fp8;            /* extension: fp8 KV pools (dtype_width_bytes == 1) */
+} kvbm_layout_config;
+
+/* A transfer plan as select_strategy returns it (transfer/strategy.rs:60-76). */
+typedef struct kvbm_transfer_plan {
+  int two_hop;          /* 0 = Direct(first) */
+  int first;            /* KVBM_STRATEGY_* */
+  int bounce_location;  /* KVBM_STORAGE_* (two-hop only) */
+  int second;           /* two-hop only */
+} kvbm_transfer_plan;
+
+typedef struct kvbm_transfer_capabilities {
+  int allow_gds;
+  int allow_gpu_rdma;
+} kvbm_transfer_capabilities;
+
+/* TransferOptions (transfer/options.rs:27-81) + the cast / streaming extensions. */
+typedef struct kvbm_transfer_options {
+  int has_layer_range;
+  size_t layer_begin, layer_end;
+  cudaStream_t cuda_stream;     /* non-NULL: caller manages sync, notification is already complete */
+  int use_caller_stream;        /* set when cuda_stream is meaningful (NULL is the legacy default stream) */
+  int cast_mode;                /* KVBM_CAST_* */
+  int max_ctas;                 /* 0 = whole GPU; else cap so attention keeps its SMs */
+  const uint32_t* layer_ready_flags; /* nullable: device flags released by the producer (attention) per layer */
+  uint32_t* layer_done_flags;        /* nullable: device-visible flags on the destination, set per layer */
+  uint32_t epoch;
+} kvbm_transfer_options;
+
+typedef struct kvbm_transfer_manager kvbm_transfer_manager;
+typedef uint64_t kvbm_layout_handle;   /* (worker_id << 16) | layout_id, cf. manager/handle.rs:16-50 */
+typedef uint64_t kvbm_notification;    /* 0 = already complete */
+
+const char* kvbm_last_error(void);
+
+/* ---- pure host logic (no GPU needed) ---- */
+int kvbm_layout_config_validate(const kvbm_layout_config* cfg);
+size_t kvbm_layout_required_bytes(const kvbm_layout_config* cfg);   /* config.rs:64-71 */
+size_t kvbm_layout_bytes_per_block(const kvbm_layout_config* cfg);  /* config.rs:76-82 */
+/* select_direct_strategy (strategy.rs:138-210).  Device ids are ignored exactly as strategy.rs:168 does. */
+int kvbm_select_direct_strategy(int src_kind, int dst_kind, const kvbm_transfer_capabilities* caps,
+                                kvbm_transfer_plan* out);
+/* validate_block_transfer, debug flavour (validation.rs:168-225). */
+int kvbm_validate_block_transfer(const size_t* src_ids, size_t n_src, const size_t* dst_ids, size_t n_dst,
+                                 size_t src_num_blocks, size_t dst_num_blocks, int same_layout);
+
+/* ---- TransferManager ---- */
+/* cuda_device_id < 0: host-only manager (Memcpy strategy only; every CUDA strategy returns KVBM_ERR_CUDA). */
+int kvbm_manager_create(int cuda_device_id, uint64_t worker_id, kvbm_transfer_manager** out);
+void kvbm_manager_destroy(kvbm_transfer_manager* m);
+
+/* register_layout over caller-owned memory (the engine's KV tensors).  device_id is where the memory lives
+ * (may differ from the manager's device: a peer GPU reachable over NVLink). */
+int kvbm_manager_register_fully_contiguous(kvbm_transfer_manager* m, const kvbm_layout_config* cfg, void* base,
+                                           size_t size, int storage_kind, int device_id,
+                                           kvbm_layout_handle* out);
+int kvbm_manager_register_layer_separate(kvbm_transfer_manager* m, const kvbm_layout_config* cfg,
+                                         void* const* layer_bases, const size_t* layer_sizes, int block_dim,
+                                         int storage_kind, int device_id, kvbm_layout_handle* out);
+int kvbm_manager_unregister(kvbm_transfer_manager* m, kvbm_layout_handle h);
+int kvbm_layout_memory_region(kvbm_transfer_manager* m, kvbm_layout_handle h, size_t block, size_t layer,
+                              size_t outer, uintptr_t* addr, size_t* size);
+int kvbm_layout_is_fully_contiguous(kvbm_transfer_manager* m, kvbm_layout_handle h);
+
+/* Enable NVLink peer mappings from the manager's device to `peer_device` (same process). */
+int kvbm_manager_enable_peer_access(kvbm_transfer_manager* m, int peer_device);
+
+/* export_metadata / import_metadata (manager/mod.rs:112,130): a self-describing blob carrying the layout
+ * geometry and, for Device storage, one CUDA IPC handle per allocation, so another PROCESS on the same
+ * NVSwitch domain can map the pool and have the transfer kernel store into it directly.
+ * kvbm_manager_export_metadata with buf == NULL returns the needed size in *len. */
+int kvbm_manager_export_metadata(kvbm_transfer_manager* m, kvbm_layout_handle h, void* buf, size_t cap,
+                                 size_t* len);
+int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void* buf, size_t len, kvbm_layout_handle* out);
+
+/* execute_transfer (manager/mod.rs:227-303).  ids are host arrays, consumed before return. */
+int kvbm_manager_execute_transfer(kvbm_transfer_manager* m, kvbm_layout_handle src, const size_t* src_ids,
+                                  kvbm_layout_handle dst, const size_t* dst_ids, size_t n,
+                                  const kvbm_transfer_options* opts, kvbm_notification* out);
+
+/* 1 -> N in ONE launch.  src_ids[d] == src_ids[0] for all d (same pointer or same contents flag
+ * `replicate`) reads HBM once and stores N times: the replacement of CollectiveOps::broadcast. */
+int kvbm_manager_execute_fanout(kvbm_transfer_manager* m, kvbm_layout_handle src, int num_dsts,
+                                const kvbm_layout_handle* dsts, const size_t* const* src_ids,
+                                const size_t* const* dst_ids, size_t n, int replicate,
+                                const kvbm_transfer_options* opts, kvbm_notification* out);
+
+/* Completion: the transfer's last warp writes a flag in pinned host memory (no cudaEventQuery polling). */
+int kvbm_notification_is_complete(kvbm_transfer_manager* m, kvbm_notification n);  /* 1 / 0 / <0 error */
+int kvbm_notification_wait(kvbm_transfer_manager* m, kvbm_notification n, int64_t timeout_us);
+
+/* accounting for the bench */
+uint64_t kvbm_manager_bytes_moved(kvbm_transfer_manager* m);
+uint64_t kvbm_manager_h2d_bytes(kvbm_transfer_manager* m);   /* block-table uploads */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVBM_PHYSICAL_H */
