@@ -1,0 +1,96 @@
+"""Prefill -> decode hand-off orchestration across processes (one process per GPU / worker).
+
+This is the control-plane sliver the data path needs and nothing more: who pushes to whom, and the
+exchange of layout metadata (the reference exchanges `SerializedLayout` blobs the same way:
+lib/kvbm-physical/src/manager/metadata.rs:87-159, manager/mod.rs:112-147).  It rides on whatever
+`torch.distributed` backend the job already has (nccl on GPUs, gloo in CPU tests); no data-path collective
+is used -- blocks are independent units pushed one-sided.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+from .physical import TransferCompleteNotification, TransferManager, TransferOptions
+
+
+@dataclass
+class Roles:
+    sources: List[int]
+    destinations: Dict[int, List[int]]    # source rank -> destination ranks
+
+    def is_source(self, rank: int) -> bool:
+        return rank in self.destinations
+
+    def is_destination(self, rank: int) -> bool:
+        return any(rank in d for d in self.destinations.values())
+
+    def source_of(self, rank: int) -> Optional[int]:
+        for s, ds in self.destinations.items():
+            if rank in ds:
+                return s
+        return None
+
+
+def assign_roles(world: int, topology: str = "fanout") -> Roles:
+    """fanout: rank 0 is the prefill GPU, ranks 1..world-1 decode (1 -> N-1; world 1 = loop-back).
+    pairs:  rank r < world/2 pushes to rank r + world/2 (TP-sharded prefill -> decode, BASELINE configs[3])."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    if topology == "fanout":
+        return Roles([0], {0: list(range(1, world)) if world > 1 else [0]})
+    if topology == "pairs":
+        if world == 1:
+            return Roles([0], {0: [0]})
+        if world % 2:
+            raise ValueError("pairs topology needs an even world size")
+        half = world // 2
+        return Roles(list(range(half)), {r: [r + half] for r in range(half)})
+    raise ValueError(f"unknown topology {topology!r}")
+
+
+class HandoffGroup:
+    """Exchanges layout metadata so every source holds a (peer-mapped) handle to its destinations' pools."""
+
+    def __init__(self, mgr: TransferManager, rank: int, world: int, topology: str = "fanout", group=None):
+        self.mgr, self.rank, self.world, self.group = mgr, rank, world, group
+        self.roles = assign_roles(world, topology)
+        self.remote: Dict[int, int] = {}     # destination rank -> handle usable from this process
+
+    def publish(self, local_dst_handle: Optional[int]) -> Dict[int, int]:
+        """Collective: every rank contributes the metadata of the pool it receives into (or None)."""
+        blob = self.mgr.export_metadata(local_dst_handle) if local_dst_handle is not None else b""
+        if self.world == 1:
+            blobs = [blob]
+        else:
+            import torch.distributed as dist
+            blobs = [None] * self.world
+            dist.all_gather_object(blobs, blob, group=self.group)
+        self.blobs = blobs
+        for dst in self.roles.destinations.get(self.rank, []):
+            if dst == self.rank:
+                self.remote[dst] = local_dst_handle
+            else:
+                if not blobs[dst]:
+                    raise RuntimeError(f"rank {dst} published no layout")
+                self.remote[dst] = self.mgr.import_metadata(blobs[dst])
+        return self.remote
+
+    def push(self, src_handle: int, src_block_ids: Sequence[Sequence[int]], dst_block_ids: Sequence[Sequence[int]],
+             replicate: bool = False, options: Optional[TransferOptions] = None) -> TransferCompleteNotification:
+        """Source side: one launch to all of this rank's destinations (list i <-> i-th destination rank)."""
+        dsts = [self.remote[d] for d in self.roles.destinations[self.rank]]
+        if len(dsts) == 1 and not replicate:
+            return self.mgr.execute_transfer(src_handle, src_block_ids[0], dsts[0], dst_block_ids[0], options)
+        return self.mgr.execute_fanout(src_handle, dsts, src_block_ids, dst_block_ids, replicate, options)
+
+
+def max_over_ranks(value: float, device=None, group=None) -> float:
+    """Timing reduction the bench contract asks for (max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
