@@ -72,18 +72,26 @@ def main():
     results.append(dict(name="torch.copy_", ms=med, gbs_rw=2 * bytes_moved / med / 1e6))
     print(results[-1], flush=True)
 
-    for warps, stages, tile, ctas in [(4, 3, 16384, 0), (4, 3, 8192, 0), (2, 3, 32768, 0), (2, 6, 16384, 0),
-                                      (8, 3, 8192, 0), (8, 2, 8192, 0), (4, 5, 8192, 0), (4, 2, 16384, 0),
-                                      (1, 6, 32768, 0), (1, 12, 16384, 0), (4, 3, 16384, 74), (4, 3, 16384, 32),
-                                      (4, 3, 16384, 16), (4, 3, 4096, 0), (16, 3, 4096, 0), (8, 6, 4096, 0)]:
-        opts = K.PagedCopyOpts(warps_per_cta=warps, stages=stages, tile_bytes=tile, max_ctas=ctas)
+    cfgs = [  # (warps, stages, pending stores, tile, ctas, cache_hint)
+        (4, 3, 1, 16384, 0, 0), (2, 3, 1, 32768, 0, 0),               # round-0 shapes (one store in flight)
+        (4, 6, 3, 8192, 0, 0), (4, 6, 2, 8192, 0, 0), (4, 6, 4, 8192, 0, 0),
+        (2, 6, 3, 16384, 0, 0), (2, 6, 2, 16384, 0, 0), (2, 6, 4, 16384, 0, 0),
+        (4, 3, 2, 16384, 0, 0), (4, 4, 2, 8192, 0, 0), (8, 3, 2, 8192, 0, 0), (8, 6, 3, 4096, 0, 0),
+        (4, 12, 6, 4096, 0, 0), (1, 6, 3, 32768, 0, 0), (1, 12, 6, 16384, 0, 0), (2, 12, 6, 8192, 0, 0),
+        (3, 4, 2, 16384, 0, 0), (6, 4, 2, 8192, 0, 0),
+        (4, 6, 3, 8192, 0, 1), (4, 6, 3, 8192, 0, 2), (4, 6, 3, 8192, 0, 3),
+        (4, 6, 3, 8192, 74, 0), (4, 6, 3, 8192, 32, 0), (4, 6, 3, 8192, 16, 0), (2, 6, 3, 16384, 16, 0),
+    ]
+    for warps, stages, pend, tile, ctas, hint in cfgs:
+        opts = K.PagedCopyOpts(warps_per_cta=warps, stages=stages, tile_bytes=tile, max_ctas=ctas, stores_in_flight=pend,
+                               cache_hint=hint)
         rc = K.paged_copy(src, [d], n, 0, nl, 0, opts, sp)
         if rc != 0:
             print("rc", rc, warps, stages, tile)
             continue
         med, best = timed(lambda: K.paged_copy(src, [d], n, 0, nl, 0, opts, sp), flush=flush)
-        results.append(dict(name="paged_tma", warps=warps, stages=stages, tile=tile, ctas=ctas, ms=med, ms_min=best,
-                            gbs_rw=2 * bytes_moved / med / 1e6))
+        results.append(dict(name="paged_tma", warps=warps, stages=stages, pending=pend, tile=tile, ctas=ctas, hint=hint,
+                            ms=med, ms_min=best, gbs_rw=2 * bytes_moved / med / 1e6))
         print(results[-1], flush=True)
     opts = K.PagedCopyOpts(force_simt=1)
     med, best = timed(lambda: K.paged_copy(src, [d], n, 0, nl, 0, opts, sp), flush=flush)

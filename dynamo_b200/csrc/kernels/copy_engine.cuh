@@ -147,10 +147,13 @@ __device__ __forceinline__ void arrive_transfer(const StreamSync& ss, int lane)
 template <class Gen>
 __device__ __forceinline__ void warp_copy_ring(const Gen& gen, uint32_t first, uint32_t stride,
                                                uint32_t total, uint8_t* slots, uint64_t* bars,
-                                               int S, uint32_t tile, bool allow_tma,
-                                               const StreamSync& ss)
+                                               int S, int P, uint32_t tile, bool allow_tma,
+                                               int cache_hint, const StreamSync& ss)
 {
+  // S slots = A loads in flight ahead of the item being stored + P stores still draining their slot.
   const int lane = threadIdx.x & 31;
+  const uint32_t A = static_cast<uint32_t>(S - P);
+  const uint64_t policy = cache_hint ? ptx::policy_evict_first() : 0;
   const uint32_t n_my = total > first ? (total - first + stride - 1) / stride : 0;
   const uint32_t slot0 = ptx::smem_addr(slots);
   const uint32_t bar0 = ptx::smem_addr(bars);
@@ -169,11 +172,14 @@ __device__ __forceinline__ void warp_copy_ring(const Gen& gen, uint32_t first, u
     if (allow_tma && piece_tma_ok(p) && lane == 0) {
       const int s = q % S;
       ptx::mbar_arrive_expect_tx(bar0 + 8 * s, p.bytes);
-      ptx::bulk_g2s(slot0 + s * tile, p.src, p.bytes, bar0 + 8 * s);
+      if (cache_hint & 1)
+        ptx::bulk_g2s_hint(slot0 + s * tile, p.src, p.bytes, bar0 + 8 * s, policy);
+      else
+        ptx::bulk_g2s(slot0 + s * tile, p.src, p.bytes, bar0 + 8 * s);
     }
   };
 
-  const uint32_t depth = static_cast<uint32_t>(S - 1) < n_my ? static_cast<uint32_t>(S - 1) : n_my;
+  const uint32_t depth = A < n_my ? A : n_my;
   for (uint32_t q = 0; q < depth; ++q) issue_load(q);
 
   for (uint32_t q = 0; q < n_my; ++q) {
@@ -196,17 +202,22 @@ __device__ __forceinline__ void warp_copy_ring(const Gen& gen, uint32_t first, u
         ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);
 #pragma unroll
         for (int d = 0; d < kMaxDst; ++d)
-          if (d < p.ndst) ptx::bulk_s2g(p.dst[d], slot0 + s * tile, p.bytes);
+          if (d < p.ndst) {
+            if (cache_hint & 2)
+              ptx::bulk_s2g_hint(p.dst[d], slot0 + s * tile, p.bytes, policy);
+            else
+              ptx::bulk_s2g(p.dst[d], slot0 + s * tile, p.bytes);
+          }
       }
       phase ^= 1u << s;
     } else {
       for (int d = 0; d < p.ndst; ++d) warp_copy_simt(p.dst[d], p.src, p.bytes, lane);
     }
     if (lane == 0) {
-      ptx::bulk_commit();       // always one group per item (possibly empty) so the count below holds
-      ptx::bulk_wait_read<1>(); // store q-1 has left its slot -> slot (q-1)%S == (q+S-1)%S is free
+      ptx::bulk_commit();        // always one group per item (possibly empty) so the count below holds
+      ptx::bulk_wait_read_n(P);  // stores q-P+1..q may still drain; store q-P has left slot (q-P)%S == (q+A)%S
     }
-    if (q + S - 1 < n_my) issue_load(q + S - 1);
+    if (q + A < n_my) issue_load(q + A);
   }
 
   if (lane == 0) {

@@ -49,33 +49,39 @@ static cudaError_t device_info(DeviceInfo* out)
 struct RingCfg {
   int warps;        // W
   int stages;       // S (input slots per warp)
+  int pending;      // P (stores allowed to keep draining their slot); loads ahead A = S - P
   uint32_t tile;    // source bytes per slot
   uint32_t smem;    // dynamic shared memory bytes
   uint32_t out_tile;  // cast only
 };
 
 constexpr uint32_t kBarBytesPerWarp = kMaxStages * 8;
+// defaults tuned on B200 (profiles/r01_sweep_*.json)
+constexpr int kDefaultWarps = 4;
+constexpr int kDefaultStages = 6;
+constexpr uint32_t kDefaultTile = 8192;
 
 static uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 
 // cast: 0 none, 1 up (out = 2x), 2 down (out = x/2)
 static RingCfg make_ring(const DeviceInfo& di, uint32_t unit_bytes, int warps, int stages, int tile,
-                         int cast)
+                         int cast, int pending = 0)
 {
   RingCfg c{};
-  c.warps = warps > 0 ? std::min(warps, 16) : 4;
-  // default tile: the whole unit when it is small, else 16 KiB pieces
-  uint32_t t = tile > 0 ? static_cast<uint32_t>(tile) : std::min<uint32_t>(std::max<uint32_t>(unit_bytes, 16), 16384);
+  c.warps = warps > 0 ? std::min(warps, 16) : kDefaultWarps;
+  // default tile: the whole unit when it is small, else kDefaultTile pieces
+  uint32_t t = tile > 0 ? static_cast<uint32_t>(tile) : std::min<uint32_t>(std::max<uint32_t>(unit_bytes, 16), kDefaultTile);
   t = round_up(t, 32);
   const uint32_t budget = static_cast<uint32_t>(di.max_smem_optin) - 1024;
   for (;;) {
     const uint32_t out = cast == 1 ? 2 * t : (cast == 2 ? t / 2 : 0);
     const uint32_t fixed = c.warps * (kBarBytesPerWarp + 2 * out);
-    int s = stages > 0 ? stages : 3;
+    int s = stages > 0 ? stages : kDefaultStages;
     s = std::min(s, kMaxStages);
     while (s > 2 && fixed + c.warps * s * t > budget) --s;
     if (fixed + c.warps * s * t <= budget) {
       c.stages = s;
+      c.pending = pending > 0 ? std::min(pending, s - 1) : std::max(1, s / 2);
       c.tile = t;
       c.out_tile = out;
       c.smem = fixed + c.warps * s * t;
@@ -87,6 +93,7 @@ static RingCfg make_ring(const DeviceInfo& di, uint32_t unit_bytes, int warps, i
       c.warps /= 2;
     else {
       c.stages = 2;
+      c.pending = 1;
       c.tile = t;
       c.out_tile = out;
       c.smem = fixed + 2 * t;
@@ -146,7 +153,7 @@ struct PairGen {
 };
 
 __global__ void __launch_bounds__(512, 1)
-kvbm_pair_copy_kernel(PairGen gen, uint32_t total, int S, uint32_t tile, int allow_tma)
+kvbm_pair_copy_kernel(PairGen gen, uint32_t total, int S, int P, uint32_t tile, int allow_tma)
 {
   extern __shared__ __align__(128) uint8_t smem[];
   const int W = blockDim.x >> 5;
@@ -157,7 +164,7 @@ kvbm_pair_copy_kernel(PairGen gen, uint32_t total, int S, uint32_t tile, int all
   // interleave warps of different CTAs over neighbouring items: item i -> CTA (i % grid), warp (i / grid) % W
   const uint32_t first = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   (void)warp_global;
-  warp_copy_ring(gen, first, gridDim.x * W, total, v.in, v.bars, S, tile, allow_tma != 0, ss);
+  warp_copy_ring(gen, first, gridDim.x * W, total, v.in, v.bars, S, P, tile, allow_tma != 0, 0, ss);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -276,7 +283,7 @@ __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const Pa
 template <int CAST>
 __global__ void __launch_bounds__(512, 1)
 kvbm_paged_copy_kernel(const __grid_constant__ PagedGen gen, const __grid_constant__ PagedSyncArgs sync,
-                       uint32_t total, int S, uint32_t out_tile, int allow_tma)
+                       uint32_t total, int S, int P, uint32_t out_tile, int allow_tma, int cache_hint)
 {
   extern __shared__ __align__(128) uint8_t smem[];
   const int W = blockDim.x >> 5;
@@ -287,7 +294,7 @@ kvbm_paged_copy_kernel(const __grid_constant__ PagedGen gen, const __grid_consta
   const uint32_t first = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   const uint32_t stride = gridDim.x * W;
   if (CAST == KVBM_CAST_NONE)
-    warp_copy_ring(gen, first, stride, total, v.in, v.bars, S, tile, allow_tma != 0, ss);
+    warp_copy_ring(gen, first, stride, total, v.in, v.bars, S, P, tile, allow_tma != 0, cache_hint, ss);
   else if (CAST == KVBM_CAST_FP8E4M3_TO_BF16)
     warp_cast_ring<true>(gen, first, stride, total, v.in, v.out, v.bars, S, tile, allow_tma != 0, ss);
   else
@@ -456,7 +463,7 @@ kvbm_kernels_launch_vectorized_copy(void** src_ptrs, void** dst_ptrs, size_t cop
   const int grid = static_cast<int>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(di.sm_count)));
   if ((e = set_smem(kvbm_pair_copy_kernel, rc.smem)) != cudaSuccess) return e;
   kvbm_pair_copy_kernel<<<grid, rc.warps * 32, rc.smem, stream>>>(gen, static_cast<uint32_t>(total), rc.stages,
-                                                                 rc.tile, 1);
+                                                                 rc.pending, rc.tile, 1);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();  // :570
 }
@@ -599,7 +606,7 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   DeviceInfo di;
   cudaError_t e = device_info(&di);
   if (e != cudaSuccess) return e;
-  RingCfg rc = make_ring(di, src->region_bytes, o.warps_per_cta, o.stages, o.tile_bytes, cast_mode);
+  RingCfg rc = make_ring(di, src->region_bytes, o.warps_per_cta, o.stages, o.tile_bytes, cast_mode, o.stores_in_flight);
 
   gen.a.n_blocks = static_cast<uint32_t>(num_blocks);
   gen.a.layer_begin = static_cast<uint32_t>(layer_begin);
@@ -622,7 +629,8 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t err = set_smem(kern, rc.smem);
     if (err != cudaSuccess) return err;
-    kern<<<grid, rc.warps * 32, rc.smem, stream>>>(gen, sync, total32, rc.stages, rc.out_tile, allow_tma);
+    kern<<<grid, rc.warps * 32, rc.smem, stream>>>(gen, sync, total32, rc.stages, rc.pending, rc.out_tile, allow_tma,
+                                                   o.cache_hint);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
   };

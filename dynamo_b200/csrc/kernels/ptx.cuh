@@ -76,6 +76,12 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint
                "r"(src_smem), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void bulk_s2g_hint(void* dst_gmem, uint32_t src_smem, uint32_t bytes, uint64_t policy)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+               "r"(src_smem), "r"(bytes), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit()
 {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -84,6 +90,28 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read()
 {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// runtime-selected "at most n groups still reading their smem source" (immediate operand in PTX)
+__device__ __forceinline__ void bulk_wait_read_n(int n)
+{
+  switch (n) {
+    case 0: bulk_wait_read<0>(); break;
+    case 1: bulk_wait_read<1>(); break;
+    case 2: bulk_wait_read<2>(); break;
+    case 3: bulk_wait_read<3>(); break;
+    case 4: bulk_wait_read<4>(); break;
+    case 5: bulk_wait_read<5>(); break;
+    case 6: bulk_wait_read<6>(); break;
+    case 7: bulk_wait_read<7>(); break;
+    case 8: bulk_wait_read<8>(); break;
+    case 9: bulk_wait_read<9>(); break;
+    case 10: bulk_wait_read<10>(); break;
+    case 11: bulk_wait_read<11>(); break;
+    case 12: bulk_wait_read<12>(); break;
+    case 13: bulk_wait_read<13>(); break;
+    case 14: bulk_wait_read<14>(); break;
+    default: bulk_wait_read<15>(); break;
+  }
 }
 template <int N>
 __device__ __forceinline__ void bulk_wait()

@@ -96,6 +96,8 @@ class PagedCopyOpts(C.Structure):
         ("force_simt", C.c_int),
         ("completion_flag", C.c_void_p),
         ("completion_value", C.c_uint32),
+        ("stores_in_flight", C.c_int),
+        ("cache_hint", C.c_int),
     ]
 
 

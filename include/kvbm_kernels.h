@@ -129,6 +129,9 @@ typedef struct kvbm_paged_copy_opts {
                                      completion_value once EVERY destination has landed: lets the host
                                      observe completion without cudaEventQuery polling */
   uint32_t completion_value;
+  int stores_in_flight;           /* 0 = default (stages/2): slots that may still be draining to the destination;
+                                     stages - stores_in_flight loads are kept in flight ahead */
+  int cache_hint;                 /* bit0: L2 evict_first on source reads, bit1: on destination writes */
 } kvbm_paged_copy_opts;
 
 /* Gather `num_blocks` non-contiguous blocks x layers [layer_begin, layer_end) x outer from `src`,
