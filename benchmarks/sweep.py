@@ -72,25 +72,26 @@ def main():
     results.append(dict(name="torch.copy_", ms=med, gbs_rw=2 * bytes_moved / med / 1e6))
     print(results[-1], flush=True)
 
-    cfgs = [  # (warps, stages, pending stores, tile, ctas, cache_hint)
-        (4, 3, 1, 16384, 0, 0), (2, 3, 1, 32768, 0, 0),               # round-0 shapes (one store in flight)
-        (4, 6, 3, 8192, 0, 0), (4, 6, 2, 8192, 0, 0), (4, 6, 4, 8192, 0, 0),
-        (2, 6, 3, 16384, 0, 0), (2, 6, 2, 16384, 0, 0), (2, 6, 4, 16384, 0, 0),
-        (4, 3, 2, 16384, 0, 0), (4, 4, 2, 8192, 0, 0), (8, 3, 2, 8192, 0, 0), (8, 6, 3, 4096, 0, 0),
-        (4, 12, 6, 4096, 0, 0), (1, 6, 3, 32768, 0, 0), (1, 12, 6, 16384, 0, 0), (2, 12, 6, 8192, 0, 0),
-        (3, 4, 2, 16384, 0, 0), (6, 4, 2, 8192, 0, 0),
-        (4, 6, 3, 8192, 0, 1), (4, 6, 3, 8192, 0, 2), (4, 6, 3, 8192, 0, 3),
-        (4, 6, 3, 8192, 74, 0), (4, 6, 3, 8192, 32, 0), (4, 6, 3, 8192, 16, 0), (2, 6, 3, 16384, 16, 0),
+    cfgs = [  # (warps, stages, pending stores, tile, ctas, cache_hint, variant)
+        (4, 3, 1, 16384, 0, 0, 0), (2, 3, 1, 32768, 0, 0, 0), (8, 3, 1, 8192, 0, 0, 0), (4, 6, 3, 8192, 0, 0, 0),
+        (6, 2, 1, 16384, 0, 0, 0), (3, 2, 1, 32768, 0, 0, 0), (12, 2, 1, 8192, 0, 0, 0), (16, 3, 1, 4096, 0, 0, 0),
+        # TMA load + SIMT store from smem (slot is free as soon as the warp has stored it)
+        (4, 3, 1, 16384, 0, 0, 1), (8, 3, 1, 8192, 0, 0, 1), (8, 6, 1, 4096, 0, 0, 1), (16, 3, 1, 4096, 0, 0, 1),
+        (16, 6, 1, 2048, 0, 0, 1), (12, 4, 1, 4096, 0, 0, 1), (8, 2, 1, 8192, 0, 0, 1), (16, 2, 1, 4096, 0, 0, 1),
+        # diagnostics: loads only / stores only (half the traffic; GB/s printed as if both directions moved)
+        (4, 3, 1, 16384, 0, 0, 2), (4, 6, 1, 8192, 0, 0, 2), (8, 3, 1, 8192, 0, 0, 2), (2, 3, 1, 32768, 0, 0, 2),
+        (4, 3, 1, 16384, 0, 0, 3), (4, 3, 2, 16384, 0, 0, 3), (4, 6, 3, 8192, 0, 0, 3), (4, 6, 5, 8192, 0, 0, 3), (8, 3, 2, 8192, 0, 0, 3),
+        (4, 3, 1, 16384, 74, 0, 0), (4, 3, 1, 16384, 32, 0, 0), (4, 3, 1, 16384, 16, 0, 0), (8, 3, 1, 8192, 16, 0, 1),
     ]
-    for warps, stages, pend, tile, ctas, hint in cfgs:
+    for warps, stages, pend, tile, ctas, hint, variant in cfgs:
         opts = K.PagedCopyOpts(warps_per_cta=warps, stages=stages, tile_bytes=tile, max_ctas=ctas, stores_in_flight=pend,
-                               cache_hint=hint)
+                               cache_hint=hint, variant=variant)
         rc = K.paged_copy(src, [d], n, 0, nl, 0, opts, sp)
         if rc != 0:
             print("rc", rc, warps, stages, tile)
             continue
         med, best = timed(lambda: K.paged_copy(src, [d], n, 0, nl, 0, opts, sp), flush=flush)
-        results.append(dict(name="paged_tma", warps=warps, stages=stages, pending=pend, tile=tile, ctas=ctas, hint=hint,
+        results.append(dict(name="paged_tma", warps=warps, stages=stages, pending=pend, tile=tile, ctas=ctas, hint=hint, variant=variant,
                             ms=med, ms_min=best, gbs_rw=2 * bytes_moved / med / 1e6))
         print(results[-1], flush=True)
     opts = K.PagedCopyOpts(force_simt=1)

@@ -91,27 +91,44 @@ struct StreamSync {
   int ndst;
   int num_layers;  // counters per layer live at workspace[l]; whole-transfer counter at [num_layers]
   int layer_begin, layer_end;
-  bool any;        // false -> every hook below is skipped
+  bool gate;         // layer_ready present: reads of a layer wait for its flag
+  bool want_layers;  // some destination wants per-layer done flags
+  bool want_done;    // some whole-transfer flag is wanted
+};
+
+// Ring geometry / behaviour of one launch (uniform across the grid).
+struct RingParams {
+  int S;              // input slots per warp
+  int P;              // byte-exact ring: stores allowed to keep draining (loads ahead A = S - P)
+  uint32_t tile_in;   // source bytes per slot
+  uint32_t tile_out;  // cast rings: bytes per output slot (2 of them)
+  bool allow_tma;
+  int cache_hint;     // bit0 evict_first loads, bit1 evict_first stores
+  int variant;        // 0 = TMA load + TMA store; 1 = TMA load + SIMT store from smem;
+                      // 2 = loads only (diagnostic), 3 = stores only (diagnostic)
 };
 
 __device__ __forceinline__ void wait_layer_ready(const StreamSync& ss, int layer, int lane)
 {
-  if (ss.layer_ready == nullptr) return;
   if (lane == 0) {
     while (ptx::ld_acquire_sys(ss.layer_ready + layer) < ss.epoch) __nanosleep(64);
   }
   __syncwarp();
 }
 
+// non-blocking probe, warp-uniform result
+__device__ __forceinline__ bool layer_is_ready(const StreamSync& ss, int layer, int lane)
+{
+  uint32_t v = 0;
+  if (lane == 0) v = ptx::ld_acquire_sys(ss.layer_ready + layer);
+  v = __shfl_sync(0xffffffffu, v, 0);
+  return v >= ss.epoch;
+}
+
 // This warp has *completed* (stores landed) everything it owns in layers [from, to).
 __device__ __forceinline__ void arrive_layers(const StreamSync& ss, int from, int to, int lane)
 {
-  if (lane != 0 || ss.workspace == nullptr) return;
-  bool want_layers = false;
-#pragma unroll
-  for (int d = 0; d < kMaxDst; ++d)
-    if (d < ss.ndst && ss.layer_done[d] != nullptr) want_layers = true;
-  if (!want_layers) return;
+  if (lane != 0 || !ss.want_layers) return;
   for (int l = from; l < to; ++l) {
     uint32_t old = ptx::atom_add_acq_rel_gpu(ss.workspace + l, 1u);
     if (old == ss.total_warps - 1) {
@@ -126,7 +143,7 @@ __device__ __forceinline__ void arrive_layers(const StreamSync& ss, int from, in
 
 __device__ __forceinline__ void arrive_transfer(const StreamSync& ss, int lane)
 {
-  if (lane != 0 || ss.workspace == nullptr) return;
+  if (lane != 0 || !ss.want_done) return;
   uint32_t old = ptx::atom_add_acq_rel_gpu(ss.workspace + ss.num_layers, 1u);
   if (old == ss.total_warps - 1) {
     ss.workspace[ss.num_layers] = 0;
@@ -138,103 +155,171 @@ __device__ __forceinline__ void arrive_transfer(const StreamSync& ss, int lane)
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Byte-exact ring.  Gen::get(item, Piece&) must be warp-uniform.
-//   first/stride/total : this warp's arithmetic progression of item indices
-//   slots              : S * tile bytes of shared memory private to this warp (16 B aligned)
-//   bars               : S mbarriers private to this warp (already initialised, count 1)
-// ------------------------------------------------------------------------------------------
-template <class Gen>
-__device__ __forceinline__ void warp_copy_ring(const Gen& gen, uint32_t first, uint32_t stride,
-                                               uint32_t total, uint8_t* slots, uint64_t* bars,
-                                               int S, int P, uint32_t tile, bool allow_tma,
-                                               int cache_hint, const StreamSync& ss)
+// every store this warp issued so far has landed (and is ordered before a following flag write)
+__device__ __forceinline__ void drain_stores(int lane)
 {
-  // S slots = A loads in flight ahead of the item being stored + P stores still draining their slot.
-  const int lane = threadIdx.x & 31;
-  const uint32_t A = static_cast<uint32_t>(S - P);
-  const uint64_t policy = cache_hint ? ptx::policy_evict_first() : 0;
-  const uint32_t n_my = total > first ? (total - first + stride - 1) / stride : 0;
-  const uint32_t slot0 = ptx::smem_addr(slots);
-  const uint32_t bar0 = ptx::smem_addr(bars);
-  uint32_t phase = 0;  // bit s = parity the next wait on slot s expects
-
-  int ready_layer = ss.layer_begin - 1;  // highest layer whose ready flag we have observed
-  int open_layer = ss.layer_begin;       // lowest layer this warp has not yet arrived for
-
-  auto issue_load = [&](uint32_t q) {
-    Piece p;
-    gen.get(first + q * stride, p);
-    if (ss.any && p.layer > ready_layer) {
-      wait_layer_ready(ss, p.layer, lane);
-      ready_layer = p.layer;
-    }
-    if (allow_tma && piece_tma_ok(p) && lane == 0) {
-      const int s = q % S;
-      ptx::mbar_arrive_expect_tx(bar0 + 8 * s, p.bytes);
-      if (cache_hint & 1)
-        ptx::bulk_g2s_hint(slot0 + s * tile, p.src, p.bytes, bar0 + 8 * s, policy);
-      else
-        ptx::bulk_g2s(slot0 + s * tile, p.src, p.bytes, bar0 + 8 * s);
-    }
-  };
-
-  const uint32_t depth = A < n_my ? A : n_my;
-  for (uint32_t q = 0; q < depth; ++q) issue_load(q);
-
-  for (uint32_t q = 0; q < n_my; ++q) {
-    Piece p;
-    gen.get(first + q * stride, p);
-    if (ss.any && p.layer > open_layer) {
-      // everything this warp owns below p.layer has been issued: drain, then publish those layers
-      if (lane == 0) {
-        ptx::bulk_wait<0>();
-        ptx::fence_proxy_async_global();
-        __threadfence_system();
-      }
-      __syncwarp();
-      arrive_layers(ss, open_layer, p.layer, lane);
-      open_layer = p.layer;
-    }
-    const int s = q % S;
-    if (allow_tma && piece_tma_ok(p)) {
-      if (lane == 0) {
-        ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);
-#pragma unroll
-        for (int d = 0; d < kMaxDst; ++d)
-          if (d < p.ndst) {
-            if (cache_hint & 2)
-              ptx::bulk_s2g_hint(p.dst[d], slot0 + s * tile, p.bytes, policy);
-            else
-              ptx::bulk_s2g(p.dst[d], slot0 + s * tile, p.bytes);
-          }
-      }
-      phase ^= 1u << s;
-    } else {
-      for (int d = 0; d < p.ndst; ++d) warp_copy_simt(p.dst[d], p.src, p.bytes, lane);
-    }
-    if (lane == 0) {
-      ptx::bulk_commit();        // always one group per item (possibly empty) so the count below holds
-      ptx::bulk_wait_read_n(P);  // stores q-P+1..q may still drain; store q-P has left slot (q-P)%S == (q+A)%S
-    }
-    if (q + A < n_my) issue_load(q + A);
-  }
-
   if (lane == 0) {
     ptx::bulk_wait<0>();
     ptx::fence_proxy_async_global();
-    __threadfence_system();
   }
+  __threadfence_system();  // SIMT stores of any lane
   __syncwarp();
-  if (ss.any) {
-    arrive_layers(ss, open_layer, ss.layer_end, lane);
-    arrive_transfer(ss, lane);
+}
+
+// smem -> global by the whole warp (variant 1): 16 B per lane, 4 independent stores in flight
+__device__ __forceinline__ void warp_store_from_smem(uint8_t* dst, uint32_t src_smem, uint32_t bytes, int lane)
+{
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint32_t n = bytes >> 4;
+  for (uint32_t i = lane; i < n; i += 32) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src_smem + i * 16));
+    ptx::st_stream_v4(d + i, v);
   }
 }
 
+template <bool UP>
+__device__ __forceinline__ void convert_smem(uint32_t in_smem, uint32_t out_smem, uint32_t src_bytes, int lane);
+template <bool UP>
+__device__ __forceinline__ void warp_cast_simt(uint8_t* dst, const uint8_t* src, uint32_t src_bytes, int lane);
+
 // ------------------------------------------------------------------------------------------
-// Casting ring.  UP: fp8 e4m3 -> bf16 (dst bytes = 2 x src bytes); !UP: bf16 -> fp8 (dst = src/2).
-//   in slots : S * tile_in ; out slots : 2 * tile_out (double buffered).
+// The ring.  CAST: 0 byte-exact, 1 fp8->bf16, 2 bf16->fp8.  Gen::get(item, Piece&) is warp-uniform.
+//   first/stride/total : this warp's arithmetic progression of item indices
+//   in_slots           : S * tile_in bytes private to this warp;  out_slots: 2 * tile_out (cast only)
+//   bars               : S mbarriers private to this warp (initialised, count 1)
+// Loads are issued ahead without ever blocking on a layer's ready flag: when the item to be stored next
+// is itself gated, the warp first drains and publishes the layers it has finished (so a consumer that
+// releases layer l+1 only after seeing layer l done cannot deadlock), then blocks.
+// ------------------------------------------------------------------------------------------
+template <int CAST, class Gen>
+__device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32_t stride, uint32_t total,
+                                          uint8_t* in_slots, uint8_t* out_slots, uint64_t* bars,
+                                          const RingParams& rp, const StreamSync& ss)
+{
+  const int lane = threadIdx.x & 31;
+  const int S = rp.S;
+  const bool sync_slot = CAST != 0 || rp.variant == 1 || rp.variant == 2;  // input slot is released synchronously
+  const uint32_t ahead = sync_slot ? static_cast<uint32_t>(S) : static_cast<uint32_t>(S - rp.P);
+  const uint32_t n_my = total > first ? (total - first + stride - 1) / stride : 0;
+  const uint32_t in0 = ptx::smem_addr(in_slots);
+  const uint32_t out0 = ptx::smem_addr(out_slots);
+  const uint32_t bar0 = ptx::smem_addr(bars);
+  const uint64_t policy = rp.cache_hint ? ptx::policy_evict_first() : 0;
+  uint32_t phase = 0;       // bit s = parity the next wait on slot s expects
+  uint32_t next_load = 0;   // items [0, next_load) have had their load issued (or need none)
+  int ready_layer = ss.gate ? ss.layer_begin - 1 : 0x7fffffff;
+  int open_layer = ss.layer_begin;  // lowest layer this warp has not yet arrived for
+
+  auto eligible = [&](const Piece& p) {
+    bool ok = rp.allow_tma && piece_tma_ok(p);
+    if (CAST != 0) ok = ok && (p.bytes & 31) == 0;  // both sides whole 16 B vectors
+    return ok;
+  };
+  auto pump = [&](uint32_t limit) {
+    while (next_load < n_my && next_load < limit) {
+      Piece p;
+      gen.get(first + next_load * stride, p);
+      if (p.layer > ready_layer) {
+        if (!layer_is_ready(ss, p.layer, lane)) break;
+        ready_layer = p.layer;
+      }
+      if (rp.variant != 3 && eligible(p) && lane == 0) {
+        const int s = next_load % S;
+        ptx::mbar_arrive_expect_tx(bar0 + 8 * s, p.bytes);
+        if (rp.cache_hint & 1)
+          ptx::bulk_g2s_hint(in0 + s * rp.tile_in, p.src, p.bytes, bar0 + 8 * s, policy);
+        else
+          ptx::bulk_g2s(in0 + s * rp.tile_in, p.src, p.bytes, bar0 + 8 * s);
+      }
+      ++next_load;
+    }
+  };
+  auto publish_upto = [&](int layer) {
+    drain_stores(lane);
+    arrive_layers(ss, open_layer, layer, lane);
+    open_layer = layer;
+  };
+
+  for (uint32_t q = 0; q < n_my; ++q) {
+    pump(q + ahead);
+    Piece p;
+    gen.get(first + q * stride, p);
+    if (next_load <= q) {  // this item's layer has not been released yet: publish what is finished, then block
+      if (ss.want_layers) publish_upto(p.layer);
+      wait_layer_ready(ss, p.layer, lane);
+      ready_layer = p.layer;
+      pump(q + ahead);
+    } else if (ss.want_layers && p.layer > open_layer) {
+      publish_upto(p.layer);
+    }
+    const int s = q % S;
+    const uint32_t slot = in0 + s * rp.tile_in;
+    if (eligible(p)) {
+      if (CAST == 0 && rp.variant == 0) {
+        if (lane == 0) {
+          ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);
+#pragma unroll
+          for (int d = 0; d < kMaxDst; ++d)
+            if (d < p.ndst) {
+              if (rp.cache_hint & 2)
+                ptx::bulk_s2g_hint(p.dst[d], slot, p.bytes, policy);
+              else
+                ptx::bulk_s2g(p.dst[d], slot, p.bytes);
+            }
+        }
+        phase ^= 1u << s;
+      } else if (CAST == 0 && rp.variant == 3) {  // stores only: whatever is in the slot
+        if (lane == 0) {
+#pragma unroll
+          for (int d = 0; d < kMaxDst; ++d)
+            if (d < p.ndst) ptx::bulk_s2g(p.dst[d], slot, p.bytes);
+        }
+      } else if (CAST == 0) {  // variants 1, 2: every lane observes the landed tile
+        ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);
+        phase ^= 1u << s;
+        if (rp.variant == 1) {
+          for (int d = 0; d < p.ndst; ++d) warp_store_from_smem(p.dst[d], slot, p.bytes, lane);
+        }
+        __syncwarp();
+      } else {
+        const uint32_t dst_bytes = CAST == 1 ? p.bytes * 2 : p.bytes / 2;
+        const uint32_t ob = out0 + (q & 1) * rp.tile_out;
+        if (lane == 0) ptx::bulk_wait_read<1>();  // store q-2 (same out buffer) has been read out
+        __syncwarp();
+        ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);  // every lane reads the slot
+        phase ^= 1u << s;
+        convert_smem<CAST == 1>(slot, ob, p.bytes, lane);
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int d = 0; d < kMaxDst; ++d)
+            if (d < p.ndst) ptx::bulk_s2g(p.dst[d], ob, dst_bytes);
+        }
+      }
+    } else {
+      for (int d = 0; d < p.ndst; ++d) {
+        if (CAST == 0)
+          warp_copy_simt(p.dst[d], p.src, p.bytes, lane);
+        else
+          warp_cast_simt<CAST == 1>(p.dst[d], p.src, p.bytes, lane);
+      }
+    }
+    if (lane == 0) {
+      ptx::bulk_commit();  // always one group per item (possibly empty) so the counts hold
+      // byte-exact TMA ring: stores q-P+1..q may still drain; store q-P has left slot (q-P)%S == (q+A)%S
+      if (!sync_slot) ptx::bulk_wait_read_n(rp.P);
+    }
+  }
+
+  drain_stores(lane);
+  arrive_layers(ss, open_layer, ss.layer_end, lane);
+  arrive_transfer(ss, lane);
+}
+
+// ------------------------------------------------------------------------------------------
+// Conversion helpers of the cast rings.
 // ------------------------------------------------------------------------------------------
 template <bool UP>
 __device__ __forceinline__ void convert_smem(uint32_t in_smem, uint32_t out_smem, uint32_t src_bytes,
@@ -293,92 +378,6 @@ __device__ __forceinline__ void warp_cast_simt(uint8_t* dst, const uint8_t* src,
     const uint32_t elems = src_bytes >> 1;
     for (uint32_t i = lane; i < elems; i += 32)
       dst[i] = static_cast<uint8_t>(ptx::bf16x2_to_e4m3x2(s[i]) & 0xff);
-  }
-}
-
-template <bool UP, class Gen>
-__device__ __forceinline__ void warp_cast_ring(const Gen& gen, uint32_t first, uint32_t stride,
-                                               uint32_t total, uint8_t* in_slots, uint8_t* out_slots,
-                                               uint64_t* bars, int S, uint32_t tile_in,
-                                               bool allow_tma, const StreamSync& ss)
-{
-  const int lane = threadIdx.x & 31;
-  const uint32_t tile_out = UP ? tile_in * 2 : tile_in / 2;
-  const uint32_t n_my = total > first ? (total - first + stride - 1) / stride : 0;
-  const uint32_t in0 = ptx::smem_addr(in_slots);
-  const uint32_t out0 = ptx::smem_addr(out_slots);
-  const uint32_t bar0 = ptx::smem_addr(bars);
-  uint32_t phase = 0;
-  int ready_layer = ss.layer_begin - 1;
-  int open_layer = ss.layer_begin;
-
-  auto elig = [&](const Piece& p) {
-    // source bytes must also be a multiple of 32 so that both sides are whole 16 B vectors
-    return allow_tma && piece_tma_ok(p) && (p.bytes & 31) == 0;
-  };
-  auto issue_load = [&](uint32_t q) {
-    Piece p;
-    gen.get(first + q * stride, p);
-    if (ss.any && p.layer > ready_layer) {
-      wait_layer_ready(ss, p.layer, lane);
-      ready_layer = p.layer;
-    }
-    if (elig(p) && lane == 0) {
-      const int s = q % S;
-      ptx::mbar_arrive_expect_tx(bar0 + 8 * s, p.bytes);
-      ptx::bulk_g2s(in0 + s * tile_in, p.src, p.bytes, bar0 + 8 * s);
-    }
-  };
-
-  const uint32_t depth = static_cast<uint32_t>(S) < n_my ? static_cast<uint32_t>(S) : n_my;
-  for (uint32_t q = 0; q < depth; ++q) issue_load(q);
-
-  for (uint32_t q = 0; q < n_my; ++q) {
-    Piece p;
-    gen.get(first + q * stride, p);
-    if (ss.any && p.layer > open_layer) {
-      if (lane == 0) {
-        ptx::bulk_wait<0>();
-        ptx::fence_proxy_async_global();
-        __threadfence_system();
-      }
-      __syncwarp();
-      arrive_layers(ss, open_layer, p.layer, lane);
-      open_layer = p.layer;
-    }
-    const int s = q % S;
-    const uint32_t dst_bytes = UP ? p.bytes * 2 : p.bytes / 2;
-    if (elig(p)) {
-      const uint32_t ob = out0 + (q & 1) * tile_out;
-      if (lane == 0) ptx::bulk_wait_read<1>();  // store q-2 (same out buffer) has been read out
-      __syncwarp();
-      ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);  // every lane reads the slot
-      phase ^= 1u << s;
-      convert_smem<UP>(in0 + s * tile_in, ob, p.bytes, lane);
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-#pragma unroll
-        for (int d = 0; d < kMaxDst; ++d)
-          if (d < p.ndst) ptx::bulk_s2g(p.dst[d], ob, dst_bytes);
-      }
-    } else {
-      for (int d = 0; d < p.ndst; ++d) warp_cast_simt<UP>(p.dst[d], p.src, p.bytes, lane);
-    }
-    if (lane == 0) ptx::bulk_commit();
-    // the input slot was consumed synchronously by this warp: refill it right away
-    if (q + S < n_my) issue_load(q + S);
-  }
-
-  if (lane == 0) {
-    ptx::bulk_wait<0>();
-    ptx::fence_proxy_async_global();
-    __threadfence_system();
-  }
-  __syncwarp();
-  if (ss.any) {
-    arrive_layers(ss, open_layer, ss.layer_end, lane);
-    arrive_transfer(ss, lane);
   }
 }
 

@@ -160,11 +160,11 @@ kvbm_pair_copy_kernel(PairGen gen, uint32_t total, int S, int P, uint32_t tile, 
   SmemView v = carve(smem, W, S, tile, 0);
   init_bars(v.bars, S);
   StreamSync ss{};
-  const uint32_t warp_global = blockIdx.x * W + (threadIdx.x >> 5);
+  ss.layer_end = 1;
+  RingParams rp{S, P, tile, 0, allow_tma != 0, 0, 0};
   // interleave warps of different CTAs over neighbouring items: item i -> CTA (i % grid), warp (i / grid) % W
   const uint32_t first = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
-  (void)warp_global;
-  warp_copy_ring(gen, first, gridDim.x * W, total, v.in, v.bars, S, P, tile, allow_tma != 0, 0, ss);
+  warp_ring<0>(gen, first, gridDim.x * W, total, v.in, v.out, v.bars, rp, ss);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,7 +261,9 @@ struct PagedSyncArgs {
 __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const PagedArgs& a, int W)
 {
   StreamSync ss{};
-  ss.any = s.any != 0;
+  ss.gate = s.layer_ready != nullptr;
+  ss.want_layers = false;
+  ss.want_done = s.completion_flag != nullptr;
   ss.layer_ready = s.layer_ready;
   ss.workspace = s.workspace;
   ss.epoch = s.epoch;
@@ -276,6 +278,8 @@ __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const Pa
   for (int d = 0; d < kMaxDst; ++d) {
     ss.done_flag[d] = s.done_flag[d];
     ss.layer_done[d] = s.layer_done[d];
+    if (d < a.ndst && s.layer_done[d] != nullptr) ss.want_layers = true;
+    if (d < a.ndst && s.done_flag[d] != nullptr) ss.want_done = true;
   }
   return ss;
 }
@@ -283,7 +287,7 @@ __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const Pa
 template <int CAST>
 __global__ void __launch_bounds__(512, 1)
 kvbm_paged_copy_kernel(const __grid_constant__ PagedGen gen, const __grid_constant__ PagedSyncArgs sync,
-                       uint32_t total, int S, int P, uint32_t out_tile, int allow_tma, int cache_hint)
+                       uint32_t total, int S, int P, uint32_t out_tile, int allow_tma, int cache_hint, int variant)
 {
   extern __shared__ __align__(128) uint8_t smem[];
   const int W = blockDim.x >> 5;
@@ -293,12 +297,8 @@ kvbm_paged_copy_kernel(const __grid_constant__ PagedGen gen, const __grid_consta
   const StreamSync ss = make_sync(sync, gen.a, W);
   const uint32_t first = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   const uint32_t stride = gridDim.x * W;
-  if (CAST == KVBM_CAST_NONE)
-    warp_copy_ring(gen, first, stride, total, v.in, v.bars, S, P, tile, allow_tma != 0, cache_hint, ss);
-  else if (CAST == KVBM_CAST_FP8E4M3_TO_BF16)
-    warp_cast_ring<true>(gen, first, stride, total, v.in, v.out, v.bars, S, tile, allow_tma != 0, ss);
-  else
-    warp_cast_ring<false>(gen, first, stride, total, v.in, v.out, v.bars, S, tile, allow_tma != 0, ss);
+  RingParams rp{S, P, tile, out_tile, allow_tma != 0, cache_hint, CAST == KVBM_CAST_NONE ? variant : 0};
+  warp_ring<CAST>(gen, first, stride, total, v.in, v.out, v.bars, rp, ss);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -630,7 +630,7 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
     cudaError_t err = set_smem(kern, rc.smem);
     if (err != cudaSuccess) return err;
     kern<<<grid, rc.warps * 32, rc.smem, stream>>>(gen, sync, total32, rc.stages, rc.pending, rc.out_tile, allow_tma,
-                                                   o.cache_hint);
+                                                   o.cache_hint, o.variant);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
   };

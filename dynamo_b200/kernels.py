@@ -98,6 +98,7 @@ class PagedCopyOpts(C.Structure):
         ("completion_value", C.c_uint32),
         ("stores_in_flight", C.c_int),
         ("cache_hint", C.c_int),
+        ("variant", C.c_int),
     ]
 
 

@@ -132,6 +132,8 @@ typedef struct kvbm_paged_copy_opts {
   int stores_in_flight;           /* 0 = default (stages/2): slots that may still be draining to the destination;
                                      stages - stores_in_flight loads are kept in flight ahead */
   int cache_hint;                 /* bit0: L2 evict_first on source reads, bit1: on destination writes */
+  int variant;                    /* 0 = TMA load + TMA store (default); 1 = TMA load + SIMT store from smem;
+                                     2 / 3 = loads-only / stores-only DIAGNOSTICS (do not copy correctly) */
 } kvbm_paged_copy_opts;
 
 /* Gather `num_blocks` non-contiguous blocks x layers [layer_begin, layer_end) x outer from `src`,
