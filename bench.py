@@ -305,8 +305,8 @@ def run_ours(args):
     # ================= leg 2: `e2e` -- host API, host block tables every step =================
     e2e_times = []
     if is_src:
-        sid_l = [list(map(int, s)) for s in sids]
-        did_l = [list(map(int, d)) for d in dids]
+        sid_l = [np.ascontiguousarray(s, dtype=np.uint64) for s in sids]   # host block tables (numpy, zero-copy into the ABI)
+        did_l = [np.ascontiguousarray(d, dtype=np.uint64) for d in dids]
 
         def step():
             if n_dst == 1:

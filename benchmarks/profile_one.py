@@ -42,6 +42,11 @@ ptr_s = torch.tensor([sb[l].data_ptr() + o * region * nbp + int(b) * region for 
 ptr_d = torch.tensor([db[l].data_ptr() + o * region * nbp + int(b) * region for b in did.tolist() for l in range(nl) for o in range(2)], dtype=torch.int64, device="cuda")
 torch.cuda.synchronize()
 w = a.which
+if w == "torch":
+    big_a = torch.empty(n * nl * 2 * region, dtype=torch.uint8, device="cuda")
+    big_b = torch.empty_like(big_a)
+    torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()   # use with: ncu --profile-from-start off
 for _ in range(a.iters):
     if w.startswith("ours"):
         opts = K.PagedCopyOpts()
@@ -58,8 +63,7 @@ for _ in range(a.iters):
         R.kvbm_kernels_launch_vectorized_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         assert R.kvbm_kernels_launch_vectorized_copy(ptr_s.data_ptr(), ptr_d.data_ptr(), region, ptr_s.numel(), sp) == 0
     else:
-        big_a = torch.empty(n * nl * 2 * region, dtype=torch.uint8, device="cuda")
-        big_b = torch.empty_like(big_a)
         big_b.copy_(big_a)
     torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
 print("done", w)

@@ -57,7 +57,6 @@ struct Layout {
   std::vector<Allocation> allocs;        // 1 (FC) or num_layers (LW)
   std::vector<uint64_t> layer_base;      // address of (block 0, layer l, outer 0)
   uint64_t* dev_layer_base = nullptr;    // copy on the manager's device (kernel descriptor)
-  std::vector<void*> ipc_mappings;       // opened CUDA IPC mappings to close on unregister
 
   // fully_contiguous.rs:225-257 / layer_separate.rs:215-247
   int memory_region(size_t b, size_t l, size_t o, uintptr_t* addr, size_t* size, std::string* why) const

@@ -158,6 +158,9 @@ struct kvbm_transfer_manager {
   Slot slots[kSlots];
   uint64_t next_seq = 1;
   std::atomic<uint64_t> bytes_moved{0}, h2d_bytes{0};
+  // CUDA IPC mappings opened by import_metadata, keyed by the 64-byte handle: an allocation shared by several
+  // imported layouts (e.g. two tensors in one allocator segment) is mapped once; closed when the manager dies.
+  std::unordered_map<std::string, void*> ipc_cache;
 
   Layout* find(kvbm_layout_handle h)
   {
@@ -479,10 +482,9 @@ extern "C" void kvbm_manager_destroy(kvbm_transfer_manager* m)
   if (m->device >= 0) {
     DeviceGuard g(m->device);
     cudaDeviceSynchronize();
-    for (auto& kv : m->layouts) {
+    for (auto& kv : m->layouts)
       if (kv.second->dev_layer_base) cudaFree(kv.second->dev_layer_base);
-      for (void* p : kv.second->ipc_mappings) cudaIpcCloseMemHandle(p);
-    }
+    for (auto& kv : m->ipc_cache) cudaIpcCloseMemHandle(kv.second);
     for (auto& s : m->slots) {
       if (s.ev) cudaEventDestroy(s.ev);
       if (s.pinned_ids) cudaFreeHost(s.pinned_ids);
@@ -549,7 +551,6 @@ extern "C" int kvbm_manager_unregister(kvbm_transfer_manager* m, kvbm_layout_han
         s.in_flight = false;
       }
     if (it->second->dev_layer_base) cudaFree(it->second->dev_layer_base);
-    for (void* p : it->second->ipc_mappings) cudaIpcCloseMemHandle(p);
   }
   m->layouts.erase(it);
   return KVBM_OK;
@@ -687,7 +688,6 @@ extern "C" int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void
   const bool same_process = hd.pid == static_cast<uint64_t>(getpid());
   std::vector<uintptr_t> bases(hd.n_allocs);
   std::vector<size_t> sizes(hd.n_allocs);
-  std::vector<void*> mappings;
   const auto* pa = static_cast<const unsigned char*>(buf) + sizeof(BlobHeader);
   DeviceGuard g(m->device);
   for (uint32_t i = 0; i < hd.n_allocs; ++i) {
@@ -700,13 +700,19 @@ extern "C" int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void
       if (m->device < 0) return fail(KVBM_ERR_CUDA, "importing a device layout needs a CUDA manager");
       cudaIpcMemHandle_t ih;
       std::memcpy(&ih, ba.ipc, 64);
+      const std::string key(reinterpret_cast<const char*>(ba.ipc), 64);
       void* mapped = nullptr;
-      cudaError_t e = cudaIpcOpenMemHandle(&mapped, ih, cudaIpcMemLazyEnablePeerAccess);
-      if (e != cudaSuccess) {
-        for (void* q : mappings) cudaIpcCloseMemHandle(q);
-        return fail_cuda(e, "cudaIpcOpenMemHandle");
+      {
+        std::lock_guard<std::mutex> lk(m->mu);
+        auto it = m->ipc_cache.find(key);
+        if (it != m->ipc_cache.end()) mapped = it->second;
       }
-      mappings.push_back(mapped);
+      if (!mapped) {
+        cudaError_t e = cudaIpcOpenMemHandle(&mapped, ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaIpcOpenMemHandle");
+        std::lock_guard<std::mutex> lk(m->mu);
+        m->ipc_cache[key] = mapped;
+      }
       bases[i] = reinterpret_cast<uintptr_t>(mapped) + ba.offset_in_ipc;
     }
   }
@@ -714,12 +720,8 @@ extern "C" int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void
   std::string why;
   int rc = hd.fully_contiguous ? make_fully_contiguous(cfg, bases.empty() ? 0 : bases[0], sizes.empty() ? 0 : sizes[0], &L, &why)
                                : make_layer_separate(cfg, bases.data(), sizes.data(), hd.n_allocs, static_cast<int>(hd.block_dim), &L, &why);
-  if (rc) {
-    for (void* q : mappings) cudaIpcCloseMemHandle(q);
-    return fail(rc, why);
-  }
+  if (rc) return fail(rc, why);
   L.remote = !same_process;
-  L.ipc_mappings = std::move(mappings);
   return finish_register(m, std::move(L), static_cast<int>(hd.storage), hd.device_id, out);
 }
 

@@ -184,6 +184,54 @@ template <bool UP>
 __device__ __forceinline__ void warp_cast_simt(uint8_t* dst, const uint8_t* src, uint32_t src_bytes, int lane);
 
 // ------------------------------------------------------------------------------------------
+// Per-warp descriptor ring.  Address generation (a handful of integer divisions and two dependent
+// table loads per item) is far too slow for the single instruction stream that drives the TMA
+// pipeline -- with one warp per scheduler every dependent instruction costs its full latency, which
+// measured ~2 us per item.  So the 32 lanes generate the descriptors of 32 consecutive items at
+// once (SIMD), park them in shared memory, and the pipeline reads them back with 3-4 LDS per item.
+// Layout (SoA, kDescRing entries each):  src[u64] | meta[u32 bytes|ok<<31, i32 layer] | dst[d][u64]...
+// ------------------------------------------------------------------------------------------
+constexpr int kDescRing = 64;
+__host__ __device__ constexpr uint32_t desc_bytes_per_warp(int ndst) { return kDescRing * (16u + 8u * static_cast<uint32_t>(ndst)); }
+
+struct DescRing {
+  uint64_t* src;
+  uint2* meta;
+  uint64_t* dst;  // [ndst][kDescRing]
+  __device__ __forceinline__ DescRing(uint8_t* mem)
+      : src(reinterpret_cast<uint64_t*>(mem)),
+        meta(reinterpret_cast<uint2*>(mem + kDescRing * 8)),
+        dst(reinterpret_cast<uint64_t*>(mem + kDescRing * 16))
+  {
+  }
+  __device__ __forceinline__ void put(uint32_t j, const Piece& p, bool ok) const
+  {
+    const uint32_t i = j & (kDescRing - 1);
+    src[i] = reinterpret_cast<uint64_t>(p.src);
+    meta[i] = make_uint2(p.bytes | (ok ? 0x80000000u : 0u), static_cast<uint32_t>(p.layer));
+#pragma unroll
+    for (int d = 0; d < kMaxDst; ++d)
+      if (d < p.ndst) dst[d * kDescRing + i] = reinterpret_cast<uint64_t>(p.dst[d]);
+  }
+  // returns eligibility; fills src/bytes/layer (+dst when want_dst)
+  __device__ __forceinline__ bool get(uint32_t j, int ndst, Piece& p, bool want_dst) const
+  {
+    const uint32_t i = j & (kDescRing - 1);
+    const uint2 m = meta[i];
+    p.src = reinterpret_cast<const uint8_t*>(src[i]);
+    p.bytes = m.x & 0x7fffffffu;
+    p.layer = static_cast<int>(m.y);
+    p.ndst = ndst;
+    if (want_dst) {
+#pragma unroll
+      for (int d = 0; d < kMaxDst; ++d)
+        if (d < ndst) p.dst[d] = reinterpret_cast<uint8_t*>(dst[d * kDescRing + i]);
+    }
+    return (m.x & 0x80000000u) != 0;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
 // The ring.  CAST: 0 byte-exact, 1 fp8->bf16, 2 bf16->fp8.  Gen::get(item, Piece&) is warp-uniform.
 //   first/stride/total : this warp's arithmetic progression of item indices
 //   in_slots           : S * tile_in bytes private to this warp;  out_slots: 2 * tile_out (cast only)
@@ -195,10 +243,13 @@ __device__ __forceinline__ void warp_cast_simt(uint8_t* dst, const uint8_t* src,
 template <int CAST, class Gen>
 __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32_t stride, uint32_t total,
                                           uint8_t* in_slots, uint8_t* out_slots, uint64_t* bars,
-                                          const RingParams& rp, const StreamSync& ss)
+                                          uint8_t* desc_mem, int ndst, const RingParams& rp,
+                                          const StreamSync& ss)
 {
   const int lane = threadIdx.x & 31;
   const int S = rp.S;
+  const DescRing ring(desc_mem);
+  uint32_t filled = 0;  // descriptors exist for this warp's items [max(0, filled - kDescRing), filled)
   const bool sync_slot = CAST != 0 || rp.variant == 1 || rp.variant == 2;  // input slot is released synchronously
   const uint32_t ahead = sync_slot ? static_cast<uint32_t>(S) : static_cast<uint32_t>(S - rp.P);
   const uint32_t n_my = total > first ? (total - first + stride - 1) / stride : 0;
@@ -216,15 +267,25 @@ __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32
     if (CAST != 0) ok = ok && (p.bytes & 31) == 0;  // both sides whole 16 B vectors
     return ok;
   };
+  auto fill = [&]() {  // all 32 lanes: descriptors of the next 32 items
+    const uint32_t j = filled + lane;
+    if (j < n_my) {
+      Piece p;
+      gen.get(first + j * stride, p);
+      ring.put(j, p, eligible(p));
+    }
+    filled += 32;
+    __syncwarp();
+  };
   auto pump = [&](uint32_t limit) {
     while (next_load < n_my && next_load < limit) {
       Piece p;
-      gen.get(first + next_load * stride, p);
+      const bool ok = ring.get(next_load, ndst, p, false);
       if (p.layer > ready_layer) {
         if (!layer_is_ready(ss, p.layer, lane)) break;
         ready_layer = p.layer;
       }
-      if (rp.variant != 3 && eligible(p) && lane == 0) {
+      if (rp.variant != 3 && ok && lane == 0) {
         const int s = next_load % S;
         ptx::mbar_arrive_expect_tx(bar0 + 8 * s, p.bytes);
         if (rp.cache_hint & 1)
@@ -242,9 +303,10 @@ __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32
   };
 
   for (uint32_t q = 0; q < n_my; ++q) {
+    while (filled < n_my && filled <= q + ahead) fill();
     pump(q + ahead);
     Piece p;
-    gen.get(first + q * stride, p);
+    const bool ok = ring.get(q, ndst, p, true);
     if (next_load <= q) {  // this item's layer has not been released yet: publish what is finished, then block
       if (ss.want_layers) publish_upto(p.layer);
       wait_layer_ready(ss, p.layer, lane);
@@ -255,7 +317,7 @@ __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32
     }
     const int s = q % S;
     const uint32_t slot = in0 + s * rp.tile_in;
-    if (eligible(p)) {
+    if (ok) {
       if (CAST == 0 && rp.variant == 0) {
         if (lane == 0) {
           ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);

@@ -58,14 +58,14 @@ struct RingCfg {
 constexpr uint32_t kBarBytesPerWarp = kMaxStages * 8;
 // defaults tuned on B200 (profiles/r01_sweep_*.json)
 constexpr int kDefaultWarps = 4;
-constexpr int kDefaultStages = 6;
-constexpr uint32_t kDefaultTile = 8192;
+constexpr int kDefaultStages = 3;
+constexpr uint32_t kDefaultTile = 16384;
 
 static uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 
 // cast: 0 none, 1 up (out = 2x), 2 down (out = x/2)
 static RingCfg make_ring(const DeviceInfo& di, uint32_t unit_bytes, int warps, int stages, int tile,
-                         int cast, int pending = 0)
+                         int cast, int pending = 0, int ndst = 1)
 {
   RingCfg c{};
   c.warps = warps > 0 ? std::min(warps, 16) : kDefaultWarps;
@@ -75,7 +75,7 @@ static RingCfg make_ring(const DeviceInfo& di, uint32_t unit_bytes, int warps, i
   const uint32_t budget = static_cast<uint32_t>(di.max_smem_optin) - 1024;
   for (;;) {
     const uint32_t out = cast == 1 ? 2 * t : (cast == 2 ? t / 2 : 0);
-    const uint32_t fixed = c.warps * (kBarBytesPerWarp + 2 * out);
+    const uint32_t fixed = c.warps * (kBarBytesPerWarp + desc_bytes_per_warp(ndst) + 2 * out);
     int s = stages > 0 ? stages : kDefaultStages;
     s = std::min(s, kMaxStages);
     while (s > 2 && fixed + c.warps * s * t > budget) --s;
@@ -102,19 +102,22 @@ static RingCfg make_ring(const DeviceInfo& di, uint32_t unit_bytes, int warps, i
   }
 }
 
-// shared-memory carve-up: [bars: W * kMaxStages * 8][in slots: W * S * tile][out slots: W * 2 * out_tile]
+// shared-memory carve-up: [bars: W * kMaxStages * 8][descriptor rings: W * desc][in slots: W * S * tile][out slots: W * 2 * out_tile]
 struct SmemView {
   uint64_t* bars;
+  uint8_t* desc;
   uint8_t* in;
   uint8_t* out;
 };
 
-__device__ __forceinline__ SmemView carve(uint8_t* base, int W, int S, uint32_t tile, uint32_t out_tile)
+__device__ __forceinline__ SmemView carve(uint8_t* base, int W, int S, uint32_t tile, uint32_t out_tile, int ndst)
 {
   const int warp = threadIdx.x >> 5;
   SmemView v;
   v.bars = reinterpret_cast<uint64_t*>(base) + warp * kMaxStages;
-  uint8_t* in0 = base + W * kBarBytesPerWarp;
+  const uint32_t db = desc_bytes_per_warp(ndst);
+  v.desc = base + W * kBarBytesPerWarp + warp * db;
+  uint8_t* in0 = base + W * (kBarBytesPerWarp + db);
   v.in = in0 + static_cast<size_t>(warp) * S * tile;
   v.out = in0 + static_cast<size_t>(W) * S * tile + static_cast<size_t>(warp) * 2 * out_tile;
   return v;
@@ -157,14 +160,14 @@ kvbm_pair_copy_kernel(PairGen gen, uint32_t total, int S, int P, uint32_t tile, 
 {
   extern __shared__ __align__(128) uint8_t smem[];
   const int W = blockDim.x >> 5;
-  SmemView v = carve(smem, W, S, tile, 0);
+  SmemView v = carve(smem, W, S, tile, 0, 1);
   init_bars(v.bars, S);
   StreamSync ss{};
   ss.layer_end = 1;
   RingParams rp{S, P, tile, 0, allow_tma != 0, 0, 0};
   // interleave warps of different CTAs over neighbouring items: item i -> CTA (i % grid), warp (i / grid) % W
   const uint32_t first = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
-  warp_ring<0>(gen, first, gridDim.x * W, total, v.in, v.out, v.bars, rp, ss);
+  warp_ring<0>(gen, first, gridDim.x * W, total, v.in, v.out, v.bars, v.desc, 1, rp, ss);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -292,13 +295,14 @@ kvbm_paged_copy_kernel(const __grid_constant__ PagedGen gen, const __grid_consta
   extern __shared__ __align__(128) uint8_t smem[];
   const int W = blockDim.x >> 5;
   const uint32_t tile = gen.a.tile;
-  SmemView v = carve(smem, W, S, tile, out_tile);
+  const int ring_ndst = gen.a.replicate ? gen.a.ndst : 1;
+  SmemView v = carve(smem, W, S, tile, out_tile, ring_ndst);
   init_bars(v.bars, S);
   const StreamSync ss = make_sync(sync, gen.a, W);
   const uint32_t first = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
   const uint32_t stride = gridDim.x * W;
   RingParams rp{S, P, tile, out_tile, allow_tma != 0, cache_hint, CAST == KVBM_CAST_NONE ? variant : 0};
-  warp_ring<CAST>(gen, first, stride, total, v.in, v.out, v.bars, rp, ss);
+  warp_ring<CAST>(gen, first, stride, total, v.in, v.out, v.bars, v.desc, ring_ndst, rp, ss);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -606,7 +610,8 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   DeviceInfo di;
   cudaError_t e = device_info(&di);
   if (e != cudaSuccess) return e;
-  RingCfg rc = make_ring(di, src->region_bytes, o.warps_per_cta, o.stages, o.tile_bytes, cast_mode, o.stores_in_flight);
+  RingCfg rc = make_ring(di, src->region_bytes, o.warps_per_cta, o.stages, o.tile_bytes, cast_mode, o.stores_in_flight,
+                         gen.a.replicate ? num_dsts : 1);
 
   gen.a.n_blocks = static_cast<uint32_t>(num_blocks);
   gen.a.layer_begin = static_cast<uint32_t>(layer_begin);

@@ -212,8 +212,23 @@ def _check(rc: int) -> None:
 
 
 def _size_array(ids: Sequence[int]):
+    """Host block-id list -> `const size_t*`.  numpy int64/uint64 arrays are passed without copying."""
     n = len(ids)
+    try:
+        import numpy as np
+        if isinstance(ids, np.ndarray) and ids.dtype in (np.uint64, np.int64) and ids.flags.c_contiguous:
+            return _NpView(ids), n
+    except ImportError:  # pragma: no cover
+        pass
     return (C.c_size_t * max(1, n))(*[int(x) for x in ids]), n
+
+
+class _NpView:
+    """Keeps the numpy array alive and presents it as a ctypes pointer argument."""
+
+    def __init__(self, arr):
+        self.arr = arr
+        self._as_parameter_ = arr.ctypes.data_as(C.POINTER(C.c_size_t))
 
 
 def select_direct_strategy(src: StorageKind, dst: StorageKind, allow_gds: bool = False,
@@ -344,8 +359,9 @@ class TransferManager:
         s_arrays = [_size_array(x)[0] for x in (src_block_ids if not replicate else [src_block_ids[0]] * nd)]
         d_arrays = [_size_array(x)[0] for x in dst_block_ids]
         PP = C.POINTER(C.c_size_t)
-        sp = (PP * nd)(*[C.cast(a, PP) for a in s_arrays])
-        dp = (PP * nd)(*[C.cast(a, PP) for a in d_arrays])
+        as_ptr = lambda a: a._as_parameter_ if isinstance(a, _NpView) else C.cast(a, PP)
+        sp = (PP * nd)(*[as_ptr(a) for a in s_arrays])
+        dp = (PP * nd)(*[as_ptr(a) for a in d_arrays])
         tok = C.c_uint64()
         o = (options or TransferOptions())._c()
         _check(lib().kvbm_manager_execute_fanout(self._h, src, nd, hs, sp, dp, n, int(replicate), C.byref(o), C.byref(tok)))

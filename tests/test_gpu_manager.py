@@ -203,14 +203,20 @@ def test_layer_streaming_with_ready_and_done_flags(mgr):
     ready = torch.zeros(nl, dtype=torch.int32, device="cuda")
     done = torch.zeros(nl, dtype=torch.int32, device="cuda")
     sid, did = list(range(n)), list(range(n, 2 * n))
+    ctl = torch.cuda.Stream()     # control-plane stream of the "engine": releases layers, waits for their arrival
     note = mgr.execute_transfer(src.h, sid, dst.h, did, TransferOptions(layer_ready_flags=ready.data_ptr(),
                                                                         layer_done_flags=done.data_ptr(), epoch=5, max_ctas=16))
-    assert not note.is_complete()          # gated on layer 0's ready flag
-    main = torch.cuda.current_stream()
-    for l in range(nl):
-        K.check(K.set_flags(ready.data_ptr(), l, 1, 5, int(main.cuda_stream)))
-        K.check(K.wait_flag(done[l:].data_ptr(), 5, int(main.cuda_stream)))   # consumer sees layer l before l+1 is released
-    note.wait()
+    try:
+        assert not note.is_complete()          # gated on layer 0's ready flag
+        for l in range(nl):
+            K.check(K.set_flags(ready.data_ptr(), l, 1, 5, int(ctl.cuda_stream)))
+            K.check(K.wait_flag(done[l:].data_ptr(), 5, int(ctl.cuda_stream)))   # layer l seen before l+1 is released
+        note.wait(20.0)
+    finally:   # whatever happened, let every spinning kernel finish so teardown cannot hang
+        rescue = torch.cuda.Stream()
+        K.set_flags(ready.data_ptr(), 0, nl, 5, int(rescue.cuda_stream))
+        if not note.is_complete():
+            K.set_flags(done.data_ptr(), 0, nl, 5, int(rescue.cuda_stream))
     torch.cuda.synchronize()
     assert done.tolist() == [5] * nl
     ref = O.Layout(O.LW, nb, nl, 2, 16, 256, 2, block_dim=O.BLOCK_IS_SECOND_DIM)
