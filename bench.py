@@ -39,14 +39,37 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-# ---- workload geometry (Llama-3-8B, bf16, block_size 16) ----
+# ---- workload geometry; defaults = BASELINE configs[1] (Llama-3-8B, bf16, block_size 16, 4k ctx) ----
 NL, OUTER, PAGE, KV_HEADS, HEAD_DIM, DTYPE_BYTES = 32, 2, 16, 8, 128, 2
 INNER = KV_HEADS * HEAD_DIM
-REGION = PAGE * INNER * DTYPE_BYTES          # 32 KiB
+REGION = PAGE * INNER * DTYPE_BYTES          # 32 KiB (destination side)
+SRC_REGION = REGION                          # differs only with --cast fp8 (16 KiB fp8 source regions)
 CTX_TOKENS = 4096
 N_BLOCKS = CTX_TOKENS // PAGE                # 256
 POOL_BLOCKS = 1024                           # pool per GPU: 1024 blocks = 2 GiB (transfer touches 512 MiB of it)
 BYTES_PER_DST = N_BLOCKS * NL * OUTER * REGION
+MODEL_NAME = "Llama-3-8B bf16"
+CAST = 0
+REPLICATE = False
+
+
+def configure(args):
+    """Non-default workloads (other BASELINE configs) for the numbers under profiles/; the driver uses defaults."""
+    global NL, KV_HEADS, INNER, REGION, SRC_REGION, CTX_TOKENS, N_BLOCKS, POOL_BLOCKS, BYTES_PER_DST, MODEL_NAME, CAST, REPLICATE
+    if args.model == "llama70b-tp4":       # configs[3]: 80 layers, 2 of 8 KV heads per rank -> 8 KiB regions
+        NL, KV_HEADS, MODEL_NAME = 80, 2, "Llama-3-70B TP=4 shard bf16"
+    elif args.model == "mixtral":          # configs[4]: same KV geometry as Llama-3-8B
+        MODEL_NAME = "Mixtral-8x7B bf16"
+    INNER = KV_HEADS * HEAD_DIM
+    REGION = PAGE * INNER * DTYPE_BYTES
+    SRC_REGION = REGION
+    if args.cast == "fp8":                 # configs[2]: fp8 KV source, bf16 destination, cast fused in the kernel
+        CAST, SRC_REGION, MODEL_NAME = 1, REGION // 2, MODEL_NAME.replace("bf16", "fp8->bf16")
+    CTX_TOKENS = args.ctx
+    N_BLOCKS = CTX_TOKENS // PAGE
+    POOL_BLOCKS = args.pool_blocks or max(1024, 2 * N_BLOCKS)
+    BYTES_PER_DST = N_BLOCKS * NL * OUTER * REGION
+    REPLICATE = args.replicate
 
 
 def peaks():
@@ -110,6 +133,7 @@ class ClockSampler:
 def cpu_path(steps, warmup, threads, pool_blocks=512):
     """Times execute_memcpy_transfer on host memory for the same 256-block / 512 MiB request."""
     from oracle import oracle as O
+    pool_blocks = max(pool_blocks, 2 * N_BLOCKS)
     mk = lambda: O.Layout(O.LW, pool_blocks, NL, OUTER, PAGE, INNER, DTYPE_BYTES, block_dim=O.BLOCK_IS_SECOND_DIM)
     src, dst = mk(), mk()
     rng = np.random.default_rng(1234)
@@ -154,20 +178,22 @@ def run_reference(args):
 
 
 def workload_config(n_gpus, where="hbm"):
-    return {"workload": "Llama-3-8B bf16 KV hand-off, 4k ctx, block_size=16: 256 blocks x 32 layers x K/V x 32 KiB = 512 MiB per destination",
+    return {"workload": f"{MODEL_NAME} KV hand-off, {CTX_TOKENS // 1024}k ctx, block_size={PAGE}: {N_BLOCKS} blocks x {NL} layers x K/V x "
+                        f"{REGION // 1024} KiB = {BYTES_PER_DST / 2**20:.0f} MiB per destination" + (" (identical payload to every destination)" if REPLICATE else ""),
             "topology": "same-GPU gather->scatter" if n_gpus == 1 else f"1 prefill -> {n_gpus - 1} decode GPUs (NVLink peer stores via CUDA IPC mappings)",
             "layout": "LayerSeparate/BlockIsSecondDim (vLLM [2,num_blocks,16,8,128] per layer)",
             "pool_blocks": POOL_BLOCKS if where == "hbm" else 512,
             "block_tables": "random permutation (seeded), non-contiguous on both sides",
-            "cache": "inputs larger than L2 (1 GiB touched per step vs 126 MB L2), no flush needed",
+            "cache": f"inputs larger than L2 ({(BYTES_PER_DST + BYTES_PER_DST * SRC_REGION // REGION) / 2**20:.0f} MiB touched per step vs 126 MB L2), no flush needed",
             "bytes_per_destination": BYTES_PER_DST}
 
 
 # =====================================================================================================
 # ours
 # =====================================================================================================
-def make_pool(torch, device):
-    bufs = [torch.empty(OUTER * POOL_BLOCKS * REGION, dtype=torch.uint8, device=device) for _ in range(NL)]
+def make_pool(torch, device, region=None):
+    region = region or REGION
+    bufs = [torch.empty(OUTER * POOL_BLOCKS * region, dtype=torch.uint8, device=device) for _ in range(NL)]
     return bufs
 
 
@@ -195,22 +221,23 @@ def run_ours(args):
             dist.barrier()
 
     cfg = LayoutConfig(POOL_BLOCKS, NL, OUTER, PAGE, INNER, dtype_width_bytes=DTYPE_BYTES)
+    src_cfg = cfg if not CAST else LayoutConfig(POOL_BLOCKS, NL, OUTER, PAGE, INNER, dtype_width_bytes=1, allow_fp8=True)
     mgr = TransferManager(device=local, worker_id=rank + 1)
     n_dst = max(1, world - 1)
     is_src = rank == 0
     is_dst = (world == 1) or rank >= 1
 
-    def register(bufs):
-        return mgr.register_layer_separate(cfg, [b.data_ptr() for b in bufs], [b.numel() for b in bufs],
+    def register(bufs, c=None):
+        return mgr.register_layer_separate(c or cfg, [b.data_ptr() for b in bufs], [b.numel() for b in bufs],
                                            BlockDimension.BlockIsSecondDim, StorageKind.Device, local)
 
     src_bufs = dst_bufs = None
     if is_src:
-        src_bufs = make_pool(torch, dev)
+        src_bufs = make_pool(torch, dev, SRC_REGION)
         g = torch.Generator(device=dev).manual_seed(1234)
         for b in src_bufs:
             b.copy_(torch.randint(0, 256, b.shape, dtype=torch.uint8, device=dev, generator=g))
-        h_src = register(src_bufs)
+        h_src = register(src_bufs, src_cfg)
     flag_buf = torch.zeros(64, dtype=torch.int32, device=dev)   # [0]=done flag of this destination
     if is_dst:
         dst_bufs = make_pool(torch, dev)
@@ -235,7 +262,7 @@ def run_ours(args):
         peer_flags = [flag_buf.data_ptr()]
 
     # ---- block tables ----
-    sids = [np.random.default_rng(10 + d).permutation(POOL_BLOCKS)[:N_BLOCKS] for d in range(n_dst)]
+    sids = [np.random.default_rng(10 + (0 if REPLICATE else d)).permutation(POOL_BLOCKS)[:N_BLOCKS] for d in range(n_dst)]
     dids = [np.random.default_rng(100 + d).permutation(POOL_BLOCKS)[:N_BLOCKS] for d in range(n_dst)]
     stream = torch.cuda.Stream(device=dev)
     sp = int(stream.cuda_stream)
@@ -250,25 +277,26 @@ def run_ours(args):
         from dynamo_b200.kernels import PagedCopyOpts, PagedDst, PagedLayout
         lay = lambda h: None
         # device descriptors straight from the registered layouts (same numbers the manager uses)
-        def desc(h, bufs_or_none):
+        def desc(h, region):
             bases = [mgr.memory_region(h, 0, l, 0)[0] for l in range(NL)]
             t = torch.tensor(bases, dtype=torch.int64, device=dev)
-            return t, PagedLayout(t.data_ptr(), REGION, REGION * POOL_BLOCKS, REGION, NL, OUTER, POOL_BLOCKS)
+            return t, PagedLayout(t.data_ptr(), region, region * POOL_BLOCKS, region, NL, OUTER, POOL_BLOCKS)
         keep = []
-        t_src, d_src = desc(h_src, src_bufs)
+        t_src, d_src = desc(h_src, SRC_REGION)
         keep.append(t_src)
         dst_descs = []
         ws = torch.zeros(NL + 1, dtype=torch.int32, device=dev)
+        shared_s = torch.from_numpy(sids[0].astype(np.int32)).to(dev)
         for d in range(n_dst):
-            t, dd = desc(h_dsts[d], None)
-            s_ids = torch.from_numpy(sids[d].astype(np.int32)).to(dev)
+            t, dd = desc(h_dsts[d], REGION)
+            s_ids = shared_s if REPLICATE else torch.from_numpy(sids[d].astype(np.int32)).to(dev)
             d_ids = torch.from_numpy(dids[d].astype(np.int32)).to(dev)
             keep += [t, s_ids, d_ids]
             dst_descs.append(PagedDst(dd, s_ids.data_ptr(), d_ids.data_ptr(), peer_flags[d], 0))
 
         def launch(epoch):
             opts = PagedCopyOpts(epoch=epoch, sync_workspace=ws.data_ptr())
-            K.check(K.paged_copy(d_src, dst_descs, N_BLOCKS, 0, NL, 0, opts, sp), "paged_copy")
+            K.check(K.paged_copy(d_src, dst_descs, N_BLOCKS, 0, NL, CAST, opts, sp), "paged_copy")
     barrier()
     if is_src:
         with torch.cuda.stream(stream):
@@ -309,10 +337,11 @@ def run_ours(args):
         did_l = [np.ascontiguousarray(d, dtype=np.uint64) for d in dids]
 
         def step():
+            o = TransferOptions(cast_mode=CAST)
             if n_dst == 1:
-                note = mgr.execute_transfer(h_src, sid_l[0], h_dsts[0], did_l[0])
+                note = mgr.execute_transfer(h_src, sid_l[0], h_dsts[0], did_l[0], o)
             else:
-                note = mgr.execute_fanout(h_src, h_dsts, sid_l, did_l)
+                note = mgr.execute_fanout(h_src, h_dsts, sid_l, did_l, REPLICATE, o)
             note.wait(60.0)
         for _ in range(W):
             step()
@@ -337,7 +366,9 @@ def run_ours(args):
 
     # ================= verification inside the bench (cheap, not timed) =================
     ok = True
-    if world == 1:
+    if CAST:
+        pass   # the cast is verified bit-for-bit in tests/test_gpu_paged.py; the probes below compare raw bytes
+    elif world == 1:
         import blake3
         for d in range(n_dst):
             hs, hd = blake3.blake3(), blake3.blake3()
@@ -371,17 +402,17 @@ def run_ours(args):
         e2e_val = total_dst_bytes / (e2e_ms * 1e-3) / 1e9
         peak, peak_src = peaks()
         if world == 1:
-            alg = 2 * BYTES_PER_DST   # B_src read once + B_dst written, per launch
+            alg = BYTES_PER_DST * SRC_REGION // REGION + BYTES_PER_DST   # B_src read once + B_dst written, per launch
             roof = {"bound": "hbm", "achieved": round(alg / (ms_per_step * 1e-3) / 1e9, 2), "peak": peak, "unit": "GB/s",
                     "frac": round(alg / (ms_per_step * 1e-3) / 1e9 / peak, 4), "traffic": ncu_traffic(), "peak_source": peak_src,
-                    "kernel": "kvbm_paged_copy_kernel<0>", "algorithmic_bytes_per_launch": alg}
+                    "kernel": f"kvbm_paged_copy_kernel<{CAST}>", "algorithmic_bytes_per_launch": alg}
         else:
             alg = total_dst_bytes     # NVLink egress of the source GPU
             roof = {"bound": "nvlink", "achieved": round(value, 2), "peak": NVLINK_PEER_GBS, "unit": "GB/s",
                     "frac": round(value / NVLINK_PEER_GBS, 4), "traffic": None,
                     "peak_source": "measured peer copy 770 GB/s per direction (B200_PROFILING.md); nominal 900",
                     "kernel": "kvbm_paged_copy_kernel<0>", "algorithmic_bytes_per_launch": alg,
-                    "hbm_read_gbs_source": round(alg / (ms_per_step * 1e-3) / 1e9, 2)}
+                    "hbm_read_gbs_source": round((BYTES_PER_DST * SRC_REGION // REGION) * (1 if REPLICATE else n_dst) / (ms_per_step * 1e-3) / 1e9, 2)}
         line = {
             "metric": "kv_transfer_gbs", "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": K_steps,
             "warmup": W, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
@@ -436,7 +467,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    # non-default workloads (other BASELINE configs); results of these runs live in profiles/
+    ap.add_argument("--model", default="llama8b", choices=["llama8b", "llama70b-tp4", "mixtral"])
+    ap.add_argument("--ctx", type=int, default=4096, help="context tokens (blocks = ctx/16)")
+    ap.add_argument("--cast", default="none", choices=["none", "fp8"])
+    ap.add_argument("--replicate", action="store_true", help="same blocks to every destination (CollectiveOps::broadcast)")
+    ap.add_argument("--pool-blocks", type=int, default=0)
     args = ap.parse_args()
+    configure(args)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         return run_reference(args)

@@ -247,3 +247,36 @@ def test_universal_roundtrip_quarter_offsets():
                         for x in range(hd):
                             off = (t * nh + h) * hd + x
                             assert u[h, l, o, t, x] == ((b * chunk_count + l * no + o) * inner + off) + 0.25
+
+
+# ---------------------------------------------------------------- v1 fatbin drop-in (DYN_FATBIN_PATH)
+def test_v1_fatbin_vectorised_copy_symbol_and_launch_contract():
+    """Loads dynamo_b200/vectorized_copy.fatbin the way the v1 block manager does
+    (lib/llm/src/block_manager/block/transfer/cuda.rs:85-153,521-548): cuModuleLoadData, symbol
+    `vectorised_copy`, grid=min(1024,pairs) x block=256, 0 dynamic smem, pointer tables in pinned memory."""
+    from cuda.bindings import driver as drv
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dynamo_b200", "vectorized_copy.fatbin")
+    assert os.path.exists(path), "build() must produce the fatbin"
+    torch.cuda.init()
+    torch.zeros(1, device="cuda")
+    data = open(path, "rb").read()
+    err, mod = drv.cuModuleLoadData(data)
+    assert err == drv.CUresult.CUDA_SUCCESS, err
+    err, fn = drv.cuModuleGetFunction(mod, b"vectorised_copy")
+    assert err == drv.CUresult.CUDA_SUCCESS, err
+    for size, pairs in [(32768, 160), (999, 7), (5 * 1024 * 1024, 2), (64, 3000)]:
+        src = torch.randint(0, 256, (pairs, size), dtype=torch.uint8, device="cuda")
+        dst = torch.zeros(pairs, size, dtype=torch.uint8, device="cuda")
+        perm = torch.randperm(pairs)
+        st = torch.tensor([src[int(i)].data_ptr() for i in perm], dtype=torch.int64).pin_memory()
+        dt = torch.tensor([dst[i].data_ptr() for i in range(pairs)], dtype=torch.int64).pin_memory()
+        args = np.array([st.data_ptr(), dt.data_ptr(), size, pairs], dtype=np.uint64)
+        a0, a1, a2 = (np.array([v], dtype=np.uint64) for v in (st.data_ptr(), dt.data_ptr(), size))
+        a3 = np.array([pairs], dtype=np.int32)
+        params = np.array([a.ctypes.data for a in (a0, a1, a2, a3)], dtype=np.uint64)
+        torch.cuda.synchronize()
+        (err,) = drv.cuLaunchKernel(fn, min(1024, pairs), 1, 1, 256, 1, 1, 0, 0, params.ctypes.data, 0)
+        assert err == drv.CUresult.CUDA_SUCCESS, err
+        torch.cuda.synchronize()
+        assert torch.equal(dst, src[perm]), (size, pairs)
+    drv.cuModuleUnload(mod)
