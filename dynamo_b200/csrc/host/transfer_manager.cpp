@@ -251,15 +251,11 @@ static int host_memcpy_transfer(const Layout& S, const Layout& D, const size_t* 
   return KVBM_OK;
 }
 
-// Acquire a slot whose previous transfer has completed (waits for the oldest if all are busy).
-static int acquire_slot(kvbm_transfer_manager* m, size_t ids_needed, size_t ws_needed, Slot** out, uint64_t* seq)
+// (Re)size one slot's resources.  cudaMalloc / cudaHostAlloc / cudaMemset synchronise the device, which would
+// deadlock against a gated (layer-streaming) transfer that is still spinning on its ready flags -- so every slot
+// is provisioned when the manager is created and this only runs again for unusually large requests.
+static int ensure_slot(Slot& sl, size_t ids_needed, size_t ws_needed)
 {
-  const uint64_t s = m->next_seq++;
-  Slot& sl = m->slots[(s - 1) % kSlots];
-  if (sl.in_flight) {
-    CU(cudaEventSynchronize(sl.ev));
-    sl.in_flight = false;
-  }
   if (!sl.ev) CU(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
   if (!sl.host_flag) {
     CU(cudaHostAlloc(reinterpret_cast<void**>(&sl.host_flag), 64, cudaHostAllocMapped | cudaHostAllocPortable));
@@ -270,7 +266,7 @@ static int acquire_slot(kvbm_transfer_manager* m, size_t ids_needed, size_t ws_n
     if (sl.dev_ids) cudaFree(sl.dev_ids);
     sl.pinned_ids = nullptr;
     sl.dev_ids = nullptr;
-    size_t cap = 1024;
+    size_t cap = 4096;
     while (cap < ids_needed) cap *= 2;
     CU(cudaHostAlloc(reinterpret_cast<void**>(&sl.pinned_ids), cap * sizeof(int32_t), cudaHostAllocPortable));
     CU(cudaMalloc(reinterpret_cast<void**>(&sl.dev_ids), cap * sizeof(int32_t)));
@@ -278,12 +274,26 @@ static int acquire_slot(kvbm_transfer_manager* m, size_t ids_needed, size_t ws_n
   }
   if (sl.ws_cap < ws_needed) {
     if (sl.dev_ws) cudaFree(sl.dev_ws);
-    size_t cap = 128;
+    size_t cap = 512;
     while (cap < ws_needed) cap *= 2;
     CU(cudaMalloc(reinterpret_cast<void**>(&sl.dev_ws), cap * sizeof(uint32_t)));
     CU(cudaMemset(sl.dev_ws, 0, cap * sizeof(uint32_t)));
     sl.ws_cap = cap;
   }
+  return KVBM_OK;
+}
+
+// Acquire a slot whose previous transfer has completed (waits for the oldest if all are busy).
+static int acquire_slot(kvbm_transfer_manager* m, size_t ids_needed, size_t ws_needed, Slot** out, uint64_t* seq)
+{
+  const uint64_t s = m->next_seq++;
+  Slot& sl = m->slots[(s - 1) % kSlots];
+  if (sl.in_flight) {
+    CU(cudaEventSynchronize(sl.ev));
+    sl.in_flight = false;
+  }
+  int rc = ensure_slot(sl, ids_needed, ws_needed);
+  if (rc) return rc;
   sl.seq = s;
   *out = &sl;
   *seq = s;
@@ -470,6 +480,10 @@ extern "C" int kvbm_manager_create(int cuda_device_id, uint64_t worker_id, kvbm_
     for (int i = 0; i < kStreams; ++i) {
       CU(cudaStreamCreateWithFlags(&m->h2d[i], cudaStreamNonBlocking));
       CU(cudaStreamCreateWithFlags(&m->d2h[i], cudaStreamNonBlocking));
+    }
+    for (auto& sl : m->slots) {
+      int rc = ensure_slot(sl, 4096, 512);
+      if (rc) return rc;
     }
   }
   *out = m.release();

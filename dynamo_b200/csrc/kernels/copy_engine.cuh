@@ -268,6 +268,7 @@ __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32
     return ok;
   };
   auto fill = [&]() {  // all 32 lanes: descriptors of the next 32 items
+    __syncwarp();      // lanes that ran ahead must not overwrite entries a slower lane still reads
     const uint32_t j = filled + lane;
     if (j < n_my) {
       Piece p;

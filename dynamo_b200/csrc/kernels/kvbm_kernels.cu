@@ -22,6 +22,8 @@ struct DeviceInfo {
   int max_smem_optin = 0;
 };
 
+static cudaError_t preload_kernels();
+
 static cudaError_t device_info(DeviceInfo* out)
 {
   constexpr int kMaxDev = 64;
@@ -36,6 +38,10 @@ static cudaError_t device_info(DeviceInfo* out)
     int a = 0, b = 0;
     if ((e = cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&b, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    // CUDA loads kernels lazily and a first-time load can wait for the device to go idle.  A transfer kernel
+    // that is spinning on layer-ready flags would then deadlock against the very first launch of the tiny
+    // flag kernel that is supposed to release it -- so every kernel of this library is loaded up front.
+    if ((e = preload_kernels()) != cudaSuccess) return e;
     smem[dev].store(b, std::memory_order_release);
     sm[dev].store(a, std::memory_order_release);
     s = a;
@@ -432,6 +438,30 @@ __global__ void kvbm_wait_flag_kernel(const uint32_t* flag, uint32_t value)
   while (ptx::ld_acquire_sys(flag) < value) __nanosleep(100);
 }
 
+static cudaError_t preload_kernels()
+{
+  cudaFuncAttributes attr;
+  cudaError_t e;
+#define KVBM_PRELOAD(k) \
+  if ((e = cudaFuncGetAttributes(&attr, k)) != cudaSuccess) return e;
+  KVBM_PRELOAD(kvbm_pair_copy_kernel)
+  KVBM_PRELOAD(kvbm_paged_copy_kernel<KVBM_CAST_NONE>)
+  KVBM_PRELOAD(kvbm_paged_copy_kernel<KVBM_CAST_FP8E4M3_TO_BF16>)
+  KVBM_PRELOAD(kvbm_paged_copy_kernel<KVBM_CAST_BF16_TO_FP8E4M3>)
+  KVBM_PRELOAD(kvbm_set_flags_kernel)
+  KVBM_PRELOAD(kvbm_wait_flag_kernel)
+  KVBM_PRELOAD((kvbm_permute_kernel<16, true>))
+  KVBM_PRELOAD((kvbm_permute_kernel<8, true>))
+  KVBM_PRELOAD((kvbm_permute_kernel<4, true>))
+  KVBM_PRELOAD((kvbm_permute_kernel<2, true>))
+  KVBM_PRELOAD((kvbm_permute_kernel<16, false>))
+  KVBM_PRELOAD((kvbm_permute_kernel<8, false>))
+  KVBM_PRELOAD((kvbm_permute_kernel<4, false>))
+  KVBM_PRELOAD((kvbm_permute_kernel<2, false>))
+#undef KVBM_PRELOAD
+  return cudaSuccess;
+}
+
 template <class K>
 static cudaError_t set_smem(K kernel, uint32_t bytes)
 {
@@ -651,6 +681,9 @@ kvbm_kernels_set_flags(uint32_t* flags, int first, int count, uint32_t value, cu
 {
   if (count == 0) return cudaSuccess;
   if (!flags || count < 0 || first < 0) return cudaErrorInvalidValue;
+  DeviceInfo di;
+  cudaError_t e = device_info(&di);
+  if (e != cudaSuccess) return e;
   kvbm_set_flags_kernel<<<(count + 127) / 128, 128, 0, stream>>>(flags, first, count, value);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
@@ -660,6 +693,9 @@ extern "C" cudaError_t
 kvbm_kernels_wait_flag(const uint32_t* flag, uint32_t value, cudaStream_t stream)
 {
   if (!flag) return cudaErrorInvalidValue;
+  DeviceInfo di;
+  cudaError_t e = device_info(&di);
+  if (e != cudaSuccess) return e;
   kvbm_wait_flag_kernel<<<1, 1, 0, stream>>>(flag, value);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
