@@ -44,18 +44,25 @@ def main():
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--inner", type=int, default=1024)
     ap.add_argument("--out", default="gpurun_out/sweep.json")
+    ap.add_argument("--peer", action="store_true", help="destination pool on cuda:1 (NVLink peer stores)")
     a = ap.parse_args()
     torch.cuda.set_device(0)
+    ddev = "cuda:0"
+    if a.peer:
+        from dynamo_b200.physical import TransferManager
+        _m = TransferManager(device=0)
+        _m.enable_peer_access(1)
+        ddev = "cuda:1"
     nl, nbp, n = a.layers, a.pool, a.blocks
     region = 16 * a.inner * 2
 
-    def pool():
-        bufs = [torch.empty(2 * nbp * region, dtype=torch.uint8, device="cuda") for _ in range(nl)]
-        base = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    def pool(dev="cuda:0"):
+        bufs = [torch.empty(2 * nbp * region, dtype=torch.uint8, device=dev) for _ in range(nl)]
+        base = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda:0")
         return bufs, base, K.PagedLayout(base.data_ptr(), region, region * nbp, region, nl, 2, nbp)
 
     sb, sbase, src = pool()
-    db, dbase, dst = pool()
+    db, dbase, dst = pool(ddev)
     for t in sb:
         t.random_(0, 256)
     sid = torch.from_numpy(np.random.default_rng(0).permutation(nbp)[:n].astype(np.int32)).cuda()
@@ -66,8 +73,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     results = []
 
-    big_a = torch.empty(bytes_moved, dtype=torch.uint8, device="cuda")
-    big_b = torch.empty(bytes_moved, dtype=torch.uint8, device="cuda")
+    big_a = torch.empty(bytes_moved, dtype=torch.uint8, device="cuda:0")
+    big_b = torch.empty(bytes_moved, dtype=torch.uint8, device=ddev)
     med, best = timed(lambda: big_b.copy_(big_a), flush=flush)
     results.append(dict(name="torch.copy_", ms=med, gbs_rw=2 * bytes_moved / med / 1e6))
     print(results[-1], flush=True)
@@ -83,6 +90,13 @@ def main():
         (4, 3, 1, 16384, 0, 0, 3), (4, 3, 2, 16384, 0, 0, 3), (4, 6, 3, 8192, 0, 0, 3), (4, 6, 5, 8192, 0, 0, 3), (8, 3, 2, 8192, 0, 0, 3),
         (4, 3, 1, 16384, 74, 0, 0), (4, 3, 1, 16384, 32, 0, 0), (4, 3, 1, 16384, 16, 0, 0), (8, 3, 1, 8192, 16, 0, 1),
     ]
+    if a.peer:   # NVLink-bound: how few SMs saturate the link, and how many stores must be in flight
+        cfgs = [(4, 3, 1, 16384, 0, 0, 0), (4, 6, 3, 8192, 0, 0, 0), (4, 6, 5, 8192, 0, 0, 0), (2, 6, 4, 16384, 0, 0, 0),
+                (4, 3, 1, 16384, 0, 0, 1), (8, 3, 1, 8192, 0, 0, 1),
+                (4, 3, 1, 16384, 74, 0, 0), (4, 3, 1, 16384, 32, 0, 0), (4, 3, 1, 16384, 16, 0, 0), (4, 3, 1, 16384, 8, 0, 0),
+                (4, 6, 4, 8192, 32, 0, 0), (4, 6, 4, 8192, 16, 0, 0), (4, 6, 4, 8192, 8, 0, 0), (2, 6, 4, 16384, 16, 0, 0),
+                (2, 6, 4, 16384, 8, 0, 0), (4, 12, 10, 4096, 16, 0, 0), (8, 3, 1, 8192, 16, 0, 1), (8, 3, 1, 8192, 32, 0, 1),
+                (4, 3, 2, 16384, 16, 0, 0), (1, 6, 4, 32768, 16, 0, 0), (1, 6, 4, 32768, 32, 0, 0)]
     for warps, stages, pend, tile, ctas, hint, variant in cfgs:
         opts = K.PagedCopyOpts(warps_per_cta=warps, stages=stages, tile_bytes=tile, max_ctas=ctas, stores_in_flight=pend,
                                cache_hint=hint, variant=variant)
