@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--inner", type=int, default=1024)
     ap.add_argument("--out", default="gpurun_out/sweep.json")
     ap.add_argument("--peer", action="store_true", help="destination pool on cuda:1 (NVLink peer stores)")
+    ap.add_argument("--fine", action="store_true", help="second-round sweep: CTA count x ring shape x L2 hints")
     a = ap.parse_args()
     torch.cuda.set_device(0)
     ddev = "cuda:0"
@@ -90,6 +91,13 @@ def main():
         (4, 3, 1, 16384, 0, 0, 3), (4, 3, 2, 16384, 0, 0, 3), (4, 6, 3, 8192, 0, 0, 3), (4, 6, 5, 8192, 0, 0, 3), (8, 3, 2, 8192, 0, 0, 3),
         (4, 3, 1, 16384, 74, 0, 0), (4, 3, 1, 16384, 32, 0, 0), (4, 3, 1, 16384, 16, 0, 0), (8, 3, 1, 8192, 16, 0, 1),
     ]
+    if a.fine:
+        cfgs = []
+        for shape in [(4, 3, 1, 16384), (4, 6, 3, 8192), (2, 3, 1, 32768), (8, 3, 1, 8192), (2, 6, 3, 16384), (4, 4, 2, 8192)]:
+            for ctas in (64, 74, 96, 111, 128, 148):
+                cfgs.append((*shape, ctas, 0, 0))
+        for hint in (1, 2, 3):
+            cfgs += [(4, 3, 1, 16384, 74, hint, 0), (4, 3, 1, 16384, 148, hint, 0), (2, 3, 1, 32768, 74, hint, 0)]
     if a.peer:   # NVLink-bound: how few SMs saturate the link, and how many stores must be in flight
         cfgs = [(4, 3, 1, 16384, 0, 0, 0), (4, 6, 3, 8192, 0, 0, 0), (4, 6, 5, 8192, 0, 0, 0), (2, 6, 4, 16384, 0, 0, 0),
                 (4, 3, 1, 16384, 0, 0, 1), (8, 3, 1, 8192, 0, 0, 1),

@@ -462,6 +462,29 @@ static cudaError_t preload_kernels()
   return cudaSuccess;
 }
 
+// Stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32) through the driver entry point:
+// the stream's front-end writes / polls the word itself -- no kernel launch, no SM occupied by a spinner.
+typedef int (*stream_memop_fn)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
+static stream_memop_fn g_write32 = nullptr, g_wait32 = nullptr;
+static std::atomic<int> g_memops_state{0};  // 0 unknown, 1 available, -1 unavailable
+
+static bool stream_memops()
+{
+  int st = g_memops_state.load(std::memory_order_acquire);
+  if (st == 0) {
+    void *w = nullptr, *q = nullptr;
+    cudaDriverEntryPointQueryResult r1, r2;
+    bool ok = cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &r1) == cudaSuccess && w &&
+              cudaGetDriverEntryPoint("cuStreamWaitValue32", &q, cudaEnableDefault, &r2) == cudaSuccess && q;
+    (void)cudaGetLastError();
+    g_write32 = reinterpret_cast<stream_memop_fn>(w);
+    g_wait32 = reinterpret_cast<stream_memop_fn>(q);
+    st = ok ? 1 : -1;
+    g_memops_state.store(st, std::memory_order_release);
+  }
+  return st == 1;
+}
+
 template <class K>
 static cudaError_t set_smem(K kernel, uint32_t bytes)
 {
@@ -684,6 +707,10 @@ kvbm_kernels_set_flags(uint32_t* flags, int first, int count, uint32_t value, cu
   DeviceInfo di;
   cudaError_t e = device_info(&di);
   if (e != cudaSuccess) return e;
+  if (count == 1 && stream_memops()) {
+    // CU_STREAM_WRITE_VALUE_DEFAULT (0): memory fence before the write => release semantics for prior work
+    if (g_write32(stream, reinterpret_cast<unsigned long long>(flags + first), value, 0) == 0) return cudaSuccess;
+  }
   kvbm_set_flags_kernel<<<(count + 127) / 128, 128, 0, stream>>>(flags, first, count, value);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
@@ -696,6 +723,10 @@ kvbm_kernels_wait_flag(const uint32_t* flag, uint32_t value, cudaStream_t stream
   DeviceInfo di;
   cudaError_t e = device_info(&di);
   if (e != cudaSuccess) return e;
+  if (stream_memops()) {
+    // CU_STREAM_WAIT_VALUE_GEQ (0): wait until (int32)(*flag - value) >= 0
+    if (g_wait32(stream, reinterpret_cast<unsigned long long>(flag), value, 0) == 0) return cudaSuccess;
+  }
   kvbm_wait_flag_kernel<<<1, 1, 0, stream>>>(flag, value);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
