@@ -177,10 +177,16 @@ def run_reference(args):
     return 0
 
 
+TOPOLOGY = "fanout"
+
+
 def workload_config(n_gpus, where="hbm"):
+    topo = ("same-GPU gather->scatter" if n_gpus == 1 else
+            f"{n_gpus // 2} x (1 prefill -> 1 decode) rank pairs (NVLink peer stores via CUDA IPC mappings)" if TOPOLOGY == "pairs" else
+            f"1 prefill -> {n_gpus - 1} decode GPUs (NVLink peer stores via CUDA IPC mappings)")
     return {"workload": f"{MODEL_NAME} KV hand-off, {CTX_TOKENS // 1024}k ctx, block_size={PAGE}: {N_BLOCKS} blocks x {NL} layers x K/V x "
                         f"{REGION // 1024} KiB = {BYTES_PER_DST / 2**20:.0f} MiB per destination" + (" (identical payload to every destination)" if REPLICATE else ""),
-            "topology": "same-GPU gather->scatter" if n_gpus == 1 else f"1 prefill -> {n_gpus - 1} decode GPUs (NVLink peer stores via CUDA IPC mappings)",
+            "topology": topo,
             "layout": "LayerSeparate/BlockIsSecondDim (vLLM [2,num_blocks,16,8,128] per layer)",
             "pool_blocks": POOL_BLOCKS if where == "hbm" else 512,
             "block_tables": "random permutation (seeded), non-contiguous on both sides",
@@ -223,9 +229,14 @@ def run_ours(args):
     cfg = LayoutConfig(POOL_BLOCKS, NL, OUTER, PAGE, INNER, dtype_width_bytes=DTYPE_BYTES)
     src_cfg = cfg if not CAST else LayoutConfig(POOL_BLOCKS, NL, OUTER, PAGE, INNER, dtype_width_bytes=1, allow_fp8=True)
     mgr = TransferManager(device=local, worker_id=rank + 1)
-    n_dst = max(1, world - 1)
-    is_src = rank == 0
-    is_dst = (world == 1) or rank >= 1
+    from dynamo_b200.disagg import assign_roles
+    roles = assign_roles(world, args.topology)
+    is_src = roles.is_source(rank)
+    is_dst = roles.is_destination(rank)
+    my_dsts = roles.destinations.get(rank, [])          # destination ranks this rank pushes to
+    n_dst = len(roles.destinations[roles.sources[0]])   # destinations per source (same for every source)
+    n_src = len(roles.sources)
+    my_dst_index = roles.destinations[roles.source_of(rank)].index(rank) if is_dst else -1
 
     def register(bufs, c=None):
         return mgr.register_layer_separate(c or cfg, [b.data_ptr() for b in bufs], [b.numel() for b in bufs],
@@ -255,8 +266,8 @@ def run_ours(args):
         blobs = [None] * world
         dist.all_gather_object(blobs, (my_blob, my_flag_blob))
         if is_src:
-            h_dsts = [mgr.import_metadata(blobs[r][0]) for r in range(1, world)]
-            peer_flags = [mgr.memory_region(mgr.import_metadata(blobs[r][1]), 0, 0, 0)[0] for r in range(1, world)]
+            h_dsts = [mgr.import_metadata(blobs[r][0]) for r in my_dsts]
+            peer_flags = [mgr.memory_region(mgr.import_metadata(blobs[r][1]), 0, 0, 0)[0] for r in my_dsts]
     else:
         h_dsts = [h_dst_local]
         peer_flags = [flag_buf.data_ptr()]
@@ -377,6 +388,8 @@ def run_ours(args):
                     hs.update(src_bufs[l].view(OUTER, POOL_BLOCKS, REGION)[o, int(sids[d][7])].cpu().numpy().tobytes())
                     hd.update(dst_bufs[l].view(OUTER, POOL_BLOCKS, REGION)[o, int(dids[d][7])].cpu().numpy().tobytes())
             ok = ok and hs.hexdigest() == hd.hexdigest()
+    elif n_src > 1:
+        pass   # pairs topology: data checks live in tests/test_gpu_multi.py; every source uses the same seeds here
     else:
         # every destination checks one block against bytes re-generated from the source's seed
         if is_src:
@@ -387,7 +400,7 @@ def run_ours(args):
         box = [probe]
         dist.broadcast_object_list(box, src=0)
         if not is_src:
-            d = rank - 1
+            d = my_dst_index
             mine = [dst_bufs[l].view(OUTER, POOL_BLOCKS, REGION)[:, int(dids[d][7])].sum(dtype=torch.int64).item() for l in (0, NL - 1)]
             ok = mine == box[0][d]
         flag = torch.tensor([1 if ok else 0], device=dev)
@@ -395,7 +408,7 @@ def run_ours(args):
         ok = bool(flag.item())
 
     if rank == 0:
-        total_dst_bytes = BYTES_PER_DST * n_dst
+        total_dst_bytes = BYTES_PER_DST * n_dst * n_src
         ms_per_step = value_ms_total / K_steps
         value = total_dst_bytes / (ms_per_step * 1e-3) / 1e9
         e2e_ms = 1e3 * float(wall.item()) / K_steps
@@ -407,9 +420,10 @@ def run_ours(args):
                     "frac": round(alg / (ms_per_step * 1e-3) / 1e9 / peak, 4), "traffic": ncu_traffic(), "peak_source": peak_src,
                     "kernel": f"kvbm_paged_copy_kernel<{CAST}>", "algorithmic_bytes_per_launch": alg}
         else:
-            alg = total_dst_bytes     # NVLink egress of the source GPU
-            roof = {"bound": "nvlink", "achieved": round(value, 2), "peak": NVLINK_PEER_GBS, "unit": "GB/s",
-                    "frac": round(value / NVLINK_PEER_GBS, 4), "traffic": None,
+            alg = total_dst_bytes // n_src     # NVLink egress of ONE source GPU per launch
+            per_src = value / n_src
+            roof = {"bound": "nvlink", "achieved": round(per_src, 2), "peak": NVLINK_PEER_GBS, "unit": "GB/s",
+                    "frac": round(per_src / NVLINK_PEER_GBS, 4), "traffic": None, "sources": n_src,
                     "peak_source": "measured peer copy 770 GB/s per direction (B200_PROFILING.md); nominal 900",
                     "kernel": "kvbm_paged_copy_kernel<0>", "algorithmic_bytes_per_launch": alg,
                     "hbm_read_gbs_source": round((BYTES_PER_DST * SRC_REGION // REGION) * (1 if REPLICATE else n_dst) / (ms_per_step * 1e-3) / 1e9, 2)}
@@ -488,8 +502,12 @@ def main():
     ap.add_argument("--cast", default="none", choices=["none", "fp8"])
     ap.add_argument("--replicate", action="store_true", help="same blocks to every destination (CollectiveOps::broadcast)")
     ap.add_argument("--pool-blocks", type=int, default=0)
+    ap.add_argument("--topology", default="fanout", choices=["fanout", "pairs"],
+                    help="fanout: rank 0 -> ranks 1..N-1 (default); pairs: rank r -> rank r+N/2 (TP-sharded prefill -> decode)")
     args = ap.parse_args()
     configure(args)
+    global TOPOLOGY
+    TOPOLOGY = args.topology
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         return run_reference(args)

@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--inner", type=int, default=1024)
     ap.add_argument("--out", default="gpurun_out/sweep.json")
     ap.add_argument("--peer", action="store_true", help="destination pool on cuda:1 (NVLink peer stores)")
+    ap.add_argument("--pull", action="store_true", help="with --peer: SOURCE pool on cuda:1, kernel on cuda:0 reads over NVLink")
     ap.add_argument("--fine", action="store_true", help="second-round sweep: CTA count x ring shape x L2 hints")
     a = ap.parse_args()
     torch.cuda.set_device(0)
@@ -62,8 +63,8 @@ def main():
         base = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda:0")
         return bufs, base, K.PagedLayout(base.data_ptr(), region, region * nbp, region, nl, 2, nbp)
 
-    sb, sbase, src = pool()
-    db, dbase, dst = pool(ddev)
+    sb, sbase, src = pool(ddev if a.pull else "cuda:0")
+    db, dbase, dst = pool("cuda:0" if a.pull else ddev)
     for t in sb:
         t.random_(0, 256)
     sid = torch.from_numpy(np.random.default_rng(0).permutation(nbp)[:n].astype(np.int32)).cuda()
