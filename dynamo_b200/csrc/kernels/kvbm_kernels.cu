@@ -263,7 +263,6 @@ struct PagedSyncArgs {
   uint32_t* completion_flag;
   uint32_t completion_value;
   uint32_t epoch;
-  int any;
   int num_layers_total;
 };
 
@@ -645,10 +644,8 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
     if (D.src_block_ids != dsts[0].src_block_ids) gen.a.replicate = 0;
     sync.done_flag[d] = D.done_flag;
     sync.layer_done[d] = D.layer_done_flags;
-    if (D.done_flag || D.layer_done_flags) sync.any = 1;
   }
   if (num_dsts == 1) gen.a.replicate = 1;
-  if (o.layer_ready_flags || o.completion_flag) sync.any = 1;
   sync.completion_flag = o.completion_flag;
   sync.completion_value = o.completion_value;
   sync.layer_ready = o.layer_ready_flags;
