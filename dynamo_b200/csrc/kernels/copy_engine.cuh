@@ -108,10 +108,13 @@ struct RingParams {
                       // 2 = loads only (diagnostic), 3 = stores only (diagnostic)
 };
 
+// Flag polls are relaxed loads; one acquire fence follows a successful probe (an ld.acquire.sys per poll would
+// invalidate L1 every time and, measured, slowed the co-resident compute kernel).
 __device__ __forceinline__ void wait_layer_ready(const StreamSync& ss, int layer, int lane)
 {
   if (lane == 0) {
-    while (ptx::ld_acquire_sys(ss.layer_ready + layer) < ss.epoch) __nanosleep(64);
+    while (ptx::ld_relaxed_sys(ss.layer_ready + layer) < ss.epoch) __nanosleep(128);
+    ptx::fence_acq_rel_sys();
   }
   __syncwarp();
 }
@@ -120,7 +123,10 @@ __device__ __forceinline__ void wait_layer_ready(const StreamSync& ss, int layer
 __device__ __forceinline__ bool layer_is_ready(const StreamSync& ss, int layer, int lane)
 {
   uint32_t v = 0;
-  if (lane == 0) v = ptx::ld_acquire_sys(ss.layer_ready + layer);
+  if (lane == 0) {
+    v = ptx::ld_relaxed_sys(ss.layer_ready + layer);
+    if (v >= ss.epoch) ptx::fence_acq_rel_sys();
+  }
   v = __shfl_sync(0xffffffffu, v, 0);
   return v >= ss.epoch;
 }
@@ -133,7 +139,7 @@ __device__ __forceinline__ void arrive_layers(const StreamSync& ss, int from, in
     uint32_t old = ptx::atom_add_acq_rel_gpu(ss.workspace + l, 1u);
     if (old == ss.total_warps - 1) {
       ss.workspace[l] = 0;  // leave the workspace zeroed for the next launch
-      __threadfence_system();
+      ptx::fence_acq_rel_sys();  // once per layer for the whole grid: everything acquired above is released below
 #pragma unroll
       for (int d = 0; d < kMaxDst; ++d)
         if (d < ss.ndst && ss.layer_done[d] != nullptr) ptx::st_release_sys(ss.layer_done[d] + l, ss.epoch);
@@ -147,7 +153,7 @@ __device__ __forceinline__ void arrive_transfer(const StreamSync& ss, int lane)
   uint32_t old = ptx::atom_add_acq_rel_gpu(ss.workspace + ss.num_layers, 1u);
   if (old == ss.total_warps - 1) {
     ss.workspace[ss.num_layers] = 0;
-    __threadfence_system();
+    ptx::fence_acq_rel_sys();
 #pragma unroll
     for (int d = 0; d < kMaxDst; ++d)
       if (d < ss.ndst && ss.done_flag[d] != nullptr) ptx::st_release_sys(ss.done_flag[d], ss.epoch);
@@ -155,14 +161,16 @@ __device__ __forceinline__ void arrive_transfer(const StreamSync& ss, int lane)
   }
 }
 
-// every store this warp issued so far has landed (and is ordered before a following flag write)
+// Every store this warp issued so far has landed and is ordered before the arrive that follows:
+// lane 0 waits for its bulk groups and crosses the async->generic proxy; __syncwarp orders the other lanes'
+// SIMT stores before lane 0's release atomic (which is cumulative).  No per-lane MEMBAR.SYS: on an SM shared
+// with a compute kernel those stalled both kernels.
 __device__ __forceinline__ void drain_stores(int lane)
 {
   if (lane == 0) {
     ptx::bulk_wait<0>();
     ptx::fence_proxy_async_global();
   }
-  __threadfence_system();  // SIMT stores of any lane
   __syncwarp();
 }
 

@@ -147,6 +147,18 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// polling load: no L1 invalidation / fence per probe (ld.acquire.sys costs a CCTL.IVALL each time); pair a
+// successful probe with fence_acq_rel_sys() once
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys()
+{
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t atom_add_acq_rel_gpu(uint32_t* p, uint32_t v)
 {
   uint32_t old;
