@@ -51,6 +51,8 @@ static cudaError_t device_info(DeviceInfo* out)
   return cudaSuccess;
 }
 
+static int default_ctas(const DeviceInfo& di) { return (di.sm_count + 1) / 2; }
+
 // Ring geometry of one launch.
 struct RingCfg {
   int warps;        // W
@@ -516,7 +518,7 @@ kvbm_kernels_launch_vectorized_copy(void** src_ptrs, void** dst_ptrs, size_t cop
 
   PairGen gen{src_ptrs, dst_ptrs, copy_size_bytes, static_cast<uint32_t>(tiles_per_pair), rc.tile};
   const uint64_t ctas_needed = (total + rc.warps - 1) / rc.warps;
-  const int grid = static_cast<int>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(di.sm_count)));
+  const int grid = static_cast<int>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(default_ctas(di))));
   if ((e = set_smem(kvbm_pair_copy_kernel, rc.smem)) != cudaSuccess) return e;
   kvbm_pair_copy_kernel<<<grid, rc.warps * 32, rc.smem, stream>>>(gen, static_cast<uint32_t>(total), rc.stages,
                                                                  rc.pending, rc.tile, 1);
@@ -676,7 +678,10 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   if (total >= (1ull << 32)) return cudaErrorInvalidValue;
 
   const uint64_t ctas_needed = (total + rc.warps - 1) / rc.warps;
-  int cap = o.max_ctas > 0 ? o.max_ctas : di.sm_count;
+  // Default: one CTA per TPC (half the SMs).  Measured on B200 (profiles/r01_sweep_n1_fine.json): 74 CTAs x 4 warps
+  // move 5.96 TB/s r+w on a same-GPU copy vs 5.70 with 148, and 32 CTAs already saturate NVLink -- and the other
+  // half of the chip stays free for whatever the engine is running.
+  int cap = o.max_ctas > 0 ? o.max_ctas : default_ctas(di);
   const int grid = static_cast<int>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(cap)));
   const int allow_tma = o.force_simt ? 0 : 1;
   const uint32_t total32 = static_cast<uint32_t>(total);

@@ -120,7 +120,7 @@ typedef struct kvbm_paged_copy_opts {
   uint32_t epoch;                 /* value written to done flags / compared with ready flags (>=) */
   const uint32_t* layer_ready_flags; /* nullable; [num_layers]; layer l is read only after flag >= epoch */
   uint32_t* sync_workspace;       /* device u32[num_layers + 1], zeroed; required iff any done/completion flag is used */
-  int max_ctas;                   /* 0 = one CTA per SM; smaller values leave SMs to the attention kernel */
+  int max_ctas;                   /* 0 = default (one CTA per TPC = #SM/2, the measured optimum); smaller values leave more SMs to the engine */
   int warps_per_cta;              /* 0 = default */
   int stages;                     /* 0 = default */
   int tile_bytes;                 /* 0 = default */
