@@ -30,6 +30,10 @@ ap.add_argument("--pool", type=int, default=2048)
 ap.add_argument("--layer-us", type=float, default=40.0)
 ap.add_argument("--ctas", type=int, default=16)
 ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--standin-blocks", type=int, default=148 * 4)
+ap.add_argument("--warps", type=int, default=0)
+ap.add_argument("--stages", type=int, default=0)
+ap.add_argument("--tile", type=int, default=0)
 ap.add_argument("--out", default="gpurun_out/overlap.json")
 a = ap.parse_args()
 
@@ -74,7 +78,7 @@ SL = C.CDLL(_standin_path)
 SL.standin_attention_layer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]
 counter = torch.zeros(1, dtype=torch.int32, device="cuda:0")
 n_vec = work_bytes // 16
-standin_blocks = 148 * 6   # leaves thread slots for the 128-thread transfer CTAs: a grid that exactly fills the chip gets a second wave when anything else is resident
+standin_blocks = a.standin_blocks   # keep it well below a full wave: a grid that exactly fills the chip gets a second wave when anything else is resident
 
 
 def compute_layer(flag_ptr=0, value=0):
@@ -113,14 +117,15 @@ def compute_and_signal():   # the producer-side cost of releasing layers, withou
 
 def transfer_only(ctas):
     d = K.PagedDst(dst, sid.data_ptr(), did.data_ptr(), 0, 0)
-    K.check(K.paged_copy(src, [d], n, 0, nl, 0, K.PagedCopyOpts(max_ctas=ctas), mp))
+    K.check(K.paged_copy(src, [d], n, 0, nl, 0, K.PagedCopyOpts(max_ctas=ctas, warps_per_cta=a.warps, stages=a.stages, tile_bytes=a.tile), mp))
 
 
 def overlapped_ours():
     epoch[0] += 1
     e = epoch[0]
     d = K.PagedDst(dst, sid.data_ptr(), did.data_ptr(), 0, done.data_ptr())
-    opts = K.PagedCopyOpts(epoch=e, layer_ready_flags=ready.data_ptr(), sync_workspace=ws.data_ptr(), max_ctas=a.ctas)
+    opts = K.PagedCopyOpts(epoch=e, layer_ready_flags=ready.data_ptr(), sync_workspace=ws.data_ptr(), max_ctas=a.ctas,
+                           warps_per_cta=a.warps, stages=a.stages, tile_bytes=a.tile)
     side.wait_stream(main)
     K.check(K.paged_copy(src, [d], n, 0, nl, 0, opts, sp))
     for l in range(nl):
@@ -140,7 +145,8 @@ def overlapped_ours_events():
     epoch[0] += 1
     e = epoch[0]
     d = K.PagedDst(dst, sid.data_ptr(), did.data_ptr(), 0, done.data_ptr())
-    opts = K.PagedCopyOpts(epoch=e, layer_ready_flags=ready.data_ptr(), sync_workspace=ws.data_ptr(), max_ctas=a.ctas)
+    opts = K.PagedCopyOpts(epoch=e, layer_ready_flags=ready.data_ptr(), sync_workspace=ws.data_ptr(), max_ctas=a.ctas,
+                           warps_per_cta=a.warps, stages=a.stages, tile_bytes=a.tile)
     side.wait_stream(main)
     K.check(K.paged_copy(src, [d], n, 0, nl, 0, opts, sp))
     for l in range(nl):
@@ -156,7 +162,8 @@ def overlapped_ours_prereleased():
     epoch[0] += 1
     e = epoch[0]
     d = K.PagedDst(dst, sid.data_ptr(), did.data_ptr(), 0, done.data_ptr())
-    opts = K.PagedCopyOpts(epoch=e, layer_ready_flags=ready.data_ptr(), sync_workspace=ws.data_ptr(), max_ctas=a.ctas)
+    opts = K.PagedCopyOpts(epoch=e, layer_ready_flags=ready.data_ptr(), sync_workspace=ws.data_ptr(), max_ctas=a.ctas,
+                           warps_per_cta=a.warps, stages=a.stages, tile_bytes=a.tile)
     K.check(K.set_flags(ready.data_ptr(), 0, nl, e, mp))
     side.wait_stream(main)
     K.check(K.paged_copy(src, [d], n, 0, nl, 0, opts, sp))
@@ -190,7 +197,7 @@ def transfer_only_ref():
         assert R.kvbm_kernels_launch_vectorized_copy(ptr_s[l].data_ptr(), ptr_d[l].data_ptr(), region, 2 * n, mp) == 0
 
 
-res = {"peer": peer, "layers": nl, "region": region, "blocks": n, "bytes": n * nl * 2 * region, "ctas": a.ctas, "layer_us_target": a.layer_us}
+res = {"standin_blocks": standin_blocks, "ring": [a.warps, a.stages, a.tile], "peer": peer, "layers": nl, "region": region, "blocks": n, "bytes": n * nl * 2 * region, "ctas": a.ctas, "layer_us_target": a.layer_us}
 res["t_compute_ms"] = t_ms(compute_only, a.iters)
 res["t_compute_plus_signals_ms"] = t_ms(compute_and_signal, a.iters)
 res["t_transfer_full_chip_ms"] = t_ms(lambda: transfer_only(0), a.iters)

@@ -681,7 +681,7 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   // Default: one CTA per TPC (half the SMs).  Measured on B200 (profiles/r01_sweep_n1_fine.json): 74 CTAs x 4 warps
   // move 5.96 TB/s r+w on a same-GPU copy vs 5.70 with 148, and 32 CTAs already saturate NVLink -- and the other
   // half of the chip stays free for whatever the engine is running.
-  int cap = o.max_ctas > 0 ? o.max_ctas : default_ctas(di);
+  int cap = o.max_ctas > 0 ? o.max_ctas : (cast_mode == KVBM_CAST_NONE ? default_ctas(di) : di.sm_count);  // the cast is ALU work: use every SM
   const int grid = static_cast<int>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(cap)));
   const int allow_tma = o.force_simt ? 0 : 1;
   const uint32_t total32 = static_cast<uint32_t>(total);

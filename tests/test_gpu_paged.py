@@ -267,3 +267,112 @@ def test_full_size_config2_roundtrip_property():
             h1.update(a_bufs[l].view(2, nb_pool, region)[o, int(sid[5])].cpu().numpy().tobytes())
             h2.update(b_bufs[l].view(2, nb_pool, region)[o, int(did[5])].cpu().numpy().tobytes())
     assert h1.hexdigest() == h2.hexdigest()
+
+
+# ------------------------------------------------------------------ full-size properties of the other BASELINE configs
+def _torch_pool(nl, nbp, region, fill=None, seed=0):
+    bufs = [torch.empty(2 * nbp * region, dtype=torch.uint8, device="cuda") for _ in range(nl)]
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    for t in bufs:
+        if fill is None:
+            t.copy_(torch.randint(0, 256, t.shape, dtype=torch.uint8, device="cuda", generator=g))
+        else:
+            t.fill_(fill)
+    base = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device="cuda")
+    return bufs, base, K.PagedLayout(base.data_ptr(), region, region * nbp, region, nl, 2, nbp)
+
+
+def test_full_size_config3_fp8_roundtrip_is_identity():
+    # BASELINE configs[2] at full size: 256 blocks x 32 layers x K/V, fp8 source (16 KiB regions) -> bf16 (32 KiB).
+    # Property: fp8 -> bf16 -> fp8 through the two fused-cast kernels is the identity on every non-NaN code, and NaN
+    # codes come back as NaN (0x7f | sign is not preserved by torch's up-cast: 0xff -> 0x7fc0 -> 0x7f).
+    nl, nbp, n = 32, 288, 256
+    a_bufs, a_base, a = _torch_pool(nl, nbp, 16384, seed=3)
+    b_bufs, b_base, b = _torch_pool(nl, nbp, 32768, fill=0)
+    c_bufs, c_base, c = _torch_pool(nl, nbp, 16384, fill=0)
+    sid = ids_dev(np.random.default_rng(0).permutation(nbp)[:n])
+    did = ids_dev(np.random.default_rng(1).permutation(nbp)[:n])
+    sp = stream_ptr()
+    assert K.paged_copy(a, [K.PagedDst(b, sid.data_ptr(), did.data_ptr(), 0, 0)], n, 0, nl, K.CastMode.FP8E4M3_TO_BF16, None, sp) == 0
+    assert K.paged_copy(b, [K.PagedDst(c, did.data_ptr(), sid.data_ptr(), 0, 0)], n, 0, nl, K.CastMode.BF16_TO_FP8E4M3, None, sp) == 0
+    torch.cuda.synchronize()
+    rows = sid.long()
+    for l in (0, 7, nl - 1):
+        av = a_bufs[l].view(2, nbp, 16384)[:, rows]
+        cv = c_bufs[l].view(2, nbp, 16384)[:, rows]
+        nan = (av & 0x7F) == 0x7F
+        assert torch.equal(cv[~nan], av[~nan])
+        assert bool(((cv[nan] & 0x7F) == 0x7F).all())
+    # and one region against the torch-generated table
+    table = torch.from_numpy(np.load(os.path.join(GOLD, "fp8_e4m3_to_bf16_torch.npy")).astype(np.int32)).cuda()
+    src_codes = a_bufs[5].view(2, nbp, 16384)[1, int(sid[9])].long()
+    got = b_bufs[5].view(2, nbp, 32768)[1, int(did[9])].view(torch.int16).int() & 0xFFFF
+    assert torch.equal(got, table[src_codes])
+
+
+def test_full_size_config4_layer_stream_equals_one_shot():
+    # BASELINE configs[3] per rank: Llama-3-70B TP4 shard, 80 layers, 8 KiB regions, 256 blocks = 320 MiB.
+    # Property: 80 single-layer transfers (layer_range = l..l+1, the reference's streaming pattern) compose to exactly
+    # the one-shot transfer, which itself equals a gather by index.
+    nl, nbp, n, region = 80, 320, 256, 8192
+    s_bufs, s_base, s = _torch_pool(nl, nbp, region, seed=4)
+    one_bufs, one_base, one = _torch_pool(nl, nbp, region, fill=0)
+    lay_bufs, lay_base, lay = _torch_pool(nl, nbp, region, fill=0)
+    sid_np = np.random.default_rng(2).permutation(nbp)[:n]
+    did_np = np.random.default_rng(3).permutation(nbp)[:n]
+    sid, did = ids_dev(sid_np), ids_dev(did_np)
+    sp = stream_ptr()
+    assert K.paged_copy(s, [K.PagedDst(one, sid.data_ptr(), did.data_ptr(), 0, 0)], n, 0, nl, 0, None, sp) == 0
+    for l in range(nl):
+        assert K.paged_copy(s, [K.PagedDst(lay, sid.data_ptr(), did.data_ptr(), 0, 0)], n, l, l + 1, 0, None, sp) == 0
+    torch.cuda.synchronize()
+    for l in range(nl):
+        assert torch.equal(one_bufs[l], lay_bufs[l])
+    for l in (0, 39, 79):
+        assert torch.equal(one_bufs[l].view(2, nbp, region)[:, did.long()], s_bufs[l].view(2, nbp, region)[:, sid.long()])
+    untouched = torch.ones(nbp, dtype=torch.bool, device="cuda")
+    untouched[did.long()] = False
+    assert not one_bufs[11].view(2, nbp, region)[:, untouched].any()
+
+
+def test_full_size_config5_16k_ctx_fanout_and_checksum_of_checksums():
+    # BASELINE configs[4] shape at 16 k ctx: 1024 blocks x 32 layers x K/V x 32 KiB = 2 GiB, replicated to 2 pools in
+    # one launch.  Property: the wrapping 64-bit lane sum over every moved region is permutation-invariant -> equal on source and both
+    # destinations (a checksum of checksums), plus exact equality on sampled layers.
+    nl, nbp, n, region = 32, 1100, 1024, 32768
+    s_bufs, _, s = _torch_pool(nl, nbp, region, seed=5)
+    d0_bufs, _, d0 = _torch_pool(nl, nbp, region, fill=0)
+    d1_bufs, _, d1 = _torch_pool(nl, nbp, region, fill=0)
+    sid = ids_dev(np.random.default_rng(7).permutation(nbp)[:n])
+    da = ids_dev(np.random.default_rng(8).permutation(nbp)[:n])
+    db = ids_dev(np.random.default_rng(9).permutation(nbp)[:n])
+    dsts = [K.PagedDst(d0, sid.data_ptr(), da.data_ptr(), 0, 0), K.PagedDst(d1, sid.data_ptr(), db.data_ptr(), 0, 0)]
+    assert K.paged_copy(s, dsts, n, 0, nl, 0, None, stream_ptr()) == 0
+    torch.cuda.synchronize()
+
+    def fold(bufs, rows):
+        acc = torch.zeros(region // 8, dtype=torch.int64, device="cuda")
+        for t in bufs:
+            v = t.view(2, nbp, region)[:, rows].reshape(-1, region // 8, 8).view(torch.int64).reshape(-1, region // 8)
+            acc += v.sum(0)   # wrapping int64 sum of every 8-byte lane: independent of block order
+        return acc
+    ref = fold(s_bufs, sid.long())
+    assert torch.equal(fold(d0_bufs, da.long()), ref)
+    assert torch.equal(fold(d1_bufs, db.long()), ref)
+    for l in (0, 31):
+        assert torch.equal(d0_bufs[l].view(2, nbp, region)[:, da.long()], s_bufs[l].view(2, nbp, region)[:, sid.long()])
+        assert torch.equal(d1_bufs[l].view(2, nbp, region)[:, db.long()], s_bufs[l].view(2, nbp, region)[:, sid.long()])
+
+
+def test_edge_geometries_single_block_many_layers_and_tiny_regions():
+    # ragged / extreme shapes: one block, 200 layers, 16-byte regions; 1 layer, outer 1; region just over one tile
+    for geom, nb, ids in [(dict(nl=200, no=2, page=1, inner=8, dt=2), 3, ([2], [0])),
+                          (dict(nl=1, no=1, page=16, inner=1024, dt=2), 5, ([0, 4, 2], [1, 3, 0])),
+                          (dict(nl=2, no=2, page=16, inner=520, dt=2), 6, ([5, 1], [0, 2]))]:
+        src_h = make_layout(O.LW, nb, block_dim=O.BLOCK_IS_SECOND_DIM, **geom)
+        dst_h = make_layout(O.LW, nb, block_dim=O.BLOCK_IS_SECOND_DIM, **geom)
+        randomize(src_h, 41)
+        randomize(dst_h, 42)
+        src_p, dst_p = DevicePool(src_h), DevicePool(dst_h)
+        assert run_paged(src_p, [dst_p], [ids[0]], [ids[1]]) == 0
+        check_against_oracle(src_h, dst_h, dst_p, ids[0], ids[1])
