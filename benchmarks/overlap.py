@@ -31,6 +31,7 @@ ap.add_argument("--layer-us", type=float, default=40.0)
 ap.add_argument("--ctas", type=int, default=16)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--standin-blocks", type=int, default=148 * 4)
+ap.add_argument("--fma", type=int, default=0, help="dependent FMA pairs per 16 B: >0 makes the stand-in compute-bound instead of HBM-saturating")
 ap.add_argument("--warps", type=int, default=0)
 ap.add_argument("--stages", type=int, default=0)
 ap.add_argument("--tile", type=int, default=0)
@@ -68,14 +69,14 @@ side = torch.cuda.Stream(priority=-1)   # the persistent transfer CTAs should wi
 mp, sp = int(main.cuda_stream), int(side.cuda_stream)
 
 # stand-in attention: copy sized to take ~layer-us at ~6 TB/s r+w
-work_bytes = int(a.layer_us * 1e-6 * 5.0e12 / 2)
+work_bytes = int(a.layer_us * 1e-6 * 5.0e12 / 2) if a.fma == 0 else int(a.layer_us * 1e-6 * 5.0e12 / 2 / max(1.0, a.fma / 24.0))
 wa = torch.empty(work_bytes, dtype=torch.uint8, device="cuda:0")
 wb = torch.empty_like(wa)
 
 
 _standin_path = os.path.join(ROOT, "benchmarks", "libstandin.so")
 SL = C.CDLL(_standin_path)
-SL.standin_attention_layer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]
+SL.standin_attention_layer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
 counter = torch.zeros(1, dtype=torch.int32, device="cuda:0")
 n_vec = work_bytes // 16
 standin_blocks = a.standin_blocks   # keep it well below a full wave: a grid that exactly fills the chip gets a second wave when anything else is resident
@@ -84,7 +85,7 @@ standin_blocks = a.standin_blocks   # keep it well below a full wave: a grid tha
 def compute_layer(flag_ptr=0, value=0):
     # SM kernel, HBM-bound (16 B read + 16 B written per thread-iteration): stands in for attention; when flag_ptr is
     # given its last block releases that layer's ready flag (what an engine's KV-write epilogue would do)
-    assert SL.standin_attention_layer(wa.data_ptr(), wb.data_ptr(), n_vec, flag_ptr, value, counter.data_ptr(), standin_blocks, mp) == 0
+    assert SL.standin_attention_layer(wa.data_ptr(), wb.data_ptr(), n_vec, flag_ptr, value, counter.data_ptr(), standin_blocks, a.fma, mp) == 0
 
 
 def t_ms(fn, iters):
@@ -197,7 +198,7 @@ def transfer_only_ref():
         assert R.kvbm_kernels_launch_vectorized_copy(ptr_s[l].data_ptr(), ptr_d[l].data_ptr(), region, 2 * n, mp) == 0
 
 
-res = {"standin_blocks": standin_blocks, "ring": [a.warps, a.stages, a.tile], "peer": peer, "layers": nl, "region": region, "blocks": n, "bytes": n * nl * 2 * region, "ctas": a.ctas, "layer_us_target": a.layer_us}
+res = {"fma_per_16B": a.fma, "standin_blocks": standin_blocks, "ring": [a.warps, a.stages, a.tile], "peer": peer, "layers": nl, "region": region, "blocks": n, "bytes": n * nl * 2 * region, "ctas": a.ctas, "layer_us_target": a.layer_us}
 res["t_compute_ms"] = t_ms(compute_only, a.iters)
 res["t_compute_plus_signals_ms"] = t_ms(compute_and_signal, a.iters)
 res["t_transfer_full_chip_ms"] = t_ms(lambda: transfer_only(0), a.iters)

@@ -6,12 +6,20 @@
 #include <cstdint>
 
 __global__ void __launch_bounds__(256) standin_layer_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n_vec,
-                                                            uint32_t* ready_flag, uint32_t value, unsigned int* counter)
+                                                            uint32_t* ready_flag, uint32_t value, unsigned int* counter, int fma_iters)
 {
+  // fma_iters > 0 adds a dependent FMA chain per vector: arithmetic intensity knob, so the stand-in can model a
+  // layer that is compute-bound (prefill attention / MLP) rather than one that saturates HBM on its own
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
     uint4 v = in[i];
-    v.x += 1;
+    float a = __uint_as_float(v.x), b = __uint_as_float(v.y);
+    for (int k = 0; k < fma_iters; ++k) {
+      a = fmaf(a, 1.0001f, b);
+      b = fmaf(b, 0.9999f, a);
+    }
+    v.x = __float_as_uint(a) + 1;
+    v.y = __float_as_uint(b);
     out[i] = v;
   }
   if (ready_flag == nullptr) return;
@@ -28,9 +36,9 @@ __global__ void __launch_bounds__(256) standin_layer_kernel(const uint4* __restr
 }
 
 extern "C" cudaError_t standin_attention_layer(const void* in, void* out, size_t n_vec, uint32_t* ready_flag, uint32_t value,
-                                               unsigned int* counter, int blocks, cudaStream_t stream)
+                                               unsigned int* counter, int blocks, int fma_iters, cudaStream_t stream)
 {
   standin_layer_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), n_vec, ready_flag,
-                                                   value, counter);
+                                                   value, counter, fma_iters);
   return cudaGetLastError();
 }

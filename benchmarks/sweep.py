@@ -46,7 +46,6 @@ def main():
     ap.add_argument("--out", default="gpurun_out/sweep.json")
     ap.add_argument("--peer", action="store_true", help="destination pool on cuda:1 (NVLink peer stores)")
     ap.add_argument("--pull", action="store_true", help="with --peer: SOURCE pool on cuda:1, kernel on cuda:0 reads over NVLink")
-    ap.add_argument("--assist", action="store_true", help="SIMT-assist sweep: extra ld/st warps next to the TMA ring")
     ap.add_argument("--fine", action="store_true", help="second-round sweep: CTA count x ring shape x L2 hints")
     a = ap.parse_args()
     torch.cuda.set_device(0)
@@ -100,16 +99,6 @@ def main():
                 cfgs.append((*shape, ctas, 0, 0))
         for hint in (1, 2, 3):
             cfgs += [(4, 3, 1, 16384, 74, hint, 0), (4, 3, 1, 16384, 148, hint, 0), (2, 3, 1, 32768, 74, hint, 0)]
-    assist_cfgs = []
-    if a.assist:
-        cfgs = [(4, 3, 1, 16384, 0, 0, 0)]
-        for ctas in (74, 148):
-            for sw in (4, 8, 12, 16, 24):
-                for pct in (25, 38, 50, 62, 75):
-                    assist_cfgs.append((4, 3, 1, 16384, ctas, sw, pct))
-            for sw, pct in ((12, 50), (24, 62)):
-                assist_cfgs.append((2, 3, 1, 32768, ctas, sw, pct))
-                assist_cfgs.append((2, 3, 1, 16384, ctas, sw, pct))
     if a.peer:   # NVLink-bound: how few SMs saturate the link, and how many stores must be in flight
         cfgs = [(4, 3, 1, 16384, 0, 0, 0), (4, 6, 3, 8192, 0, 0, 0), (4, 6, 5, 8192, 0, 0, 0), (2, 6, 4, 16384, 0, 0, 0),
                 (4, 3, 1, 16384, 0, 0, 1), (8, 3, 1, 8192, 0, 0, 1),
@@ -128,25 +117,6 @@ def main():
         results.append(dict(name="paged_tma", warps=warps, stages=stages, pending=pend, tile=tile, ctas=ctas, hint=hint, variant=variant,
                             ms=med, ms_min=best, gbs_rw=2 * bytes_moved / med / 1e6))
         print(results[-1], flush=True)
-    for warps, stages, pend, tile, ctas, sw, pct in assist_cfgs:
-        opts = K.PagedCopyOpts(warps_per_cta=warps, stages=stages, tile_bytes=tile, max_ctas=ctas, stores_in_flight=pend,
-                               simt_warps=sw, simt_share_pct=pct)
-        rc = K.paged_copy(src, [d], n, 0, nl, 0, opts, sp)
-        if rc != 0:
-            print("rc", rc, warps, stages, tile, sw, pct)
-            continue
-        med, best = timed(lambda: K.paged_copy(src, [d], n, 0, nl, 0, opts, sp), flush=flush)
-        results.append(dict(name="paged_assist", warps=warps, stages=stages, tile=tile, ctas=ctas, simt_warps=sw, simt_pct=pct,
-                            ms=med, ms_min=best, gbs_rw=2 * bytes_moved / med / 1e6))
-        print(results[-1], flush=True)
-    # correctness of the assisted kernel on this full-size transfer (both groups wrote their share)
-    if a.assist:
-        for t in db:
-            t.zero_()
-        K.check(K.paged_copy(src, [d], n, 0, nl, 0, K.PagedCopyOpts(simt_warps=12, simt_share_pct=50), sp))
-        torch.cuda.synchronize()
-        okc = all(torch.equal(db[l].view(2, nbp, region)[:, did.long()], sb[l].view(2, nbp, region)[:, sid.long()]) for l in range(nl))
-        print("assist_bit_exact", okc, flush=True)
     opts = K.PagedCopyOpts(force_simt=1)
     med, best = timed(lambda: K.paged_copy(src, [d], n, 0, nl, 0, opts, sp), flush=flush)
     results.append(dict(name="paged_simt", ms=med, gbs_rw=2 * bytes_moved / med / 1e6))

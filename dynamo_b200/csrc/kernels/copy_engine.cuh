@@ -40,13 +40,6 @@ __device__ __forceinline__ void warp_copy_simt(uint8_t* dst, const uint8_t* src,
     const uint4* s = reinterpret_cast<const uint4*>(src);
     uint4* d = reinterpret_cast<uint4*>(dst);
     uint32_t i = lane;
-    for (; i + 224 < n; i += 256) {
-      uint4 r[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) r[k] = ptx::ld_stream_v4(s + i + 32 * k);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) ptx::st_stream_v4(d + i + 32 * k, r[k]);
-    }
     for (; i + 96 < n; i += 128) {
       uint4 a = ptx::ld_stream_v4(s + i), b = ptx::ld_stream_v4(s + i + 32);
       uint4 c = ptx::ld_stream_v4(s + i + 64), e = ptx::ld_stream_v4(s + i + 96);
@@ -282,15 +275,28 @@ __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32
     if (CAST != 0) ok = ok && (p.bytes & 31) == 0;  // both sides whole 16 B vectors
     return ok;
   };
-  auto fill = [&]() {  // all 32 lanes: descriptors of the next 32 items
-    __syncwarp();      // lanes that ran ahead must not overwrite entries a slower lane still reads
+  // Descriptor generation is software-pipelined: the table loads of the NEXT batch of 32 items are issued
+  // kPrefetchLead items early (results stay in registers, nothing waits on them) and only written to the ring
+  // when the batch is actually needed, so their DRAM/L2 latency never drains the TMA pipeline.
+  constexpr uint32_t kPrefetchLead = 16;
+  Piece pre;
+  bool pre_valid = false;
+  auto prefetch = [&]() {  // all 32 lanes
     const uint32_t j = filled + lane;
-    if (j < n_my) {
-      Piece p;
-      gen.get(first + j * stride, p);
-      ring.put(j, p, eligible(p));
-    }
+    pre.bytes = 0;
+    pre.ndst = 0;
+    pre.layer = 0;
+    pre.src = nullptr;
+    if (j < n_my) gen.get(first + j * stride, pre);
+    pre_valid = true;
+  };
+  auto fill = [&]() {  // all 32 lanes: publish the prefetched descriptors of the next 32 items
+    if (!pre_valid) prefetch();
+    __syncwarp();  // lanes that ran ahead must not overwrite entries a slower lane still reads
+    const uint32_t j = filled + lane;
+    if (j < n_my) ring.put(j, pre, eligible(pre));
     filled += 32;
+    pre_valid = false;
     __syncwarp();
   };
   auto pump = [&](uint32_t limit) {
@@ -320,6 +326,7 @@ __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32
 
   for (uint32_t q = 0; q < n_my; ++q) {
     while (filled < n_my && filled <= q + ahead) fill();
+    if (!pre_valid && filled < n_my && filled <= q + ahead + kPrefetchLead) prefetch();
     pump(q + ahead);
     Piece p;
     const bool ok = ring.get(q, ndst, p, true);
@@ -393,57 +400,6 @@ __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32
 
   drain_stores(lane);
   arrive_layers(ss, open_layer, ss.layer_end, lane);
-  arrive_transfer(ss, lane);
-}
-
-// ------------------------------------------------------------------------------------------
-// SIMT assist.  The TMA path of a TPC sustains only so many outstanding DRAM requests (one CTA per TPC already
-// saturates it: 74 CTAs outrun 148), while the LSU path has its own, separate request capacity.  Extra warps in
-// the same CTA therefore copy a share of the items with plain 128-bit ld/st, descriptors coming from the same
-// SIMD descriptor ring.  Only for ungated byte-exact transfers.
-// ------------------------------------------------------------------------------------------
-template <class Gen>
-struct SubsetGen {  // items {p*den + off .. p*den + off + cnt) for p = 0,1,...  of the base generator
-  const Gen& base;
-  uint32_t den, off, cnt;
-  __device__ __forceinline__ void get(uint32_t j, Piece& p) const
-  {
-    const uint32_t period = j / cnt;
-    base.get(period * den + off + (j - period * cnt), p);
-  }
-  __device__ __forceinline__ static uint32_t size(uint32_t total, uint32_t den, uint32_t off, uint32_t cnt)
-  {
-    const uint32_t full = total / den, rem = total - full * den;
-    const uint32_t extra = rem > off ? (rem - off < cnt ? rem - off : cnt) : 0;
-    return full * cnt + extra;
-  }
-};
-
-template <class Gen>
-__device__ __forceinline__ void warp_simt_loop(const Gen& gen, uint32_t first, uint32_t stride, uint32_t total,
-                                               uint8_t* desc_mem, int ndst, const StreamSync& ss)
-{
-  const int lane = threadIdx.x & 31;
-  const DescRing ring(desc_mem);
-  const uint32_t n_my = total > first ? (total - first + stride - 1) / stride : 0;
-  uint32_t filled = 0;
-  for (uint32_t q = 0; q < n_my; ++q) {
-    if (q == filled) {
-      __syncwarp();
-      const uint32_t j = filled + lane;
-      if (j < n_my) {
-        Piece p;
-        gen.get(first + j * stride, p);
-        ring.put(j, p, false);
-      }
-      filled += 32;
-      __syncwarp();
-    }
-    Piece p;
-    ring.get(q, ndst, p, true);
-    for (int d = 0; d < p.ndst; ++d) warp_copy_simt(p.dst[d], p.src, p.bytes, lane);
-  }
-  __syncwarp();
   arrive_transfer(ss, lane);
 }
 

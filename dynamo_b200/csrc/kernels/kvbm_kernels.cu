@@ -8,7 +8,6 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
-#include <cstdlib>
 #include <vector>
 
 namespace kvbm {
@@ -54,18 +53,6 @@ static cudaError_t device_info(DeviceInfo* out)
 
 static int default_ctas(const DeviceInfo& di) { return (di.sm_count + 1) / 2; }
 
-// SIMT-assist defaults (tuned on B200, profiles/r01_sweep_n1_assist.json); the environment overrides exist for
-// tuning the legacy ABI, which has no options argument.
-static int env_int(const char* name, int dflt)
-{
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
-static int default_simt_warps() { static const int v = env_int("KVBM_SIMT_WARPS", 0); return v; }
-static int default_simt_pct() { static const int v = env_int("KVBM_SIMT_PCT", 50); return v; }
-
-static void set_simt_split(struct RingCfg* c, int pct);
-
 // Ring geometry of one launch.
 struct RingCfg {
   int warps;        // W
@@ -74,17 +61,7 @@ struct RingCfg {
   uint32_t tile;    // source bytes per slot
   uint32_t smem;    // dynamic shared memory bytes
   uint32_t out_tile;  // cast only
-  int simt_warps;     // extra warps copying with ld/st (SIMT assist)
-  uint32_t simt_cnt, simt_den;  // of every simt_den consecutive items the last simt_cnt go to the SIMT warps
 };
-
-static void set_simt_split(RingCfg* c, int pct)
-{
-  c->simt_den = 16;
-  int cnt = (pct * 16 + 50) / 100;
-  cnt = cnt < 1 ? 1 : (cnt > 15 ? 15 : cnt);
-  c->simt_cnt = c->simt_warps > 0 ? static_cast<uint32_t>(cnt) : 0;
-}
 
 constexpr uint32_t kBarBytesPerWarp = kMaxStages * 8;
 // defaults tuned on B200 (profiles/r01_sweep_*.json)
@@ -96,10 +73,9 @@ static uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 
 // cast: 0 none, 1 up (out = 2x), 2 down (out = x/2)
 static RingCfg make_ring(const DeviceInfo& di, uint32_t unit_bytes, int warps, int stages, int tile,
-                         int cast, int pending = 0, int ndst = 1, int simt_warps = 0)
+                         int cast, int pending = 0, int ndst = 1)
 {
   RingCfg c{};
-  c.simt_warps = simt_warps;
   c.warps = warps > 0 ? std::min(warps, 16) : kDefaultWarps;
   // default tile: the whole unit when it is small, else kDefaultTile pieces
   uint32_t t = tile > 0 ? static_cast<uint32_t>(tile) : std::min<uint32_t>(std::max<uint32_t>(unit_bytes, 16), kDefaultTile);
@@ -107,7 +83,7 @@ static RingCfg make_ring(const DeviceInfo& di, uint32_t unit_bytes, int warps, i
   const uint32_t budget = static_cast<uint32_t>(di.max_smem_optin) - 1024;
   for (;;) {
     const uint32_t out = cast == 1 ? 2 * t : (cast == 2 ? t / 2 : 0);
-    const uint32_t fixed = c.warps * (kBarBytesPerWarp + desc_bytes_per_warp(ndst) + 2 * out) + c.simt_warps * desc_bytes_per_warp(ndst);
+    const uint32_t fixed = c.warps * (kBarBytesPerWarp + desc_bytes_per_warp(ndst) + 2 * out);
     int s = stages > 0 ? stages : kDefaultStages;
     s = std::min(s, kMaxStages);
     while (s > 2 && fixed + c.warps * s * t > budget) --s;
@@ -140,7 +116,6 @@ struct SmemView {
   uint8_t* desc;
   uint8_t* in;
   uint8_t* out;
-  uint8_t* simt_desc;  // base of the SIMT warps' descriptor rings
 };
 
 __device__ __forceinline__ SmemView carve(uint8_t* base, int W, int S, uint32_t tile, uint32_t out_tile, int ndst)
@@ -153,7 +128,6 @@ __device__ __forceinline__ SmemView carve(uint8_t* base, int W, int S, uint32_t 
   uint8_t* in0 = base + W * (kBarBytesPerWarp + db);
   v.in = in0 + static_cast<size_t>(warp) * S * tile;
   v.out = in0 + static_cast<size_t>(W) * S * tile + static_cast<size_t>(warp) * 2 * out_tile;
-  v.simt_desc = in0 + static_cast<size_t>(W) * S * tile + static_cast<size_t>(W) * 2 * out_tile;
   return v;
 }
 
@@ -189,36 +163,19 @@ struct PairGen {
   }
 };
 
-__global__ void __launch_bounds__(1024, 1)
-kvbm_pair_copy_kernel(PairGen gen, uint32_t total, int S, int P, uint32_t tile, int allow_tma, int W, uint32_t simt_cnt,
-                      uint32_t simt_den)
+__global__ void __launch_bounds__(512, 1)
+kvbm_pair_copy_kernel(PairGen gen, uint32_t total, int S, int P, uint32_t tile, int allow_tma)
 {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5;
-  const int Ws = (blockDim.x >> 5) - W;
+  const int W = blockDim.x >> 5;
+  SmemView v = carve(smem, W, S, tile, 0, 1);
+  init_bars(v.bars, S);
   StreamSync ss{};
   ss.layer_end = 1;
-  if (warp < W) {
-    SmemView v = carve(smem, W, S, tile, 0, 1);
-    init_bars(v.bars, S);
-    RingParams rp{S, P, tile, 0, allow_tma != 0, 0, 0};
-    // interleave warps of different CTAs over neighbouring items: item i -> CTA (i % grid), warp (i / grid) % W
-    const uint32_t first = warp * gridDim.x + blockIdx.x;
-    if (Ws == 0) {
-      warp_ring<0>(gen, first, gridDim.x * W, total, v.in, v.out, v.bars, v.desc, 1, rp, ss);
-    } else {
-      const SubsetGen<PairGen> sub{gen, simt_den, 0, simt_den - simt_cnt};
-      warp_ring<0>(sub, first, gridDim.x * W, SubsetGen<PairGen>::size(total, simt_den, 0, simt_den - simt_cnt), v.in, v.out, v.bars,
-                   v.desc, 1, rp, ss);
-    }
-  } else {
-    const uint32_t db = desc_bytes_per_warp(1);
-    uint8_t* simt_base = smem + W * (kBarBytesPerWarp + db) + static_cast<size_t>(W) * S * tile;
-    const SubsetGen<PairGen> sub{gen, simt_den, simt_den - simt_cnt, simt_cnt};
-    const uint32_t first = (warp - W) * gridDim.x + blockIdx.x;
-    warp_simt_loop(sub, first, gridDim.x * Ws, SubsetGen<PairGen>::size(total, simt_den, simt_den - simt_cnt, simt_cnt),
-                   simt_base + (warp - W) * db, 1, ss);
-  }
+  RingParams rp{S, P, tile, 0, allow_tma != 0, 0, 0};
+  // interleave warps of different CTAs over neighbouring items: item i -> CTA (i % grid), warp (i / grid) % W
+  const uint32_t first = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+  warp_ring<0>(gen, first, gridDim.x * W, total, v.in, v.out, v.bars, v.desc, 1, rp, ss);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -338,38 +295,21 @@ __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const Pa
 }
 
 template <int CAST>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(512, 1)
 kvbm_paged_copy_kernel(const __grid_constant__ PagedGen gen, const __grid_constant__ PagedSyncArgs sync,
-                       uint32_t total, int S, int P, uint32_t out_tile, int allow_tma, int cache_hint, int variant, int W,
-                       uint32_t simt_cnt, uint32_t simt_den)
+                       uint32_t total, int S, int P, uint32_t out_tile, int allow_tma, int cache_hint, int variant)
 {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5;
-  const int Ws = (blockDim.x >> 5) - W;
+  const int W = blockDim.x >> 5;
   const uint32_t tile = gen.a.tile;
   const int ring_ndst = gen.a.replicate ? gen.a.ndst : 1;
-  const StreamSync ss = make_sync(sync, gen.a, W + Ws);
-  if (warp < W) {
-    SmemView v = carve(smem, W, S, tile, out_tile, ring_ndst);
-    init_bars(v.bars, S);
-    const uint32_t first = warp * gridDim.x + blockIdx.x;
-    const uint32_t stride = gridDim.x * W;
-    RingParams rp{S, P, tile, out_tile, allow_tma != 0, cache_hint, CAST == KVBM_CAST_NONE ? variant : 0};
-    if (Ws == 0) {
-      warp_ring<CAST>(gen, first, stride, total, v.in, v.out, v.bars, v.desc, ring_ndst, rp, ss);
-    } else {
-      const SubsetGen<PagedGen> sub{gen, simt_den, 0, simt_den - simt_cnt};
-      warp_ring<CAST>(sub, first, stride, SubsetGen<PagedGen>::size(total, simt_den, 0, simt_den - simt_cnt), v.in, v.out, v.bars,
-                      v.desc, ring_ndst, rp, ss);
-    }
-  } else if (CAST == KVBM_CAST_NONE) {
-    const uint32_t db = desc_bytes_per_warp(ring_ndst);
-    uint8_t* simt_base = smem + W * (kBarBytesPerWarp + db) + static_cast<size_t>(W) * S * tile + static_cast<size_t>(W) * 2 * out_tile;
-    const SubsetGen<PagedGen> sub{gen, simt_den, simt_den - simt_cnt, simt_cnt};
-    const uint32_t first = (warp - W) * gridDim.x + blockIdx.x;
-    warp_simt_loop(sub, first, gridDim.x * Ws, SubsetGen<PagedGen>::size(total, simt_den, simt_den - simt_cnt, simt_cnt),
-                   simt_base + (warp - W) * db, ring_ndst, ss);
-  }
+  SmemView v = carve(smem, W, S, tile, out_tile, ring_ndst);
+  init_bars(v.bars, S);
+  const StreamSync ss = make_sync(sync, gen.a, W);
+  const uint32_t first = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+  const uint32_t stride = gridDim.x * W;
+  RingParams rp{S, P, tile, out_tile, allow_tma != 0, cache_hint, CAST == KVBM_CAST_NONE ? variant : 0};
+  warp_ring<CAST>(gen, first, stride, total, v.in, v.out, v.bars, v.desc, ring_ndst, rp, ss);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -571,8 +511,7 @@ kvbm_kernels_launch_vectorized_copy(void** src_ptrs, void** dst_ptrs, size_t cop
   if (e != cudaSuccess) return e;
 
   const uint32_t unit = copy_size_bytes > (1u << 20) ? (1u << 20) : static_cast<uint32_t>(copy_size_bytes);
-  RingCfg rc = make_ring(di, unit, 0, 0, 0, 0, 0, 1, std::max(0, std::min(default_simt_warps(), 28)));
-  set_simt_split(&rc, default_simt_pct());
+  RingCfg rc = make_ring(di, unit, 0, 0, 0, 0);
   const uint64_t tiles_per_pair = (copy_size_bytes + rc.tile - 1) / rc.tile;
   const uint64_t total = tiles_per_pair * static_cast<uint64_t>(num_pairs);
   if (tiles_per_pair >= (1ull << 31) || total >= (1ull << 32)) return cudaErrorInvalidValue;
@@ -581,9 +520,8 @@ kvbm_kernels_launch_vectorized_copy(void** src_ptrs, void** dst_ptrs, size_t cop
   const uint64_t ctas_needed = (total + rc.warps - 1) / rc.warps;
   const int grid = static_cast<int>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(default_ctas(di))));
   if ((e = set_smem(kvbm_pair_copy_kernel, rc.smem)) != cudaSuccess) return e;
-  kvbm_pair_copy_kernel<<<grid, (rc.warps + rc.simt_warps) * 32, rc.smem, stream>>>(gen, static_cast<uint32_t>(total), rc.stages,
-                                                                                   rc.pending, rc.tile, 1, rc.warps, rc.simt_cnt,
-                                                                                   rc.simt_den);
+  kvbm_pair_copy_kernel<<<grid, rc.warps * 32, rc.smem, stream>>>(gen, static_cast<uint32_t>(total), rc.stages,
+                                                                 rc.pending, rc.tile, 1);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();  // :570
 }
@@ -724,17 +662,8 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   DeviceInfo di;
   cudaError_t e = device_info(&di);
   if (e != cudaSuccess) return e;
-  const bool assist_ok = cast_mode == KVBM_CAST_NONE && !o.layer_ready_flags && o.variant == 0 && !o.force_simt;
-  bool wants_layer_flags = false;
-  for (int d = 0; d < num_dsts; ++d)
-    if (dsts[d].layer_done_flags) wants_layer_flags = true;
-  int simt_warps = o.simt_warps < 0 ? 0 : (o.simt_warps > 0 ? o.simt_warps : default_simt_warps());
-  if (!assist_ok || wants_layer_flags) simt_warps = 0;
-  simt_warps = std::min(simt_warps, 28);
   RingCfg rc = make_ring(di, src->region_bytes, o.warps_per_cta, o.stages, o.tile_bytes, cast_mode, o.stores_in_flight,
-                         gen.a.replicate ? num_dsts : 1, simt_warps);
-  if (rc.warps + rc.simt_warps > 32) rc.simt_warps = 32 - rc.warps;
-  set_simt_split(&rc, o.simt_share_pct > 0 ? o.simt_share_pct : default_simt_pct());
+                         gen.a.replicate ? num_dsts : 1);
 
   gen.a.n_blocks = static_cast<uint32_t>(num_blocks);
   gen.a.layer_begin = static_cast<uint32_t>(layer_begin);
@@ -760,9 +689,8 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t err = set_smem(kern, rc.smem);
     if (err != cudaSuccess) return err;
-    kern<<<grid, (rc.warps + rc.simt_warps) * 32, rc.smem, stream>>>(gen, sync, total32, rc.stages, rc.pending, rc.out_tile,
-                                                                     allow_tma, o.cache_hint, o.variant, rc.warps, rc.simt_cnt,
-                                                                     rc.simt_den);
+    kern<<<grid, rc.warps * 32, rc.smem, stream>>>(gen, sync, total32, rc.stages, rc.pending, rc.out_tile, allow_tma,
+                                                   o.cache_hint, o.variant);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
   };

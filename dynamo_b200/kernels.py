@@ -99,8 +99,6 @@ class PagedCopyOpts(C.Structure):
         ("stores_in_flight", C.c_int),
         ("cache_hint", C.c_int),
         ("variant", C.c_int),
-        ("simt_warps", C.c_int),
-        ("simt_share_pct", C.c_int),
     ]
 
 

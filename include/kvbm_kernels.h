@@ -134,9 +134,6 @@ typedef struct kvbm_paged_copy_opts {
   int cache_hint;                 /* bit0: L2 evict_first on source reads, bit1: on destination writes */
   int variant;                    /* 0 = TMA load + TMA store (default); 1 = TMA load + SIMT store from smem;
                                      2 / 3 = loads-only / stores-only DIAGNOSTICS (do not copy correctly) */
-  int simt_warps;                 /* SIMT assist: extra warps per CTA copying a share of the items with 128-bit ld/st next to
-                                     the TMA ring (separate request paths). 0 = default, -1 = off. Ignored for casts / gating */
-  int simt_share_pct;             /* share of items (percent, in 1/16 steps) given to the SIMT warps; 0 = default */
 } kvbm_paged_copy_opts;
 
 /* Gather `num_blocks` non-contiguous blocks x layers [layer_begin, layer_end) x outer from `src`,

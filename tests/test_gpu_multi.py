@@ -151,3 +151,25 @@ def test_cross_process_ipc_push():
     for p in procs:
         p.join(timeout=60)
     assert all(v == "ok" for v in res.values()), res
+
+
+def test_pull_direction_decode_side_reads_prefill_pool():
+    """NIXL-READ style (what vLLM's NixlConnector does, components/src/dynamo/vllm/handlers.py:2076-2083): the manager
+    on the DECODE GPU maps the prefill pool and the same kernel, launched there, loads over NVLink and stores locally."""
+    mgr = TransferManager(device=1, worker_id=2)
+    mgr.enable_peer_access(0)
+    src = _pool(0)
+    g = torch.Generator(device="cuda:0").manual_seed(9)
+    for b in src:
+        b.copy_(torch.randint(0, 256, b.shape, dtype=torch.uint8, device="cuda:0", generator=g))
+    dst = _pool(1)
+    h_src, h_dst = _register(mgr, src, 0), _register(mgr, dst, 1)
+    rng = np.random.default_rng(4)
+    sid, did = list(map(int, rng.permutation(NB)[:30])), list(map(int, rng.permutation(NB)[:30]))
+    torch.cuda.synchronize(0)
+    mgr.execute_transfer(h_src, sid, h_dst, did).wait()
+    ref = O.Layout(O.LW, NB, NL, NO, PAGE, INNER, DT, block_dim=O.BLOCK_IS_SECOND_DIM)
+    O.execute_memcpy_transfer(_twin(src), ref, sid, did)
+    for a, b in zip(_twin(dst).buffers, ref.buffers):
+        assert np.array_equal(a, b)
+    mgr.close()
