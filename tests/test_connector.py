@@ -1,0 +1,154 @@
+"""Worker side of the KVBM connector -- wire formats and the per-iteration state machine.
+
+Reference behaviour mirrored (relative to /root/reference):
+  lib/bindings/kvbm/src/block_manager/vllm/connector.rs:158-185      ConnectorMetadata JSON
+  lib/llm/src/block_manager/connector/protocol.rs:60-140             request / requirement enums (serde names)
+  lib/llm/src/block_manager/distributed/utils.rs:47-84               BlockTransferRequest (connector_req omitted when None)
+  lib/bindings/kvbm/src/block_manager/vllm/connector/worker.rs:237-470  bind / clear / save_kv_layer / get_finished
+  lib/llm/src/block_manager/connector/scheduler.rs:148-268           slot completion = completed == len(operations)
+  lib/llm/src/block_manager/layout.rs:163-176                        layer_separate_auto
+"""
+import json
+import uuid
+
+import numpy as np
+import pytest
+import torch
+
+from dynamo_b200.connector import (DEVICE, HOST, IMMEDIATE, LOAD, SCHEDULED, STORE, BlockTransferRequest, ConnectorMetadata,
+                                   KvConnectorWorker, LeaderTransferRequest, SchedulerRequirement, WorkerTransferRequest,
+                                   layer_separate_auto)
+from dynamo_b200.physical import BlockDimension
+from oracle import oracle as O
+
+NB, NL, PAGE, HEADS, HD = 12, 3, 16, 2, 8
+
+
+def test_wire_formats_match_serde_json():
+    u = str(uuid.UUID(int=7))
+    op = WorkerTransferRequest("req-1", u, STORE, SCHEDULED)
+    assert op.to_json() == {"request_id": "req-1", "uuid": u, "transfer_type": "Store", "request_type": "Scheduled"}
+    md = ConnectorMetadata(3)
+    md.create_slot("req-1", 2)
+    md.add_operations([op])
+    wire = json.loads(md.to_bytes())
+    assert wire == {"iteration": 3, "new_slots": [{"request_id": "req-1", "expected_immediate_ops": 2}],
+                    "operations": [op.to_json()]}
+    back = ConnectorMetadata.from_bytes(md.to_bytes())
+    assert back.iteration == 3 and back.operations[0] == op
+    # externally tagged enum variants of SchedulerRequirement
+    assert SchedulerRequirement("IterationComplete", 4).to_json() == {"IterationComplete": 4}
+    assert SchedulerRequirement("LayerComplete", 4, 2).to_json() == {"LayerComplete": [2, 4]}
+    assert SchedulerRequirement("LayerNameComplete", 4, "l0").to_json() == {"LayerNameComplete": ["l0", 4]}
+    for r in (SchedulerRequirement("IterationComplete", 4), SchedulerRequirement("LayerComplete", 4, 2)):
+        assert SchedulerRequirement.from_json(r.to_json()) == r
+    # BlockTransferRequest: tuple list as arrays, connector_req skipped when None (skip_serializing_if)
+    b = BlockTransferRequest(DEVICE, HOST, [(0, 3), (5, 1)])
+    assert b.to_json() == {"from_pool": "Device", "to_pool": "Host", "blocks": [[0, 3], [5, 1]]}
+    b2 = BlockTransferRequest(HOST, DEVICE, [(1, 2)], LeaderTransferRequest("r", u, SchedulerRequirement("IterationComplete", 1), SCHEDULED))
+    assert BlockTransferRequest.from_json(json.loads(json.dumps(b2.to_json()))) == b2
+    with pytest.raises(ValueError):
+        WorkerTransferRequest.from_json({"request_id": "x", "uuid": u, "transfer_type": "Copy", "request_type": "Scheduled"})
+    with pytest.raises(ValueError):
+        BlockTransferRequest.from_json({"from_pool": "Tape", "to_pool": "Host", "blocks": []})
+
+
+def test_layer_separate_auto_detection():
+    assert layer_separate_auto([2, 1024, 16, 8, 128], 1024) == BlockDimension.BlockIsSecondDim   # vLLM flash-attn layout
+    assert layer_separate_auto([1024, 2, 16, 8, 128], 1024) == BlockDimension.BlockIsFirstDim
+    assert layer_separate_auto([4096, 2, 16, 8, 128], 1024) == BlockDimension.BlockIsFirstDim    # shape[0] >= num_blocks
+    with pytest.raises(ValueError):
+        layer_separate_auto([7], 4)
+
+
+def make_worker(host_blocks=8):
+    caches = [(f"model.layers.{l}.attn", torch.zeros(2, NB, PAGE, HEADS, HD, dtype=torch.bfloat16)) for l in range(NL)]
+    w = KvConnectorWorker(None, "worker-0", host_blocks=host_blocks)
+    w.register_kv_caches(NB, PAGE, 0, 2, caches, [0] * NL)
+    return w, caches
+
+
+def fill_sequential(caches):
+    twin = O.Layout(O.LW, NB, NL, 2, PAGE, HEADS * HD, 2, block_dim=O.BLOCK_IS_SECOND_DIM,
+                    bases=[t.data_ptr() for _, t in caches])
+    twin.fill_blocks(range(NB), -1)
+    return twin
+
+
+def test_registration_rules():
+    w, caches = make_worker()
+    assert w.device_config.outer_dim == 2 and w.device_config.inner_dim == HEADS * HD and w.device_config.num_layers == NL
+    with pytest.raises(RuntimeError):                      # worker.rs:139-142
+        w.register_kv_caches(NB, PAGE, 0, 2, caches, [0] * NL)
+    w2 = KvConnectorWorker()
+    with pytest.raises(AssertionError):                    # worker.rs:144-148
+        w2.register_kv_caches(NB, PAGE, 0, 2, caches, [0])
+    w.close()
+
+
+def test_store_flow_offload_after_last_layer_and_get_finished():
+    """One decode iteration: a Store (offload) operation is announced in the metadata, becomes eligible only when the
+    last layer was saved and its iteration completed, moves Device -> Host, and the request finishes afterwards."""
+    w, caches = make_worker()
+    twin = fill_sequential(caches)
+    u = str(uuid.uuid4())
+    md = ConnectorMetadata(1)
+    md.create_slot("req-A", 0)
+    md.add_operations([WorkerTransferRequest("req-A", u, STORE, SCHEDULED)])
+    w.bind_connector_metadata(md.to_bytes())
+    assert w.has_slot("req-A") and w.slots["req-A"].operations == []          # stores are deferred (worker.rs:300)
+    # the leader's transfer request arrives early; it must wait for IterationComplete(1)
+    w.handle_block_transfer(BlockTransferRequest(DEVICE, HOST, [(2, 0), (7, 1)],
+                                                 LeaderTransferRequest("req-A", u, SchedulerRequirement("IterationComplete", 1), SCHEDULED)).to_json())
+    for l in range(NL):
+        w.save_kv_layer(caches[l][0])
+        assert (len(w.slots["req-A"].operations) == 1) == (l == NL - 1)       # enqueued on the LAST layer (worker.rs:329-350)
+    assert not w.is_complete("req-A")
+    assert w.get_finished(["req-A"]) == (set(), set())                        # not finished: transfer has not run
+    w.clear_connector_metadata()                                              # iteration 1 complete -> requirement met
+    off, on = w.get_finished([])
+    assert off == {"req-A"} and on == set() and not w.has_slot("req-A")
+    host = O.Layout(O.FC, 8, NL, 2, PAGE, HEADS * HD, 2, bases=[w._host_mem.data_ptr()])
+    assert host.block_checksum(0) == twin.block_checksum(2) and host.block_checksum(1) == twin.block_checksum(7)
+    assert w.get_finished(["never-started"]) == (set(), set())                # unknown ids are ignored (worker.rs:383-389)
+    w.close()
+
+
+def test_load_flow_onboard_is_immediate_and_tracked():
+    w, caches = make_worker()
+    host = O.Layout(O.FC, 8, NL, 2, PAGE, HEADS * HD, 2, bases=[w._host_mem.data_ptr()])
+    host.fill_blocks(range(8), -1)
+    u1, u2 = str(uuid.uuid4()), str(uuid.uuid4())
+    md = ConnectorMetadata(1)
+    md.create_slot("req-B", 1)
+    md.add_operations([WorkerTransferRequest("req-B", u1, LOAD, SCHEDULED)])
+    w.bind_connector_metadata(md.to_bytes())
+    assert w.slots["req-B"].operations == [u1] and "req-B" in w.maybe_finished_onboarding   # loads enqueue at bind
+    assert w.get_finished([]) == (set(), set())
+    w.handle_block_transfer(BlockTransferRequest(HOST, DEVICE, [(3, 5)], LeaderTransferRequest("req-B", u1, None, SCHEDULED)))
+    # an Immediate operation was never announced: it is recorded on arrival (record_operation, scheduler.rs:258-263)
+    w.handle_block_transfer(BlockTransferRequest(HOST, DEVICE, [(4, 6)], LeaderTransferRequest("req-B", u2, None, IMMEDIATE)))
+    off, on = w.get_finished([])
+    assert on == {"req-B"} and off == set()
+    dev = O.Layout(O.LW, NB, NL, 2, PAGE, HEADS * HD, 2, block_dim=O.BLOCK_IS_SECOND_DIM, bases=[t.data_ptr() for _, t in caches])
+    assert dev.block_checksum(5) == host.block_checksum(3) and dev.block_checksum(6) == host.block_checksum(4)
+    w.clear_connector_metadata()
+    w.close()
+
+
+def test_iteration_mismatch_and_duplicate_slot_are_rejected():
+    w, _ = make_worker(host_blocks=0)
+    md = ConnectorMetadata(5)                                                  # worker starts at iteration 1 (worker.rs:251-255)
+    with pytest.raises(AssertionError):
+        w.bind_connector_metadata(md.to_bytes())
+    w2, _ = make_worker(host_blocks=0)
+    md = ConnectorMetadata(1)
+    md.create_slot("x", 0)
+    w2.bind_connector_metadata(md.to_bytes())
+    w2.clear_connector_metadata()
+    md2 = ConnectorMetadata(2)
+    md2.create_slot("x", 0)
+    with pytest.raises(AssertionError):                                        # "slot already exists" (worker.rs:267-270)
+        w2.bind_connector_metadata(md2.to_bytes())
+    w.close()
+    w2.close()
