@@ -1,0 +1,78 @@
+/*
+ * kvbm_router.h -- C ABI of libkvbm_router.so: the KV-aware routing index that turns prefix hits into the block
+ * tables the transfer path moves (BASELINE configs[4] "kv_router RadixTree prefix-hit routing").
+ *
+ * C++ restatement of (relative to /root/reference/lib/kv-router/src):
+ *   protocols.rs:20-25      XXH3_SEED = 1337, compute_hash = xxh3_64_with_seed
+ *   protocols.rs:74-133     compute_block_hash_for_seq (full blocks only, LoRA name mixed into the seed, eagle window)
+ *   protocols.rs:135-172    compute_seq_hash_for_block (rolling parent || block hash)
+ *   indexer/radix_tree.rs   RadixTree::{find_matches :165-306, apply_event :315-450, remove_worker, clear_all_blocks}
+ *   active_set.rs:9-40      reconcile_active_workers
+ * XXH3 itself is the third-party xxHash library (the reference pins the xxhash-rust crate 0.8); this build uses the
+ * single-header xxhash.h that ships inside the image's pyarrow wheel.
+ */
+#ifndef KVBM_ROUTER_H
+#define KVBM_ROUTER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  KVR_OK = 0,
+  KVR_ERR_PARENT_BLOCK_NOT_FOUND = 1,   /* KvCacheEventError::ParentBlockNotFound */
+  KVR_ERR_BLOCK_NOT_FOUND = 2,          /* KvCacheEventError::BlockNotFound */
+  KVR_ERR_INVALID_BLOCK_SEQUENCE = 3,   /* KvCacheEventError::InvalidBlockSequence */
+  KVR_ERR_ARGUMENT = 4,
+};
+
+#define KVR_XXH3_SEED 1337ull
+
+/* compute_hash (protocols.rs:23-25) */
+uint64_t kvr_compute_hash(const void* data, size_t len);
+/* compute_block_hash_for_seq without multimodal info; returns the number of hashes written (<= cap).
+ * lora_name may be NULL / "" (base model).  is_eagle: window = block_size + 1, stride = block_size. */
+size_t kvr_compute_block_hash_for_seq(const uint32_t* tokens, size_t n_tokens, uint32_t kv_block_size,
+                                      const char* lora_name, int is_eagle, uint64_t* out, size_t cap);
+/* compute_seq_hash_for_block */
+void kvr_compute_seq_hash_for_block(const uint64_t* block_hashes, size_t n, uint64_t* out);
+
+typedef struct kvr_radix_tree kvr_radix_tree;
+
+/* expiration_ms < 0: no frequency tracking (RadixTree::new); else new_with_frequency(Some(duration)) */
+kvr_radix_tree* kvr_tree_create(int64_t expiration_ms);
+void kvr_tree_destroy(kvr_radix_tree* t);
+
+/* RouterEvent{worker_id, KvCacheEvent{event_id, data: Stored{parent_hash?, blocks:[{block_hash, tokens_hash}]}, dp_rank}} */
+int kvr_tree_apply_stored(kvr_radix_tree* t, uint64_t worker_id, uint32_t dp_rank, uint64_t event_id, int has_parent,
+                          uint64_t parent_hash, size_t n_blocks, const uint64_t* block_hashes,
+                          const uint64_t* tokens_hashes);
+int kvr_tree_apply_removed(kvr_radix_tree* t, uint64_t worker_id, uint32_t dp_rank, uint64_t event_id, size_t n_blocks,
+                           const uint64_t* block_hashes);
+/* Cleared event: registers (worker_id, dp_rank) like every apply_event does, then clears every dp rank of worker_id */
+int kvr_tree_apply_cleared(kvr_radix_tree* t, uint64_t worker_id, uint32_t dp_rank);
+void kvr_tree_remove_worker(kvr_radix_tree* t, uint64_t worker_id);
+void kvr_tree_remove_worker_dp_rank(kvr_radix_tree* t, uint64_t worker_id, uint32_t dp_rank);
+void kvr_tree_clear_all_blocks(kvr_radix_tree* t, uint64_t worker_id);
+/* get_workers: sorted unique worker ids; returns count (writes up to cap) */
+size_t kvr_tree_get_workers(kvr_radix_tree* t, uint64_t* out, size_t cap);
+
+/* introspection used by the tests (the reference's tests read `trie.lookup` / `trie.root` directly) */
+int64_t kvr_tree_lookup_size(kvr_radix_tree* t, uint64_t worker_id, uint32_t dp_rank); /* -1: worker not in lookup */
+size_t kvr_tree_lookup_len(kvr_radix_tree* t);
+/* node reached from the root along `path` (tokens hashes); returns 0 and fills counts, or -1 if the path does not exist */
+int kvr_tree_node_info(kvr_radix_tree* t, const uint64_t* path, size_t n, size_t* n_workers, size_t* n_children);
+
+/* find_matches(sequence, early_exit) -> OverlapScores.  Arrays are filled up to their capacity; the return value is the
+ * number of scored workers; *n_freq receives the number of frequency entries written. */
+size_t kvr_tree_find_matches(kvr_radix_tree* t, const uint64_t* sequence, size_t n, int early_exit, uint64_t* worker_ids,
+                             uint32_t* dp_ranks, uint32_t* scores, uint64_t* tree_sizes, size_t cap, uint64_t* frequencies,
+                             size_t freq_cap, size_t* n_freq);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

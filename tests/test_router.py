@@ -1,0 +1,239 @@
+"""KV routing index: C++ RadixTree + XXH3 hashing vs the reference's own scenario tests and a
+pure-Python restatement.
+
+Reference tests transcribed (relative to /root/reference/lib/kv-router/src):
+  indexer/radix_tree.rs:578-858   test_radix_tree            (store / partial remove / parent-hash continuation)
+  indexer/radix_tree.rs:859-901   test_radix_tree_apply_event_errors
+  indexer/radix_tree.rs:902-1033  test_clear_all_blocks
+  indexer/tests.rs:500-560,786-812,1008-1048   partial match, shared prefix, dp ranks, clear clears all dp ranks
+  protocols.rs:929-1187           hash determinism / LoRA / eagle-window properties
+test_utils.rs:60-101: make_blocks(i) -> tokens_hash = i, block_hash = i*100.
+"""
+import json
+import struct
+
+import numpy as np
+import pytest
+import xxhash
+
+from dynamo_b200 import router as R
+from oracle import router_oracle as RO
+
+W0, W1 = (0, 0), (1, 0)
+
+
+def store(t, worker, ids, parent=None, dp=0):
+    t.apply_stored(worker, [i * 100 for i in ids], list(ids), None if parent is None else parent, dp)
+
+
+def remove(t, worker, ids, dp=0):
+    t.apply_removed(worker, [i * 100 for i in ids], dp)
+
+
+def test_radix_tree_reference_scenario():
+    t = R.RadixTree()
+    store(t, 0, [1, 2, 3])
+    assert t.find_matches([1, 2, 3]).scores[W0] == 3
+    assert t.lookup_len() == 1 and t.lookup_size(0) == 3
+    assert t.node_info([]) == (0, 1) and t.node_info([1]) == (1, 1)
+    store(t, 1, [1, 4, 5])
+    s = t.find_matches([1, 2, 3]).scores
+    assert s[W0] == 3 and s[W1] == 1
+    assert t.lookup_len() == 2 and t.lookup_size(0) == 3 and t.lookup_size(1) == 3
+    assert t.node_info([]) == (0, 1) and t.node_info([1]) == (2, 2)
+    remove(t, 1, [5])
+    assert t.lookup_size(0) == 3 and t.lookup_size(1) == 2 and t.node_info([1]) == (2, 2)
+    remove(t, 1, [4])
+    assert t.lookup_size(1) == 1 and t.node_info([1]) == (2, 2)
+    store(t, 1, [2, 6, 7], parent=100)                        # continue under block_hash 100
+    s = t.find_matches([1, 2, 3]).scores
+    assert s[W0] == 3 and s[W1] == 2
+    assert t.lookup_size(0) == 3 and t.lookup_size(1) == 4
+    assert t.node_info([1]) == (2, 2) and t.node_info([1, 2])[0] == 2   # block 200 now has both workers
+    ts = t.find_matches([1, 2, 3]).tree_sizes
+    assert ts[W0] == 3 and ts[W1] == 4
+
+
+def test_apply_event_errors():
+    t = R.RadixTree()
+    with pytest.raises(R.KvCacheEventError) as e:
+        store(t, 0, [1, 2, 3], parent=12345)
+    assert e.value.kind == "ParentBlockNotFound"
+    with pytest.raises(R.KvCacheEventError) as e:
+        remove(t, 0, [1, 2, 3])
+    assert e.value.kind == "BlockNotFound"
+    store(t, 0, [1])
+    with pytest.raises(R.KvCacheEventError) as e:             # parent appears in its own continuation
+        store(t, 0, [1, 2, 3], parent=100)
+    assert e.value.kind == "InvalidBlockSequence"
+
+
+def test_clear_all_blocks_reference_scenario():
+    t = R.RadixTree()
+    assert t.find_matches([0]).scores == {}
+    t.clear_all_blocks(0)
+    assert t.lookup_size(0) is None
+    store(t, 0, [0, 1, 3])
+    store(t, 1, [0, 2, 3])
+    assert t.find_matches([0]).scores == {W0: 1, W1: 1}
+    t.clear_all_blocks(0)
+    assert t.lookup_size(0) == 0
+    assert t.find_matches([0, 2]).scores == {W1: 2}
+    assert t.find_matches([0, 1, 3]).scores == {W1: 1}
+    store(t, 0, [4, 5])
+    assert t.find_matches([4, 5]).scores == {W0: 2}
+    t.clear_all_blocks(0)
+    t.clear_all_blocks(0)
+    assert t.lookup_size(0) == 0
+    t.clear_all_blocks(1)
+    assert t.lookup_len() == 2 and t.lookup_size(0) == 0 and t.lookup_size(1) == 0
+    store(t, 0, [6])
+    store(t, 1, [6])
+    t.remove_worker(0)
+    t.clear_all_blocks(0)
+    assert t.lookup_size(0) is None
+    assert t.find_matches([6]).scores == {W1: 1}
+    t.clear_all_blocks(2)
+    assert t.lookup_size(2) is None and t.lookup_size(1) is not None
+    assert t.find_matches([6]).scores == {W1: 1}
+
+
+def test_partial_match_shared_prefix_dp_ranks_and_early_exit():
+    t = R.RadixTree()
+    store(t, 0, [1, 2, 3])
+    assert t.find_matches([1, 2, 9]).scores == {W0: 2}         # tests.rs:500-511
+    assert t.find_matches([9, 1, 2]).scores == {}              # miss query
+    assert t.find_matches([]).scores == {}                     # empty query
+    store(t, 1, [1, 2, 4])
+    s = t.find_matches([1, 2, 3]).scores
+    assert s == {W0: 3, W1: 2}                                 # tests.rs:529-560
+    store(t, 0, [1, 2, 3], dp=1)                               # tests.rs:786-812: dp ranks are separate workers
+    s = t.find_matches([1, 2, 3]).scores
+    assert s[(0, 0)] == 3 and s[(0, 1)] == 3 and s[W1] == 2
+    t.apply_cleared(0)                                         # tests.rs:1008-1048: cleared drops every dp rank of the worker
+    assert t.find_matches([1, 2, 3]).scores == {W1: 2}
+    assert t.lookup_size(0, 0) == 0 and t.lookup_size(0, 1) == 0
+    assert t.get_workers() == [0, 1]
+    t2 = R.RadixTree()
+    store(t2, 7, [1, 2, 3, 4])
+    assert t2.find_matches([1, 2, 3, 4], early_exit=True).scores == {(7, 0): 1}   # single active worker exits at depth 1
+
+
+def test_remove_mid_chain_block_is_not_cascaded():
+    # radix_tree.rs:243-256 + tests.rs:851-903: a Removed event does not cascade; descendants keep stale workers
+    t = R.RadixTree()
+    store(t, 0, [1, 2, 3])
+    remove(t, 0, [2])
+    assert t.find_matches([1, 2, 3]).scores == {W0: 1}
+    assert t.lookup_size(0) == 2
+
+
+def test_router_event_json_shapes():
+    t = R.RadixTree()
+    ev = {"worker_id": 3, "event": {"event_id": 1, "data": {"stored": {"parent_hash": None, "blocks": [
+        {"block_hash": 100, "tokens_hash": 1}, {"block_hash": 200, "tokens_hash": 2}]}}, "dp_rank": 0}}
+    t.apply_event(json.dumps(ev))
+    assert t.find_matches([1, 2]).scores == {(3, 0): 2}
+    t.apply_event({"worker_id": 3, "event": {"event_id": 2, "data": {"removed": {"block_hashes": [200]}}, "dp_rank": 0}})
+    assert t.find_matches([1, 2]).scores == {(3, 0): 1}
+    t.apply_event({"worker_id": 3, "event": {"event_id": 3, "data": "cleared", "dp_rank": 0}})
+    assert t.find_matches([1, 2]).scores == {}
+
+
+def test_frequency_tracking():
+    t = R.RadixTree(expiration_ms=60_000)                      # tests.rs:1955-2040 in miniature
+    store(t, 0, [1, 2, 3])
+    assert t.find_matches([1, 2, 3]).frequencies == []         # first visit: zeros are omitted
+    assert t.find_matches([1, 2, 3]).frequencies == [1, 1, 1]
+    assert t.find_matches([1, 2]).frequencies == [2, 2]
+    assert t.find_matches([1, 2, 3]).frequencies == [3, 3, 2]
+    assert R.RadixTree().find_matches([1]).frequencies == []
+
+
+# ---------------------------------------------------------------- hashing (protocols.rs)
+def test_hash_definitions_against_xxh3():
+    assert R.compute_hash(b"hello") == xxhash.xxh3_64_intdigest(b"hello", seed=1337)          # protocols.rs:20-25
+    toks = list(range(1000, 1100))
+    h = R.compute_block_hash_for_seq(toks, 16)
+    assert len(h) == 6                                                                         # only full blocks
+    assert h[2] == xxhash.xxh3_64_intdigest(struct.pack("<16I", *toks[32:48]), seed=1337)      # le_bytes(u32)
+    assert h == RO.compute_block_hash_for_seq(toks, 16)
+    s = R.compute_seq_hash_for_block(h)
+    assert s[0] == h[0] and s[1] == xxhash.xxh3_64_intdigest(struct.pack("<QQ", s[0], h[1]), seed=1337)
+    assert s == RO.compute_seq_hash_for_block(h)
+    assert R.compute_block_hash_for_seq(toks, 0) == [] and R.compute_block_hash_for_seq([], 16) == []
+    assert R.compute_seq_hash_for_block([]) == []
+
+
+def test_hash_properties_lora_and_eagle():
+    toks = list(np.random.default_rng(0).integers(0, 50000, 70))
+    base = R.compute_block_hash_for_seq(toks, 16)
+    assert base == R.compute_block_hash_for_seq(toks, 16)                                      # deterministic
+    assert base == R.compute_block_hash_for_seq(toks, 16, lora_name="")                        # empty name == base model
+    a, b = R.compute_block_hash_for_seq(toks, 16, "adapter-a"), R.compute_block_hash_for_seq(toks, 16, "adapter-b")
+    assert len(a) == len(base) and all(x != y for x, y in zip(a, base)) and all(x != y for x, y in zip(a, b))
+    assert a == RO.compute_block_hash_for_seq(toks, 16, "adapter-a")
+    seed = (1337 + xxhash.xxh3_64_intdigest(b"adapter-a")) & ((1 << 64) - 1)                   # seed mixing, protocols.rs:83-86
+    assert a[0] == xxhash.xxh3_64_intdigest(struct.pack("<16I", *toks[:16]), seed=seed)
+    eagle = R.compute_block_hash_for_seq(toks, 16, is_eagle=True)                              # window 17, stride 16
+    assert len(eagle) == (len(toks) - 1) // 16
+    assert eagle[1] == xxhash.xxh3_64_intdigest(struct.pack("<17I", *toks[16:33]), seed=1337)
+    assert eagle == RO.compute_block_hash_for_seq(toks, 16, is_eagle=True)
+
+
+# ---------------------------------------------------------------- randomized differential vs the Python restatement
+def test_random_event_streams_match_oracle():
+    rng = np.random.default_rng(42)
+    for trial in range(30):
+        t, o = R.RadixTree(), RO.RadixTree()
+        for step in range(120):
+            w, dp = int(rng.integers(0, 4)), int(rng.integers(0, 2))
+            kind = rng.integers(0, 10)
+            if kind < 6:
+                n = int(rng.integers(1, 6))
+                ids = [int(x) for x in rng.integers(1, 12, n)]
+                parent = None
+                known = list(o.lookup.get((w, dp), {}).keys())
+                if known and rng.integers(0, 2):
+                    parent = int(known[int(rng.integers(0, len(known)))])
+                want = o.apply_stored(w, [i * 100 for i in ids], ids, parent, dp)
+                try:
+                    t.apply_stored(w, [i * 100 for i in ids], ids, parent, dp)
+                    got = None
+                except R.KvCacheEventError as e:
+                    got = e.kind
+                assert got == want, (trial, step)
+            elif kind < 8:
+                ids = [int(x) for x in rng.integers(1, 12, int(rng.integers(1, 4)))]
+                want = o.apply_removed(w, [i * 100 for i in ids], dp)
+                try:
+                    t.apply_removed(w, [i * 100 for i in ids], dp)
+                    got = None
+                except R.KvCacheEventError as e:
+                    got = e.kind
+                assert got == want
+            elif kind == 8:
+                o.apply_cleared(w, dp)
+                t.apply_cleared(w, dp)
+            else:
+                o.remove_worker(w)
+                t.remove_worker(w)
+            q = [int(x) for x in rng.integers(1, 12, int(rng.integers(1, 7)))]
+            for ee in (False, True):
+                assert t.find_matches(q, ee).scores == o.find_matches(q, ee), (trial, step, q, ee)
+            assert t.lookup_len() == len(o.lookup)
+
+
+def test_prefix_hit_block_table_feeds_the_transfer_path():
+    # configs[4]: a decode worker that already caches the first blocks of the prompt only needs the suffix moved
+    block_size, n_blocks = 16, 20
+    tokens = list(np.random.default_rng(1).integers(0, 32000, block_size * n_blocks))
+    local = R.compute_block_hash_for_seq(tokens, block_size)
+    seq = R.compute_seq_hash_for_block(local)
+    t = R.RadixTree()
+    t.apply_stored(5, seq[:12], local[:12])                   # decode worker 5 holds the first 12 blocks (h = 0.6)
+    src_ids, dst_ids = list(range(100, 120)), list(range(40, 60))
+    s, d, matched = R.prefix_hit_block_table(t, (5, 0), local, src_ids, dst_ids)
+    assert matched == 12 and s == src_ids[12:] and d == dst_ids[12:]
+    s, d, matched = R.prefix_hit_block_table(t, (6, 0), local, src_ids, dst_ids)
+    assert matched == 0 and len(s) == 20
