@@ -296,7 +296,7 @@ def run_ours(args):
         t_src, d_src = desc(h_src, SRC_REGION)
         keep.append(t_src)
         dst_descs = []
-        ws = torch.zeros(NL + 1, dtype=torch.int32, device=dev)
+        ws = torch.zeros(NL + 2, dtype=torch.int32, device=dev)
         shared_s = torch.from_numpy(sids[0].astype(np.int32)).to(dev)
         for d in range(n_dst):
             t, dd = desc(h_dsts[d], REGION)

@@ -387,7 +387,7 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
   const size_t lists = replicate ? static_cast<size_t>(nd) + 1 : 2 * static_cast<size_t>(nd);
   Slot* sl;
   uint64_t seq;
-  int rc = acquire_slot(m, lists * n, S->cfg.num_layers + 1, &sl, &seq);
+  int rc = acquire_slot(m, lists * n, S->cfg.num_layers + 2, &sl, &seq);
   if (rc) return rc;
   auto narrow = [&](const size_t* ids, int32_t* dstp) { for (size_t i = 0; i < n; ++i) dstp[i] = static_cast<int32_t>(ids[i]); };
   std::vector<const int32_t*> dev_src(nd), dev_dst(nd);
@@ -424,6 +424,7 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
   ko.layer_ready_flags = o.layer_ready_flags;
   ko.sync_workspace = sl->dev_ws;
   ko.max_ctas = o.max_ctas;
+  ko.gate_timeout_ms = o.gate_timeout_ms;
   ko.completion_flag = sl->host_flag;
   ko.completion_value = static_cast<uint32_t>(seq);
   cudaError_t e = kvbm_kernels_paged_copy_v2(&sdesc, dd, nd, static_cast<int>(n), static_cast<int>(lb), static_cast<int>(le), o.cast_mode, &ko, stream);
@@ -769,6 +770,7 @@ extern "C" int kvbm_notification_is_complete(kvbm_transfer_manager* m, kvbm_noti
   Slot& sl = m->slots[(n - 1) % kSlots];
   if (sl.seq != n) return sl.seq > n ? 1 : -1;  // slot recycled by a later transfer => ours completed
   const uint32_t v = *reinterpret_cast<volatile uint32_t*>(sl.host_flag);
+  if (v == 0xFFFFFFFFu) return -2;  // the gated kernel gave up waiting for a layer_ready flag
   return v == static_cast<uint32_t>(n) ? 1 : 0;
 }
 
@@ -780,6 +782,7 @@ extern "C" int kvbm_notification_wait(kvbm_transfer_manager* m, kvbm_notificatio
   for (;;) {
     int c = kvbm_notification_is_complete(m, n);
     if (c == 1) return KVBM_OK;
+    if (c == -2) return fail(KVBM_ERR_TIMEOUT, "gated transfer aborted: a layer_ready flag was not released within the gate timeout");
     if (c < 0) return fail(KVBM_ERR_HANDLE, "unknown notification");
     if ((++spins & 63) == 0) {
       if (timeout_us >= 0 &&

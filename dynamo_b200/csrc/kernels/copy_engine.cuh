@@ -91,6 +91,7 @@ struct StreamSync {
   int ndst;
   int num_layers;  // counters per layer live at workspace[l]; whole-transfer counter at [num_layers]
   int layer_begin, layer_end;
+  uint64_t gate_timeout_ns;  // a gated wait longer than this aborts the transfer instead of spinning forever
   bool gate;         // layer_ready present: reads of a layer wait for its flag
   bool want_layers;  // some destination wants per-layer done flags
   bool want_done;    // some whole-transfer flag is wanted
@@ -110,13 +111,27 @@ struct RingParams {
 
 // Flag polls are relaxed loads; one acquire fence follows a successful probe (an ld.acquire.sys per poll would
 // invalidate L1 every time and, measured, slowed the co-resident compute kernel).
-__device__ __forceinline__ void wait_layer_ready(const StreamSync& ss, int layer, int lane)
+// Returns false when the flag was not released within gate_timeout_ns: a spinning kernel that waits for work
+// which can never be submitted (e.g. because a lazy module load is itself waiting for this kernel) must not hang
+// the GPU; the warp then records the abort in the workspace and stops.
+__device__ __forceinline__ bool wait_layer_ready(const StreamSync& ss, int layer, int lane)
 {
+  uint32_t ok = 1;
   if (lane == 0) {
-    while (ptx::ld_relaxed_sys(ss.layer_ready + layer) < ss.epoch) __nanosleep(128);
+    const uint64_t t0 = ptx::globaltimer_ns();
+    uint32_t polls = 0;
+    while (ptx::ld_relaxed_sys(ss.layer_ready + layer) < ss.epoch) {
+      __nanosleep(128);
+      if ((++polls & 1023u) == 0 && ptx::globaltimer_ns() - t0 > ss.gate_timeout_ns) {
+        ok = 0;
+        if (ss.workspace != nullptr) atomicExch(ss.workspace + ss.num_layers + 1, 1u);
+        break;
+      }
+    }
     ptx::fence_acq_rel_sys();
   }
-  __syncwarp();
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  return ok != 0;
 }
 
 // non-blocking probe, warp-uniform result
@@ -153,11 +168,17 @@ __device__ __forceinline__ void arrive_transfer(const StreamSync& ss, int lane)
   uint32_t old = ptx::atom_add_acq_rel_gpu(ss.workspace + ss.num_layers, 1u);
   if (old == ss.total_warps - 1) {
     ss.workspace[ss.num_layers] = 0;
+    const bool aborted = ss.gate && atomicExch(ss.workspace + ss.num_layers + 1, 0u) != 0;
+    if (aborted)  // warps that gave up skipped their layer arrivals: leave every counter zeroed for the next launch
+      for (int l = ss.layer_begin; l < ss.layer_end; ++l) ss.workspace[l] = 0;
     ptx::fence_acq_rel_sys();
+    if (!aborted) {
 #pragma unroll
-    for (int d = 0; d < kMaxDst; ++d)
-      if (d < ss.ndst && ss.done_flag[d] != nullptr) ptx::st_release_sys(ss.done_flag[d], ss.epoch);
-    if (ss.completion_flag != nullptr) ptx::st_release_sys(ss.completion_flag, ss.completion_value);
+      for (int d = 0; d < kMaxDst; ++d)
+        if (d < ss.ndst && ss.done_flag[d] != nullptr) ptx::st_release_sys(ss.done_flag[d], ss.epoch);
+    }
+    // 0xFFFFFFFF = "this transfer gave up waiting for a layer": destinations are NOT told it completed
+    if (ss.completion_flag != nullptr) ptx::st_release_sys(ss.completion_flag, aborted ? 0xFFFFFFFFu : ss.completion_value);
   }
 }
 
@@ -269,6 +290,7 @@ __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32
   uint32_t next_load = 0;   // items [0, next_load) have had their load issued (or need none)
   int ready_layer = ss.gate ? ss.layer_begin - 1 : 0x7fffffff;
   int open_layer = ss.layer_begin;  // lowest layer this warp has not yet arrived for
+  bool aborted = false;
 
   auto eligible = [&](const Piece& p) {
     bool ok = rp.allow_tma && piece_tma_ok(p);
@@ -332,7 +354,10 @@ __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32
     const bool ok = ring.get(q, ndst, p, true);
     if (next_load <= q) {  // this item's layer has not been released yet: publish what is finished, then block
       if (ss.want_layers) publish_upto(p.layer);
-      wait_layer_ready(ss, p.layer, lane);
+      if (!wait_layer_ready(ss, p.layer, lane)) {  // gate timeout: abandon the rest (the abort is recorded)
+        aborted = true;
+        break;
+      }
       ready_layer = p.layer;
       pump(q + ahead);
     } else if (ss.want_layers && p.layer > open_layer) {
@@ -399,7 +424,7 @@ __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32
   }
 
   drain_stores(lane);
-  arrive_layers(ss, open_layer, ss.layer_end, lane);
+  if (!aborted) arrive_layers(ss, open_layer, ss.layer_end, lane);  // never publish layers that were not copied
   arrive_transfer(ss, lane);
 }
 

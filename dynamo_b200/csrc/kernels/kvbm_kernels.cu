@@ -266,6 +266,7 @@ struct PagedSyncArgs {
   uint32_t completion_value;
   uint32_t epoch;
   int num_layers_total;
+  uint64_t gate_timeout_ns;
 };
 
 __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const PagedArgs& a, int W)
@@ -277,6 +278,7 @@ __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const Pa
   ss.layer_ready = s.layer_ready;
   ss.workspace = s.workspace;
   ss.epoch = s.epoch;
+  ss.gate_timeout_ns = s.gate_timeout_ns;
   ss.completion_flag = s.completion_flag;
   ss.completion_value = s.completion_value;
   ss.total_warps = gridDim.x * W;
@@ -654,6 +656,8 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   sync.workspace = o.sync_workspace;
   sync.epoch = o.epoch;
   sync.num_layers_total = static_cast<int>(src->num_layers);
+  sync.gate_timeout_ns = static_cast<uint64_t>(o.gate_timeout_ms > 0 ? o.gate_timeout_ms : 10000) * 1000000ull;
+  if (o.layer_ready_flags && !o.sync_workspace) return cudaErrorInvalidValue;  // the abort word lives in the workspace
   bool needs_ws = o.completion_flag != nullptr;
   for (int d = 0; d < num_dsts; ++d)
     if (dsts[d].done_flag || dsts[d].layer_done_flags) needs_ws = true;

@@ -155,6 +155,12 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p)
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint64_t globaltimer_ns()
+{
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void fence_acq_rel_sys()
 {
   asm volatile("fence.acq_rel.sys;" ::: "memory");

@@ -99,6 +99,7 @@ class PagedCopyOpts(C.Structure):
         ("stores_in_flight", C.c_int),
         ("cache_hint", C.c_int),
         ("variant", C.c_int),
+        ("gate_timeout_ms", C.c_int),
     ]
 
 

@@ -94,6 +94,7 @@ class _COptions(C.Structure):
         ("layer_ready_flags", C.c_void_p),
         ("layer_done_flags", C.c_void_p),
         ("epoch", C.c_uint32),
+        ("gate_timeout_ms", C.c_int),
     ]
 
 
@@ -135,6 +136,7 @@ class TransferOptions:
     layer_ready_flags: int = 0
     layer_done_flags: int = 0
     epoch: int = 0
+    gate_timeout_ms: int = 0
 
     @staticmethod
     def from_layer_range(layer_range: Optional[range]) -> "TransferOptions":
@@ -144,7 +146,7 @@ class TransferOptions:
         lr = self.layer_range
         return _COptions(int(lr is not None), lr.start if lr is not None else 0, lr.stop if lr is not None else 0,
                          self.cuda_stream or 0, int(self.cuda_stream is not None), int(self.cast_mode), self.max_ctas,
-                         self.layer_ready_flags, self.layer_done_flags, self.epoch)
+                         self.layer_ready_flags, self.layer_done_flags, self.epoch, self.gate_timeout_ms)
 
 
 @dataclass
@@ -255,6 +257,8 @@ class TransferCompleteNotification:
 
     def is_complete(self) -> bool:
         rc = lib().kvbm_notification_is_complete(self._mgr._h, self.token)
+        if rc == -2:
+            raise KvbmError(ErrorCode.TIMEOUT, "gated transfer aborted: a layer_ready flag was not released within the gate timeout")
         if rc < 0:
             raise KvbmError(ErrorCode.HANDLE, "unknown notification")
         return rc == 1

@@ -119,7 +119,7 @@ enum {
 typedef struct kvbm_paged_copy_opts {
   uint32_t epoch;                 /* value written to done flags / compared with ready flags (>=) */
   const uint32_t* layer_ready_flags; /* nullable; [num_layers]; layer l is read only after flag >= epoch */
-  uint32_t* sync_workspace;       /* device u32[num_layers + 1], zeroed; required iff any done/completion flag is used */
+  uint32_t* sync_workspace;       /* device u32[num_layers + 2], zeroed (left zeroed); required iff any flag or gating is used */
   int max_ctas;                   /* 0 = default (one CTA per TPC = #SM/2, the measured optimum); smaller values leave more SMs to the engine */
   int warps_per_cta;              /* 0 = default */
   int stages;                     /* 0 = default */
@@ -134,6 +134,8 @@ typedef struct kvbm_paged_copy_opts {
   int cache_hint;                 /* bit0: L2 evict_first on source reads, bit1: on destination writes */
   int variant;                    /* 0 = TMA load + TMA store (default); 1 = TMA load + SIMT store from smem;
                                      2 / 3 = loads-only / stores-only DIAGNOSTICS (do not copy correctly) */
+  int gate_timeout_ms;            /* gated transfers: a layer_ready wait longer than this aborts the launch (completion word
+                                     becomes 0xFFFFFFFF, done flags are not written) instead of hanging the GPU; 0 = 10 s */
 } kvbm_paged_copy_opts;
 
 /* Gather `num_blocks` non-contiguous blocks x layers [layer_begin, layer_end) x outer from `src`,

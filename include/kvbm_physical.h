@@ -102,6 +102,7 @@ typedef struct kvbm_transfer_options {
   const uint32_t* layer_ready_flags; /* nullable: device flags released by the producer (attention) per layer */
   uint32_t* layer_done_flags;        /* nullable: device-visible flags on the destination, set per layer */
   uint32_t epoch;
+  int gate_timeout_ms;               /* 0 = 10 s; see kvbm_paged_copy_opts.gate_timeout_ms */
 } kvbm_transfer_options;
 
 typedef struct kvbm_transfer_manager kvbm_transfer_manager;

@@ -1,6 +1,10 @@
 import os
 import sys
 
+# Gated (layer-streaming) transfers spin on device flags; a first-time lazy kernel load elsewhere in the process can wait
+# for the device to idle and dead-lock against them.  Engines that use gating must load eagerly.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -22,6 +22,11 @@ def test_layer_streamed_store_without_host_sync():
     main = torch.cuda.current_stream()
     for e in events:
         e.record(main)                      # materialise the handles (vLLM creates them once, connector_worker.py:150-160)
+    # warm every torch kernel the "forward pass" below uses BEFORE a gated transfer starts spinning (lazy module loading)
+    warm = torch.randint(-30000, 30000, (8,), dtype=torch.int16, device="cuda").view(torch.bfloat16)
+    caches[0][1].view(-1)[:8].copy_(warm)
+    caches[0][1].zero_()
+    torch.cuda.synchronize()
     w = KvConnectorWorker(None, "gpu-worker", host_blocks=16)
     w.register_kv_caches(NB, PAGE, 0, 2, caches, [e.cuda_event for e in events])
     u = str(uuid.uuid4())
@@ -31,7 +36,7 @@ def test_layer_streamed_store_without_host_sync():
     w.bind_connector_metadata(md.to_bytes())
     blocks = [(3, 0), (9, 1), (30, 2), (17, 3)]
     # the gated transfer is launched BEFORE the forward pass: it may read layer l only after that layer's flag
-    opts = TransferOptions(layer_ready_flags=w.ready_flags_ptr(), epoch=w._epoch, max_ctas=8)
+    opts = TransferOptions(layer_ready_flags=w.ready_flags_ptr(), epoch=w._epoch, max_ctas=8, gate_timeout_ms=20000)
     w.handle_block_transfer(BlockTransferRequest(DEVICE, HOST, blocks, LeaderTransferRequest("req", u, None, SCHEDULED)), opts)
     assert not w.is_complete("req") or len(w.slots["req"].operations) == 0
     g = torch.Generator(device="cuda").manual_seed(5)
