@@ -274,7 +274,7 @@ __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const Pa
   StreamSync ss{};
   ss.gate = s.layer_ready != nullptr;
   ss.want_layers = false;
-  ss.want_done = s.completion_flag != nullptr;
+  ss.want_done = s.completion_flag != nullptr || s.layer_ready != nullptr;  // gated launches always count their warps (abort cleanup)
   ss.layer_ready = s.layer_ready;
   ss.workspace = s.workspace;
   ss.epoch = s.epoch;
