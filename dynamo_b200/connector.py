@@ -272,10 +272,9 @@ class KvConnectorWorker:
         idx = self.layers_complete - 1
         if self._ready_flags is not None and idx < len(self.layer_events):
             # device-side: helper stream waits the layer's event, then releases the layer's ready flag (no host block)
-            import torch
             ev = self.layer_events[idx]
             if ev:
-                torch.cuda.cudart().cudaStreamWaitEvent(self._helper_stream.cuda_stream, ev, 0)
+                K.check(K.stream_wait_event(int(self._helper_stream.cuda_stream), ev), "stream_wait_event")
             K.check(K.set_flags(self._ready_flags.data_ptr(), idx, 1, self._epoch, int(self._helper_stream.cuda_stream)), "set_flags")
         self._completed_layers.add((idx, self.worker_iteration))
         if self.layers_complete == len(self.kv_cache_layers):

@@ -738,6 +738,13 @@ kvbm_kernels_wait_flag(const uint32_t* flag, uint32_t value, cudaStream_t stream
   return cudaGetLastError();
 }
 
+extern "C" cudaError_t
+kvbm_kernels_stream_wait_event(cudaStream_t stream, void* event)
+{
+  if (!event) return cudaErrorInvalidValue;
+  return cudaStreamWaitEvent(stream, static_cast<cudaEvent_t>(event), 0);
+}
+
 extern "C" uint64_t
 kvbm_kernels_launch_count(void)
 {

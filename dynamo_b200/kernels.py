@@ -127,6 +127,8 @@ def lib() -> C.CDLL:
         L.kvbm_kernels_set_flags.restype = i
         L.kvbm_kernels_wait_flag.argtypes = [vp, C.c_uint32, vp]
         L.kvbm_kernels_wait_flag.restype = i
+        L.kvbm_kernels_stream_wait_event.argtypes = [vp, vp]
+        L.kvbm_kernels_stream_wait_event.restype = i
         L.kvbm_kernels_launch_count.restype = C.c_uint64
         L.kvbm_kernels_build_info.restype = C.c_char_p
         _configured = True
@@ -137,7 +139,7 @@ EXPORTED_SYMBOLS = [
     "kvbm_kernels_launch_vectorized_copy", "kvbm_kernels_memcpy_batch",
     "kvbm_kernels_launch_universal_from_block", "kvbm_kernels_launch_block_from_universal",
     "kvbm_kernels_has_memcpy_batch_async", "kvbm_kernels_is_stub_build",
-    "kvbm_kernels_paged_copy_v2", "kvbm_kernels_set_flags", "kvbm_kernels_wait_flag",
+    "kvbm_kernels_paged_copy_v2", "kvbm_kernels_set_flags", "kvbm_kernels_wait_flag", "kvbm_kernels_stream_wait_event",
     "kvbm_kernels_launch_count", "kvbm_kernels_build_info",
 ]
 
@@ -188,6 +190,10 @@ def paged_copy(src: PagedLayout, dsts: Sequence[PagedDst], num_blocks: int, laye
 
 def set_flags(flags_ptr: int, first: int, count: int, value: int, stream: int) -> int:
     return lib().kvbm_kernels_set_flags(flags_ptr, first, count, value, stream)
+
+
+def stream_wait_event(stream: int, event: int) -> int:
+    return lib().kvbm_kernels_stream_wait_event(stream, event)
 
 
 def wait_flag(flag_ptr: int, value: int, stream: int) -> int:

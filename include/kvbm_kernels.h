@@ -152,6 +152,9 @@ cudaError_t kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_
 cudaError_t kvbm_kernels_set_flags(uint32_t* flags, int first, int count, uint32_t value,
                                    cudaStream_t stream);
 cudaError_t kvbm_kernels_wait_flag(const uint32_t* flag, uint32_t value, cudaStream_t stream);
+/* cudaStreamWaitEvent for hosts without a CUDA binding: `event` is a raw cudaEvent_t / CUevent handle.  With
+ * set_flags this turns an engine's existing per-layer event into a device-side ready flag on a helper stream. */
+cudaError_t kvbm_kernels_stream_wait_event(cudaStream_t stream, void* event);
 
 /* Number of kernel launches issued by this library since load (bench accounting). */
 uint64_t kvbm_kernels_launch_count(void);
