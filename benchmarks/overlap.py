@@ -35,6 +35,9 @@ ap.add_argument("--fma", type=int, default=0, help="dependent FMA pairs per 16 B
 ap.add_argument("--warps", type=int, default=0)
 ap.add_argument("--stages", type=int, default=0)
 ap.add_argument("--tile", type=int, default=0)
+ap.add_argument("--standin", choices=["stream", "gemm"], default="stream",
+                help="stream: the synthetic streaming/FMA kernel; gemm: a real tensor-core layer (cuBLAS bf16 GEMM chain via torch.matmul)")
+ap.add_argument("--gemm-n", type=int, default=4096)
 ap.add_argument("--out", default="gpurun_out/overlap.json")
 a = ap.parse_args()
 
@@ -82,7 +85,20 @@ n_vec = work_bytes // 16
 standin_blocks = a.standin_blocks   # keep it well below a full wave: a grid that exactly fills the chip gets a second wave when anything else is resident
 
 
+if a.standin == "gemm":
+    gA = torch.randn(a.gemm_n, a.gemm_n, dtype=torch.bfloat16, device="cuda:0")
+    gB = torch.randn(a.gemm_n, a.gemm_n, dtype=torch.bfloat16, device="cuda:0")
+    gC = torch.empty_like(gA)
+
+
 def compute_layer(flag_ptr=0, value=0):
+    if a.standin == "gemm":
+        # a real prefill-shaped layer: one cuBLAS bf16 GEMM (tcgen05 kernel, ~1 CTA/SM, large smem); the ready flag is
+        # released by a stream mem-op right behind it
+        torch.matmul(gA, gB, out=gC)
+        if flag_ptr:
+            K.check(K.set_flags(flag_ptr, 0, 1, value, mp))
+        return
     # SM kernel, HBM-bound (16 B read + 16 B written per thread-iteration): stands in for attention; when flag_ptr is
     # given its last block releases that layer's ready flag (what an engine's KV-write epilogue would do)
     assert SL.standin_attention_layer(wa.data_ptr(), wb.data_ptr(), n_vec, flag_ptr, value, counter.data_ptr(), standin_blocks, a.fma, mp) == 0
@@ -180,9 +196,23 @@ def overlapped_ours_prereleased():
     K.check(K.set_flags(ready.data_ptr(), 0, nl, e, mp))
     side.wait_stream(main)
     K.check(K.paged_copy(src, [d], n, 0, nl, 0, opts, sp))
+    pre_ev[1].record(side)
     for l in range(nl):
         compute_layer()
+    pre_ev[2].record(main)
     main.wait_stream(side)
+
+
+pre_ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+
+def prereleased_who_waits():
+    """Which side is starved when both run ungated: time to the end of the transfer and to the end of the compute."""
+    torch.cuda.synchronize()
+    pre_ev[0].record(main)
+    overlapped_ours_prereleased()
+    torch.cuda.synchronize()
+    return pre_ev[0].elapsed_time(pre_ev[1]), pre_ev[0].elapsed_time(pre_ev[2])
 
 
 # reference-style: per layer pointer tables (host-built once here; the reference rebuilds them every call) + K1 launch
@@ -210,23 +240,38 @@ def transfer_only_ref():
         assert R.kvbm_kernels_launch_vectorized_copy(ptr_s[l].data_ptr(), ptr_d[l].data_ptr(), region, 2 * n, mp) == 0
 
 
-res = {"fma_per_16B": a.fma, "standin_blocks": standin_blocks, "ring": [a.warps, a.stages, a.tile], "peer": peer, "layers": nl, "region": region, "blocks": n, "bytes": n * nl * 2 * region, "ctas": a.ctas, "layer_us_target": a.layer_us}
-res["t_compute_ms"] = t_ms(compute_only, a.iters)
-res["t_compute_plus_signals_ms"] = t_ms(compute_and_signal, a.iters)
-res["t_transfer_full_chip_ms"] = t_ms(lambda: transfer_only(0), a.iters)
-res["t_transfer_capped_ms"] = t_ms(lambda: transfer_only(a.ctas), a.iters)
-res["t_overlapped_ours_ms"] = t_ms(overlapped_ours, a.iters)
-res["t_overlapped_ours_events_ms"] = t_ms(overlapped_ours_events, a.iters)
-res["t_overlapped_ours_prereleased_ms"] = t_ms(overlapped_ours_prereleased, a.iters)
-res["t_overlapped_ours_per_layer_ms"] = t_ms(overlapped_ours_per_layer, a.iters)
+res = {"standin": a.standin, "gemm_n": a.gemm_n if a.standin == "gemm" else None, "fma_per_16B": a.fma, "standin_blocks": standin_blocks, "ring": [a.warps, a.stages, a.tile], "peer": peer, "layers": nl, "region": region, "blocks": n, "bytes": n * nl * 2 * region, "ctas": a.ctas, "layer_us_target": a.layer_us}
+# Round-robin over the modes (one timed pass each per round) so clock / thermal drift hits every mode alike; medians.
+modes = {"t_compute_ms": compute_only, "t_compute_plus_signals_ms": compute_and_signal,
+         "t_transfer_full_chip_ms": lambda: transfer_only(0), "t_transfer_capped_ms": lambda: transfer_only(a.ctas),
+         "t_overlapped_ours_ms": overlapped_ours, "t_overlapped_ours_events_ms": overlapped_ours_events,
+         "t_overlapped_ours_prereleased_ms": overlapped_ours_prereleased,
+         "t_overlapped_ours_per_layer_ms": overlapped_ours_per_layer}
+if R is not None:
+    modes["t_transfer_ref_per_layer_ms"] = transfer_only_ref
+    modes["t_overlapped_ref_style_ms"] = overlapped_ref_style
+samples = {k: [] for k in modes}
+for k, fn in modes.items():   # warm every path (and load every kernel) before anything is timed
+    fn()
+    torch.cuda.synchronize()
+for _ in range(a.iters):
+    for k, fn in modes.items():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        fn()
+        e1.record(main)
+        torch.cuda.synchronize()
+        samples[k].append(e0.elapsed_time(e1))
+for k, v in samples.items():
+    res[k] = float(np.median(v))
+tt, tc = prereleased_who_waits()
+res["prereleased_transfer_end_ms"], res["prereleased_compute_end_ms"] = tt, tc
 res["slowdown_vs_compute_ours_per_layer"] = res["t_overlapped_ours_per_layer_ms"] / res["t_compute_ms"]
 res["slowdown_vs_compute_ours_events"] = res["t_overlapped_ours_events_ms"] / res["t_compute_ms"]
 res["hidden_fraction_ours_events"] = (res["t_compute_ms"] + res["t_transfer_capped_ms"] - res["t_overlapped_ours_events_ms"]) / res["t_transfer_capped_ms"]
 res["hidden_fraction_ours"] = (res["t_compute_plus_signals_ms"] + res["t_transfer_capped_ms"] - res["t_overlapped_ours_ms"]) / res["t_transfer_capped_ms"]
 res["slowdown_vs_compute_ours"] = res["t_overlapped_ours_ms"] / res["t_compute_ms"]
 if R is not None:
-    res["t_transfer_ref_per_layer_ms"] = t_ms(transfer_only_ref, a.iters)
-    res["t_overlapped_ref_style_ms"] = t_ms(overlapped_ref_style, a.iters)
     res["slowdown_vs_compute_ref_style"] = res["t_overlapped_ref_style_ms"] / res["t_compute_ms"]
 torch.cuda.synchronize()
 assert done.tolist() == [epoch[0]] * nl, "layer done flags not published"
