@@ -51,11 +51,12 @@ BYTES_PER_DST = N_BLOCKS * NL * OUTER * REGION
 MODEL_NAME = "Llama-3-8B bf16"
 CAST = 0
 REPLICATE = False
+NVLS = False
 
 
 def configure(args):
     """Non-default workloads (other BASELINE configs) for the numbers under profiles/; the driver uses defaults."""
-    global NL, KV_HEADS, INNER, REGION, SRC_REGION, CTX_TOKENS, N_BLOCKS, POOL_BLOCKS, BYTES_PER_DST, MODEL_NAME, CAST, REPLICATE
+    global NL, KV_HEADS, INNER, REGION, SRC_REGION, CTX_TOKENS, N_BLOCKS, POOL_BLOCKS, BYTES_PER_DST, MODEL_NAME, CAST, REPLICATE, NVLS
     if args.model == "llama70b-tp4":       # configs[3]: 80 layers, 2 of 8 KV heads per rank -> 8 KiB regions
         NL, KV_HEADS, MODEL_NAME = 80, 2, "Llama-3-70B TP=4 shard bf16"
     elif args.model == "mixtral":          # configs[4]: same KV geometry as Llama-3-8B
@@ -70,6 +71,7 @@ def configure(args):
     POOL_BLOCKS = args.pool_blocks or max(1024, 2 * N_BLOCKS)
     BYTES_PER_DST = N_BLOCKS * NL * OUTER * REGION
     REPLICATE = args.replicate
+    NVLS = bool(getattr(args, "nvls", False)) and args.replicate and args.gpus > 1
 
 
 def peaks():
@@ -183,6 +185,7 @@ TOPOLOGY = "fanout"
 def workload_config(n_gpus, where="hbm"):
     topo = ("same-GPU gather->scatter" if n_gpus == 1 else
             f"{n_gpus // 2} x (1 prefill -> 1 decode) rank pairs (NVLink peer stores via CUDA IPC mappings)" if TOPOLOGY == "pairs" else
+            f"1 prefill -> {n_gpus - 1} decode GPUs, ONE write per tile to an NVLink multicast mapping (NVLS; the switch fans out)" if NVLS else
             f"1 prefill -> {n_gpus - 1} decode GPUs (NVLink peer stores via CUDA IPC mappings)")
     return {"workload": f"{MODEL_NAME} KV hand-off, {CTX_TOKENS // 1024}k ctx, block_size={PAGE}: {N_BLOCKS} blocks x {NL} layers x K/V x "
                         f"{REGION // 1024} KiB = {BYTES_PER_DST / 2**20:.0f} MiB per destination" + (" (identical payload to every destination)" if REPLICATE else ""),
@@ -250,7 +253,35 @@ def run_ours(args):
             b.copy_(torch.randint(0, 256, b.shape, dtype=torch.uint8, device=dev, generator=g))
         h_src = register(src_bufs, src_cfg)
     flag_buf = torch.zeros(64, dtype=torch.int32, device=dev)   # [0]=done flag of this destination
-    if is_dst:
+    mc_group, mc_base = None, 0
+    if NVLS:
+        # every rank (the source included: the root of the reference's ncclBcast keeps a copy too) binds one pool
+        # allocation to the multicast object; layers lie back to back in it
+        from dynamo_b200.disagg import share_fd
+        from dynamo_b200.physical import MulticastGroup
+        per_layer = OUTER * POOL_BLOCKS * REGION
+        tag = os.environ.get("MASTER_PORT", "0")
+        if rank == 0:
+            mc_group = MulticastGroup.create(world, NL * per_layer, shareable=True)
+            share_fd(0, world, mc_group.export_fd(), "mc-" + tag)
+        else:
+            mc_group = MulticastGroup.from_fd(share_fd(rank, world, None, "mc-" + tag), world, NL * per_layer)
+        mc_group.add_device(local)
+        barrier()
+        pool_ptr = mc_group.bind_local(local)
+
+        class _Raw:
+            def __init__(self, ptr, nbytes):
+                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+        whole = torch.as_tensor(_Raw(pool_ptr, NL * per_layer), device=dev)
+        whole.zero_()
+        dst_bufs = [whole[l * per_layer:(l + 1) * per_layer] for l in range(NL)]
+        h_dst_local = register(dst_bufs)
+        torch.cuda.synchronize()
+        barrier()
+        if is_src:
+            mc_base = mc_group.map(local)
+    elif is_dst:
         dst_bufs = make_pool(torch, dev)
         for b in dst_bufs:
             b.zero_()
@@ -260,13 +291,19 @@ def run_ours(args):
     # ---- exchange layout metadata (CUDA IPC handles inside) so rank 0 can map every decode pool ----
     flag_cfg = LayoutConfig(1, 1, 1, 1, 128, dtype_width_bytes=2)
     if world > 1:
-        my_blob = mgr.export_metadata(h_dst_local) if is_dst else b""
+        my_blob = mgr.export_metadata(h_dst_local) if (is_dst and not NVLS) else b""
         h_flag_local = mgr.register_fully_contiguous(flag_cfg, flag_buf.data_ptr(), 256, StorageKind.Device, local)
         my_flag_blob = mgr.export_metadata(h_flag_local)
         blobs = [None] * world
         dist.all_gather_object(blobs, (my_blob, my_flag_blob))
         if is_src:
-            h_dsts = [mgr.import_metadata(blobs[r][0]) for r in my_dsts]
+            if NVLS:
+                per_layer = OUTER * POOL_BLOCKS * REGION
+                h_mc = mgr.register_layer_separate(cfg, [mc_base + l * per_layer for l in range(NL)], [per_layer] * NL,
+                                                   BlockDimension.BlockIsSecondDim, StorageKind.Device, local)
+                h_dsts = [h_mc] * len(my_dsts)
+            else:
+                h_dsts = [mgr.import_metadata(blobs[r][0]) for r in my_dsts]
             peer_flags = [mgr.memory_region(mgr.import_metadata(blobs[r][1]), 0, 0, 0)[0] for r in my_dsts]
     else:
         h_dsts = [h_dst_local]
@@ -274,7 +311,7 @@ def run_ours(args):
 
     # ---- block tables ----
     sids = [np.random.default_rng(10 + (0 if REPLICATE else d)).permutation(POOL_BLOCKS)[:N_BLOCKS] for d in range(n_dst)]
-    dids = [np.random.default_rng(100 + d).permutation(POOL_BLOCKS)[:N_BLOCKS] for d in range(n_dst)]
+    dids = [np.random.default_rng(100 + (0 if NVLS else d)).permutation(POOL_BLOCKS)[:N_BLOCKS] for d in range(n_dst)]
     stream = torch.cuda.Stream(device=dev)
     sp = int(stream.cuda_stream)
     K_steps, W = args.steps, args.warmup
@@ -306,7 +343,7 @@ def run_ours(args):
             dst_descs.append(PagedDst(dd, s_ids.data_ptr(), d_ids.data_ptr(), peer_flags[d], 0))
 
         def launch(epoch):
-            opts = PagedCopyOpts(epoch=epoch, sync_workspace=ws.data_ptr())
+            opts = PagedCopyOpts(epoch=epoch, sync_workspace=ws.data_ptr(), multicast=1 if NVLS else 0)
             K.check(K.paged_copy(d_src, dst_descs, N_BLOCKS, 0, NL, CAST, opts, sp), "paged_copy")
     barrier()
     if is_src:
@@ -348,8 +385,8 @@ def run_ours(args):
         did_l = [np.ascontiguousarray(d, dtype=np.uint64) for d in dids]
 
         def step():
-            o = TransferOptions(cast_mode=CAST)
-            if n_dst == 1:
+            o = TransferOptions(cast_mode=CAST, multicast=1 if NVLS else 0)
+            if n_dst == 1 or NVLS:
                 note = mgr.execute_transfer(h_src, sid_l[0], h_dsts[0], did_l[0], o)
             else:
                 note = mgr.execute_fanout(h_src, h_dsts, sid_l, did_l, REPLICATE, o)
@@ -427,6 +464,11 @@ def run_ours(args):
                     "peak_source": "measured peer copy 770 GB/s per direction (B200_PROFILING.md); nominal 900",
                     "kernel": "kvbm_paged_copy_kernel<0>", "algorithmic_bytes_per_launch": alg,
                     "hbm_read_gbs_source": round((BYTES_PER_DST * SRC_REGION // REGION) * (1 if REPLICATE else n_dst) / (ms_per_step * 1e-3) / 1e9, 2)}
+            if NVLS:   # the source sends the payload ONCE; the switch delivers it to every bound GPU
+                egress = BYTES_PER_DST / (ms_per_step * 1e-3) / 1e9
+                roof.update({"achieved": round(egress, 2), "frac": round(egress / NVLINK_PEER_GBS, 4), "algorithmic_bytes_per_launch": BYTES_PER_DST,
+                             "nvls": True, "delivered_gbs_all_destinations": round(value, 2),
+                             "note": "achieved = NVLink egress of the source (1x payload); value = bytes delivered to the N-1 decode GPUs"})
         line = {
             "metric": "kv_transfer_gbs", "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": K_steps,
             "warmup": W, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
@@ -474,6 +516,8 @@ def run_ours(args):
                             "decode_ttft_drop_ms_vs_cpu_path": round(cpu_ms - ours_ms, 3)}
         print(json.dumps(line), flush=True)
     barrier()
+    if mc_group is not None:
+        mc_group.detach()
     mgr.close()
     if world > 1:
         dist.destroy_process_group()
@@ -501,6 +545,7 @@ def main():
     ap.add_argument("--ctx", type=int, default=4096, help="context tokens (blocks = ctx/16)")
     ap.add_argument("--cast", default="none", choices=["none", "fp8"])
     ap.add_argument("--replicate", action="store_true", help="same blocks to every destination (CollectiveOps::broadcast)")
+    ap.add_argument("--nvls", action="store_true", help="with --replicate: write once to an NVLink multicast mapping (the switch fans out)")
     ap.add_argument("--pool-blocks", type=int, default=0)
     ap.add_argument("--topology", default="fanout", choices=["fanout", "pairs"],
                     help="fanout: rank 0 -> ranks 1..N-1 (default); pairs: rank r -> rank r+N/2 (TP-sharded prefill -> decode)")

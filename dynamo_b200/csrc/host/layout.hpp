@@ -142,4 +142,7 @@ inline int make_layer_separate(const kvbm_layout_config& cfg, const uintptr_t* b
   return KVBM_OK;
 }
 
+// records the thread's last error message (kvbm_last_error) and returns `code`; defined in transfer_manager.cpp
+int set_last_error(int code, const std::string& msg);
+
 }  // namespace kvbm_host

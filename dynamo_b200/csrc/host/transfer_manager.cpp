@@ -27,6 +27,7 @@ static int fail(int code, const std::string& msg)
   g_last_error = msg;
   return code;
 }
+int set_last_error(int code, const std::string& msg) { return fail(code, msg); }
 static int fail_cuda(cudaError_t e, const char* what)
 {
   g_last_error = std::string(what) + " failed: " + cudaGetErrorName(e) + " (" + std::to_string(static_cast<int>(e)) + ")";
@@ -116,7 +117,12 @@ struct Slot {
   cudaEvent_t ev = nullptr;
   uint64_t seq = 0;               // owner
   bool in_flight = false;
+  bool owns_ids = false;          // false: pinned_ids / dev_ids point into the manager's arenas
+  bool owns_ws = false;
+  bool owns_flag = false;
 };
+constexpr size_t kArenaIds = 4096;  // int32 entries per slot carved from the arenas (16 KiB: 2 x 2048-block tables)
+constexpr size_t kArenaWs = 512;    // workspace words per slot
 
 #pragma pack(push, 1)
 struct BlobHeader {
@@ -156,6 +162,10 @@ struct kvbm_transfer_manager {
   cudaStream_t d2h[kStreams] = {};
   std::atomic<uint32_t> rr_h2d{0}, rr_d2h{0};
   Slot slots[kSlots];
+  // one pinned and one device allocation back all slots (128 cudaHostAlloc + 128 cudaMalloc per manager took seconds
+  // on a multi-GPU box); a slot only allocates privately when a transfer outgrows its share
+  uint8_t* pinned_arena = nullptr;
+  uint8_t* dev_arena = nullptr;
   uint64_t next_seq = 1;
   std::atomic<uint64_t> bytes_moved{0}, h2d_bytes{0};
   // CUDA IPC mappings opened by import_metadata, keyed by the 64-byte handle: an allocation shared by several
@@ -260,25 +270,57 @@ static int ensure_slot(Slot& sl, size_t ids_needed, size_t ws_needed)
   if (!sl.host_flag) {
     CU(cudaHostAlloc(reinterpret_cast<void**>(&sl.host_flag), 64, cudaHostAllocMapped | cudaHostAllocPortable));
     *sl.host_flag = 0;
+    sl.owns_flag = true;
   }
   if (sl.cap < ids_needed) {
-    if (sl.pinned_ids) cudaFreeHost(sl.pinned_ids);
-    if (sl.dev_ids) cudaFree(sl.dev_ids);
+    if (sl.owns_ids) {
+      if (sl.pinned_ids) cudaFreeHost(sl.pinned_ids);
+      if (sl.dev_ids) cudaFree(sl.dev_ids);
+    }
     sl.pinned_ids = nullptr;
     sl.dev_ids = nullptr;
+    sl.cap = 0;
     size_t cap = 4096;
     while (cap < ids_needed) cap *= 2;
     CU(cudaHostAlloc(reinterpret_cast<void**>(&sl.pinned_ids), cap * sizeof(int32_t), cudaHostAllocPortable));
+    sl.owns_ids = true;
     CU(cudaMalloc(reinterpret_cast<void**>(&sl.dev_ids), cap * sizeof(int32_t)));
     sl.cap = cap;
   }
   if (sl.ws_cap < ws_needed) {
-    if (sl.dev_ws) cudaFree(sl.dev_ws);
+    if (sl.owns_ws && sl.dev_ws) cudaFree(sl.dev_ws);
+    sl.dev_ws = nullptr;
+    sl.ws_cap = 0;
     size_t cap = 512;
     while (cap < ws_needed) cap *= 2;
     CU(cudaMalloc(reinterpret_cast<void**>(&sl.dev_ws), cap * sizeof(uint32_t)));
+    sl.owns_ws = true;
     CU(cudaMemset(sl.dev_ws, 0, cap * sizeof(uint32_t)));
     sl.ws_cap = cap;
+  }
+  return KVBM_OK;
+}
+
+// Carve every slot's default share out of two arenas (called once, device current).
+static int provision_slots(kvbm_transfer_manager* m)
+{
+  const size_t pin_per = kArenaIds * sizeof(int32_t) + 64;                       // ids + flag word (own cache line)
+  const size_t dev_per = kArenaIds * sizeof(int32_t) + kArenaWs * sizeof(uint32_t);
+  CU(cudaHostAlloc(reinterpret_cast<void**>(&m->pinned_arena), pin_per * kSlots, cudaHostAllocMapped | cudaHostAllocPortable));
+  CU(cudaMalloc(reinterpret_cast<void**>(&m->dev_arena), dev_per * kSlots));
+  CU(cudaMemset(m->dev_arena, 0, dev_per * kSlots));
+  std::memset(m->pinned_arena, 0, pin_per * kSlots);
+  for (int i = 0; i < kSlots; ++i) {
+    Slot& sl = m->slots[i];
+    uint8_t* hp = m->pinned_arena + pin_per * i;
+    uint8_t* dp = m->dev_arena + dev_per * i;
+    sl.pinned_ids = reinterpret_cast<int32_t*>(hp);
+    sl.host_flag = reinterpret_cast<uint32_t*>(hp + kArenaIds * sizeof(int32_t));
+    sl.dev_ids = reinterpret_cast<int32_t*>(dp);
+    sl.dev_ws = reinterpret_cast<uint32_t*>(dp + kArenaIds * sizeof(int32_t));
+    sl.cap = kArenaIds;
+    sl.ws_cap = kArenaWs;
+    CU(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
   }
   return KVBM_OK;
 }
@@ -425,6 +467,7 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
   ko.sync_workspace = sl->dev_ws;
   ko.max_ctas = o.max_ctas;
   ko.gate_timeout_ms = o.gate_timeout_ms;
+  ko.multicast = o.multicast;
   ko.completion_flag = sl->host_flag;
   ko.completion_value = static_cast<uint32_t>(seq);
   cudaError_t e = kvbm_kernels_paged_copy_v2(&sdesc, dd, nd, static_cast<int>(n), static_cast<int>(lb), static_cast<int>(le), o.cast_mode, &ko, stream);
@@ -482,10 +525,8 @@ extern "C" int kvbm_manager_create(int cuda_device_id, uint64_t worker_id, kvbm_
       CU(cudaStreamCreateWithFlags(&m->h2d[i], cudaStreamNonBlocking));
       CU(cudaStreamCreateWithFlags(&m->d2h[i], cudaStreamNonBlocking));
     }
-    for (auto& sl : m->slots) {
-      int rc = ensure_slot(sl, 4096, 512);
-      if (rc) return rc;
-    }
+    int rc = provision_slots(m.get());
+    if (rc) return rc;
   }
   *out = m.release();
   return KVBM_OK;
@@ -502,11 +543,13 @@ extern "C" void kvbm_manager_destroy(kvbm_transfer_manager* m)
     for (auto& kv : m->ipc_cache) cudaIpcCloseMemHandle(kv.second);
     for (auto& s : m->slots) {
       if (s.ev) cudaEventDestroy(s.ev);
-      if (s.pinned_ids) cudaFreeHost(s.pinned_ids);
-      if (s.dev_ids) cudaFree(s.dev_ids);
-      if (s.host_flag) cudaFreeHost(s.host_flag);
-      if (s.dev_ws) cudaFree(s.dev_ws);
+      if (s.owns_ids && s.pinned_ids) cudaFreeHost(s.pinned_ids);
+      if (s.owns_ids && s.dev_ids) cudaFree(s.dev_ids);
+      if (s.owns_flag && s.host_flag) cudaFreeHost(s.host_flag);
+      if (s.owns_ws && s.dev_ws) cudaFree(s.dev_ws);
     }
+    if (m->pinned_arena) cudaFreeHost(m->pinned_arena);
+    if (m->dev_arena) cudaFree(m->dev_arena);
     for (int i = 0; i < kStreams; ++i) {
       if (m->h2d[i]) cudaStreamDestroy(m->h2d[i]);
       if (m->d2h[i]) cudaStreamDestroy(m->d2h[i]);

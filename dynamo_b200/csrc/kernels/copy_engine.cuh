@@ -105,7 +105,7 @@ struct RingParams {
   uint32_t tile_out;  // cast rings: bytes per output slot (2 of them)
   bool allow_tma;
   int cache_hint;     // bit0 evict_first loads, bit1 evict_first stores
-  int variant;        // 0 = TMA load + TMA store; 1 = TMA load + SIMT store from smem;
+  int variant;        // 0 = TMA load + TMA store; 1 = TMA load + SIMT store from smem; 4 = TMA load + multimem.st (NVLS);
                       // 2 = loads only (diagnostic), 3 = stores only (diagnostic)
 };
 
@@ -207,6 +207,32 @@ __device__ __forceinline__ void warp_store_from_smem(uint8_t* dst, uint32_t src_
   }
 }
 
+// smem -> NVLink multicast address (variant 4): one store, the switch delivers it to every bound device
+__device__ __forceinline__ void warp_store_from_smem_mc(uint8_t* dst, uint32_t src_smem, uint32_t bytes, int lane)
+{
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint32_t n = bytes >> 4;
+  for (uint32_t i = lane; i < n; i += 32) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src_smem + i * 16));
+    ptx::multimem_st_v4(d + i, v);
+  }
+}
+// global -> multicast for pieces the TMA load cannot take (the launcher guarantees 4-byte granularity)
+__device__ __forceinline__ void warp_copy_simt_mc(uint8_t* dst, const uint8_t* src, uint32_t bytes, int lane)
+{
+  const uintptr_t both = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | bytes;
+  if ((both & 15) == 0) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    for (uint32_t i = lane; i < (bytes >> 4); i += 32) ptx::multimem_st_v4(d + i, ptx::ld_stream_v4(s + i));
+  } else {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+    for (uint32_t i = lane; i < (bytes >> 2); i += 32) ptx::multimem_st_b32(d + i, s[i]);
+  }
+}
+
 template <bool UP>
 __device__ __forceinline__ void convert_smem(uint32_t in_smem, uint32_t out_smem, uint32_t src_bytes, int lane);
 template <bool UP>
@@ -279,7 +305,7 @@ __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32
   const int S = rp.S;
   const DescRing ring(desc_mem);
   uint32_t filled = 0;  // descriptors exist for this warp's items [max(0, filled - kDescRing), filled)
-  const bool sync_slot = CAST != 0 || rp.variant == 1 || rp.variant == 2;  // input slot is released synchronously
+  const bool sync_slot = CAST != 0 || rp.variant == 1 || rp.variant == 2 || rp.variant == 4;  // input slot is released synchronously
   const uint32_t ahead = sync_slot ? static_cast<uint32_t>(S) : static_cast<uint32_t>(S - rp.P);
   const uint32_t n_my = total > first ? (total - first + stride - 1) / stride : 0;
   const uint32_t in0 = ptx::smem_addr(in_slots);
@@ -390,6 +416,8 @@ __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32
         phase ^= 1u << s;
         if (rp.variant == 1) {
           for (int d = 0; d < p.ndst; ++d) warp_store_from_smem(p.dst[d], slot, p.bytes, lane);
+        } else if (rp.variant == 4) {
+          warp_store_from_smem_mc(p.dst[0], slot, p.bytes, lane);
         }
         __syncwarp();
       } else {
@@ -410,7 +438,9 @@ __device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32
       }
     } else {
       for (int d = 0; d < p.ndst; ++d) {
-        if (CAST == 0)
+        if (CAST == 0 && rp.variant == 4)
+          warp_copy_simt_mc(p.dst[d], p.src, p.bytes, lane);
+        else if (CAST == 0)
           warp_copy_simt(p.dst[d], p.src, p.bytes, lane);
         else
           warp_cast_simt<CAST == 1>(p.dst[d], p.src, p.bytes, lane);

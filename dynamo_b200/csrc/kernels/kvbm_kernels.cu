@@ -267,6 +267,7 @@ struct PagedSyncArgs {
   uint32_t epoch;
   int num_layers_total;
   uint64_t gate_timeout_ns;
+  int num_flag_dsts;  // destinations that get flags (== data destinations unless multicast)
 };
 
 __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const PagedArgs& a, int W)
@@ -282,7 +283,7 @@ __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const Pa
   ss.completion_flag = s.completion_flag;
   ss.completion_value = s.completion_value;
   ss.total_warps = gridDim.x * W;
-  ss.ndst = a.ndst;
+  ss.ndst = s.num_flag_dsts;
   ss.num_layers = s.num_layers_total;
   ss.layer_begin = static_cast<int>(a.layer_begin);
   ss.layer_end = static_cast<int>(a.layer_begin + a.n_layers);
@@ -290,8 +291,8 @@ __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const Pa
   for (int d = 0; d < kMaxDst; ++d) {
     ss.done_flag[d] = s.done_flag[d];
     ss.layer_done[d] = s.layer_done[d];
-    if (d < a.ndst && s.layer_done[d] != nullptr) ss.want_layers = true;
-    if (d < a.ndst && s.done_flag[d] != nullptr) ss.want_done = true;
+    if (d < s.num_flag_dsts && s.layer_done[d] != nullptr) ss.want_layers = true;
+    if (d < s.num_flag_dsts && s.done_flag[d] != nullptr) ss.want_done = true;
   }
   return ss;
 }
@@ -629,13 +630,25 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   kvbm_paged_copy_opts o{};
   if (opts) o = *opts;
 
+  // NVLS: dsts[0] is addressed through a multicast mapping and carries the payload for every bound device; the
+  // other entries only name the flags of the remaining receivers.
+  const bool mc = o.multicast != 0;
+  if (mc && (cast_mode != KVBM_CAST_NONE || (src->region_bytes & 3) || (src->block_stride & 3) || (src->outer_stride & 3) ||
+             (dsts[0].layout.block_stride & 15) || (dsts[0].layout.outer_stride & 15)))
+    return cudaErrorInvalidValue;
+  const int data_dsts = mc ? 1 : num_dsts;
+
   PagedGen gen{};
   PagedSyncArgs sync{};
   gen.a.src = *src;
-  gen.a.ndst = num_dsts;
+  gen.a.ndst = data_dsts;
   gen.a.replicate = 1;
+  sync.num_flag_dsts = num_dsts;
   for (int d = 0; d < num_dsts; ++d) {
     const kvbm_paged_dst& D = dsts[d];
+    sync.done_flag[d] = D.done_flag;
+    sync.layer_done[d] = D.layer_done_flags;
+    if (d >= data_dsts) continue;
     // same compatibility rules as execute_cuda_transfer (executor/cuda.rs:52-67) + region size match
     // (executor/memcpy.rs:143-153), adjusted for the element-width change of a cast
     if (!D.layout.layer_base || !D.src_block_ids || !D.dst_block_ids) return cudaErrorInvalidValue;
@@ -646,10 +659,8 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
     gen.a.src_ids[d] = D.src_block_ids;
     gen.a.dst_ids[d] = D.dst_block_ids;
     if (D.src_block_ids != dsts[0].src_block_ids) gen.a.replicate = 0;
-    sync.done_flag[d] = D.done_flag;
-    sync.layer_done[d] = D.layer_done_flags;
   }
-  if (num_dsts == 1) gen.a.replicate = 1;
+  if (data_dsts == 1) gen.a.replicate = 1;
   sync.completion_flag = o.completion_flag;
   sync.completion_value = o.completion_value;
   sync.layer_ready = o.layer_ready_flags;
@@ -667,7 +678,7 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   cudaError_t e = device_info(&di);
   if (e != cudaSuccess) return e;
   RingCfg rc = make_ring(di, src->region_bytes, o.warps_per_cta, o.stages, o.tile_bytes, cast_mode, o.stores_in_flight,
-                         gen.a.replicate ? num_dsts : 1);
+                         gen.a.replicate ? data_dsts : 1);
 
   gen.a.n_blocks = static_cast<uint32_t>(num_blocks);
   gen.a.layer_begin = static_cast<uint32_t>(layer_begin);
@@ -677,7 +688,7 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   gen.a.tiles_per_region = (src->region_bytes + rc.tile - 1) / rc.tile;
   gen.a.dst_num = num;
   gen.a.dst_den = den;
-  const uint64_t fan = gen.a.replicate ? 1 : static_cast<uint64_t>(num_dsts);
+  const uint64_t fan = gen.a.replicate ? 1 : static_cast<uint64_t>(data_dsts);
   const uint64_t total = static_cast<uint64_t>(gen.a.n_layers) * gen.a.n_blocks * gen.a.outer * fan * gen.a.tiles_per_region;
   if (total >= (1ull << 32)) return cudaErrorInvalidValue;
 
@@ -694,7 +705,7 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
     cudaError_t err = set_smem(kern, rc.smem);
     if (err != cudaSuccess) return err;
     kern<<<grid, rc.warps * 32, rc.smem, stream>>>(gen, sync, total32, rc.stages, rc.pending, rc.out_tile, allow_tma,
-                                                   o.cache_hint, o.variant);
+                                                   o.cache_hint, mc ? (o.multicast == 2 ? 0 : 4) : o.variant);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
   };

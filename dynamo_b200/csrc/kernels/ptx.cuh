@@ -188,6 +188,19 @@ __device__ __forceinline__ void st_stream_v4(void* p, const uint4& v)
                : "memory");
 }
 
+// Store to an NVLink multicast (multimem) address: the NVSwitch replicates the write to every device bound to the
+// multicast object.  PTX only defines multimem.* instructions on such addresses (it assembles to a plain STG).
+__device__ __forceinline__ void multimem_st_v4(void* p, const uint4& v)
+{
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+__device__ __forceinline__ void multimem_st_b32(void* p, uint32_t v)
+{
+  asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ---------------------------------------------------------------- fp8 e4m3fn <-> bf16
 // two e4m3 codes (low 16 bits) -> two bf16 (exact).  NaN codes (0x7f/0xff) -> 0x7fc0.
 __device__ __forceinline__ uint32_t e4m3x2_to_bf16x2(uint16_t two)

@@ -94,3 +94,44 @@ def max_over_ranks(value: float, device=None, group=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def share_fd(rank: int, world: int, fd: Optional[int], name: str, timeout_s: float = 60.0) -> int:
+    """Hand one POSIX file descriptor from rank 0 to every other rank of the node (SCM_RIGHTS over an abstract
+    AF_UNIX socket named after `name`).  Used for the shareable handle of a multicast object
+    (`MulticastGroup.export_fd` -> `MulticastGroup.from_fd`); torch.distributed cannot carry descriptors."""
+    import socket
+    import time
+    addr = "\0kvbm-fd-" + name
+    if rank == 0:
+        if fd is None:
+            raise ValueError("rank 0 must provide the descriptor")
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        srv.bind(addr)
+        srv.listen(world)
+        srv.settimeout(timeout_s)
+        try:
+            for _ in range(world - 1):
+                conn, _ = srv.accept()
+                with conn:
+                    socket.send_fds(conn, [b"fd"], [fd])
+        finally:
+            srv.close()
+        return fd
+    deadline = time.monotonic() + timeout_s
+    while True:
+        c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        try:
+            c.connect(addr)
+        except (FileNotFoundError, ConnectionRefusedError):
+            c.close()
+            if time.monotonic() > deadline:
+                raise TimeoutError(f"rank 0 never offered descriptor {name!r}")
+            time.sleep(0.02)
+            continue
+        with c:
+            c.settimeout(timeout_s)
+            _, fds, _, _ = socket.recv_fds(c, 16, 1)
+        if not fds:
+            raise RuntimeError("no descriptor received")
+        return fds[0]

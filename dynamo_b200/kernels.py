@@ -100,6 +100,7 @@ class PagedCopyOpts(C.Structure):
         ("cache_hint", C.c_int),
         ("variant", C.c_int),
         ("gate_timeout_ms", C.c_int),
+        ("multicast", C.c_int),
     ]
 
 

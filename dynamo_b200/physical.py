@@ -95,6 +95,7 @@ class _COptions(C.Structure):
         ("layer_done_flags", C.c_void_p),
         ("epoch", C.c_uint32),
         ("gate_timeout_ms", C.c_int),
+        ("multicast", C.c_int),
     ]
 
 
@@ -137,6 +138,7 @@ class TransferOptions:
     layer_done_flags: int = 0
     epoch: int = 0
     gate_timeout_ms: int = 0
+    multicast: int = 0                    # destination layout lives in a MulticastGroup.map() range (NVLS)
 
     @staticmethod
     def from_layer_range(layer_range: Optional[range]) -> "TransferOptions":
@@ -146,7 +148,8 @@ class TransferOptions:
         lr = self.layer_range
         return _COptions(int(lr is not None), lr.start if lr is not None else 0, lr.stop if lr is not None else 0,
                          self.cuda_stream or 0, int(self.cuda_stream is not None), int(self.cast_mode), self.max_ctas,
-                         self.layer_ready_flags, self.layer_done_flags, self.epoch, self.gate_timeout_ms)
+                         self.layer_ready_flags, self.layer_done_flags, self.epoch, self.gate_timeout_ms,
+                         int(self.multicast))
 
 
 @dataclass
@@ -167,6 +170,9 @@ EXPORTED_SYMBOLS = [
     "kvbm_manager_export_metadata", "kvbm_manager_import_metadata", "kvbm_manager_execute_transfer",
     "kvbm_manager_execute_fanout", "kvbm_notification_is_complete", "kvbm_notification_wait",
     "kvbm_manager_bytes_moved", "kvbm_manager_h2d_bytes",
+    "kvbm_mc_supported", "kvbm_mc_group_create", "kvbm_mc_group_export_fd", "kvbm_mc_group_import_fd",
+    "kvbm_mc_group_size", "kvbm_mc_group_add_device", "kvbm_mc_group_bind_local", "kvbm_mc_group_map",
+    "kvbm_mc_group_destroy",
 ]
 
 
@@ -204,6 +210,17 @@ def lib() -> C.CDLL:
         L.kvbm_manager_bytes_moved.restype = u64
         L.kvbm_manager_h2d_bytes.argtypes = [vp]
         L.kvbm_manager_h2d_bytes.restype = u64
+        L.kvbm_mc_supported.argtypes = [i]
+        L.kvbm_mc_group_create.argtypes = [i, sz, i, P(vp)]
+        L.kvbm_mc_group_export_fd.argtypes = [vp, P(i)]
+        L.kvbm_mc_group_import_fd.argtypes = [i, i, sz, P(vp)]
+        L.kvbm_mc_group_size.argtypes = [vp]
+        L.kvbm_mc_group_size.restype = sz
+        L.kvbm_mc_group_add_device.argtypes = [vp, i]
+        L.kvbm_mc_group_bind_local.argtypes = [vp, i, P(vp)]
+        L.kvbm_mc_group_map.argtypes = [vp, i, P(vp)]
+        L.kvbm_mc_group_destroy.argtypes = [vp]
+        L.kvbm_mc_group_destroy.restype = None
         _configured = True
     return L
 
@@ -383,3 +400,74 @@ class TransferManager:
 
     def h2d_bytes(self) -> int:
         return lib().kvbm_manager_h2d_bytes(self._h)
+
+
+def multicast_supported(device: int = 0) -> bool:
+    """CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED (NVSwitch multicast objects usable from this process)."""
+    return bool(lib().kvbm_mc_supported(device))
+
+
+class MulticastGroup:
+    """NVLS multicast group (`kvbm_mc_group_*`, include/kvbm_physical.h): the receivers' pools are bound to one
+    multicast object; the sender maps it and transfers with `TransferOptions(multicast=1)`, so identical KV blocks reach
+    every bound GPU with ONE write per tile -- the replacement of the grouped `ncclBcast` per region
+    (lib/kvbm-engine/src/collectives/nccl.rs:421-462).
+
+    Call order across all participants: create()/from_fd() -> add_device() for every device (by its owning process)
+    -> barrier -> bind_local() on every receiver -> barrier -> map() on the sender."""
+
+    def __init__(self, handle: int, num_devices: int):
+        self._h = C.c_void_p(handle)
+        self.num_devices = num_devices
+
+    @staticmethod
+    def create(num_devices: int, bytes_per_device: int, shareable: bool = False) -> "MulticastGroup":
+        h = C.c_void_p()
+        _check(lib().kvbm_mc_group_create(num_devices, bytes_per_device, int(shareable), C.byref(h)))
+        return MulticastGroup(h.value, num_devices)
+
+    @staticmethod
+    def from_fd(fd: int, num_devices: int, bytes_per_device: int) -> "MulticastGroup":
+        h = C.c_void_p()
+        _check(lib().kvbm_mc_group_import_fd(fd, num_devices, bytes_per_device, C.byref(h)))
+        return MulticastGroup(h.value, num_devices)
+
+    @property
+    def size(self) -> int:
+        return lib().kvbm_mc_group_size(self._h)
+
+    def export_fd(self) -> int:
+        fd = C.c_int(-1)
+        _check(lib().kvbm_mc_group_export_fd(self._h, C.byref(fd)))
+        return fd.value
+
+    def add_device(self, device: int) -> None:
+        _check(lib().kvbm_mc_group_add_device(self._h, device))
+
+    def bind_local(self, device: int) -> int:
+        """Allocate + bind this device's pool; returns its ordinary (unicast) device address."""
+        p = C.c_void_p()
+        _check(lib().kvbm_mc_group_bind_local(self._h, device, C.byref(p)))
+        return p.value
+
+    def map(self, device: int) -> int:
+        """Map the multicast object for the sending device; returns the multicast address of offset 0."""
+        p = C.c_void_p()
+        _check(lib().kvbm_mc_group_map(self._h, device, C.byref(p)))
+        return p.value
+
+    def close(self) -> None:
+        if self._h:
+            lib().kvbm_mc_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def detach(self) -> None:
+        """Forget the group without tearing it down (the driver reclaims it at process exit).  Unbinding a multicast
+        object takes the driver seconds; a process that is about to exit need not wait for it."""
+        self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass

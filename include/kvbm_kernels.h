@@ -136,6 +136,12 @@ typedef struct kvbm_paged_copy_opts {
                                      2 / 3 = loads-only / stores-only DIAGNOSTICS (do not copy correctly) */
   int gate_timeout_ms;            /* gated transfers: a layer_ready wait longer than this aborts the launch (completion word
                                      becomes 0xFFFFFFFF, done flags are not written) instead of hanging the GPU; 0 = 10 s */
+  int multicast;                  /* NVLS: non-zero = dsts[0].layout.layer_base[] hold NVLink MULTICAST addresses (a mapping of a
+                                     CUmulticastObject, see kvbm_mc_group_* in kvbm_physical.h).  The payload is written ONCE
+                                     (1 = multimem.st from shared memory, 2 = TMA bulk store) and the NVSwitch delivers it to every
+                                     device bound to the object; dsts[1..] contribute only their done / layer_done flags.  This is
+                                     the replacement of the grouped ncclBcast (kvbm-engine collectives/nccl.rs:421-462): egress of
+                                     the source GPU is 1x the payload instead of Nx.  Requires cast_mode NONE, 16-byte strides. */
 } kvbm_paged_copy_opts;
 
 /* Gather `num_blocks` non-contiguous blocks x layers [layer_begin, layer_end) x outer from `src`,

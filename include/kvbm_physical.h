@@ -103,6 +103,7 @@ typedef struct kvbm_transfer_options {
   uint32_t* layer_done_flags;        /* nullable: device-visible flags on the destination, set per layer */
   uint32_t epoch;
   int gate_timeout_ms;               /* 0 = 10 s; see kvbm_paged_copy_opts.gate_timeout_ms */
+  int multicast;                     /* non-zero: the destination layout is registered over a kvbm_mc_group_map() range */
 } kvbm_transfer_options;
 
 typedef struct kvbm_transfer_manager kvbm_transfer_manager;
@@ -166,6 +167,28 @@ int kvbm_manager_execute_fanout(kvbm_transfer_manager* m, kvbm_layout_handle src
 /* Completion: the transfer's last warp writes a flag in pinned host memory (no cudaEventQuery polling). */
 int kvbm_notification_is_complete(kvbm_transfer_manager* m, kvbm_notification n);  /* 1 / 0 / <0 error */
 int kvbm_notification_wait(kvbm_transfer_manager* m, kvbm_notification n, int64_t timeout_us);
+
+/* ---- NVLS multicast groups: identical KV blocks to N GPUs with ONE write per tile --------------------------------
+ * Replaces CollectiveOps::broadcast / the grouped ncclBcast per region (lib/kvbm-engine/src/collectives/mod.rs:75-106,
+ * nccl.rs:421-462).  Every receiver binds a pool allocation of the same size to one CUmulticastObject; the sender maps
+ * the object and passes a layout over that mapping with kvbm_transfer_options.multicast (host API) or
+ * kvbm_paged_copy_opts.multicast (kernel ABI).  Block b of the layout lands at the same offset in every bound pool.
+ * Order of calls (all participating processes): create | import_fd  ->  add_device (every device, by its owner)
+ * -> [barrier] -> bind_local (each receiver) -> [barrier] -> map (the sender).  bind_local / map block inside the
+ * driver until every device has been added.  Needs NVSwitch + CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED. */
+typedef struct kvbm_mc_group kvbm_mc_group;
+int kvbm_mc_supported(int device);   /* 1 / 0 (kvbm_last_error says why) */
+/* bytes_per_device is rounded up to the multicast granularity (kvbm_mc_group_size).  shareable != 0 allows export_fd. */
+int kvbm_mc_group_create(int num_devices, size_t bytes_per_device, int shareable, kvbm_mc_group** out);
+int kvbm_mc_group_export_fd(kvbm_mc_group* g, int* fd);   /* POSIX fd; pass it to the peers over SCM_RIGHTS */
+int kvbm_mc_group_import_fd(int fd, int num_devices, size_t bytes_per_device, kvbm_mc_group** out);
+size_t kvbm_mc_group_size(const kvbm_mc_group* g);
+int kvbm_mc_group_add_device(kvbm_mc_group* g, int device);
+/* allocate this device's pool (cuMemCreate), map it for the device and bind it at offset 0 of the object */
+int kvbm_mc_group_bind_local(kvbm_mc_group* g, int device, void** unicast_ptr);
+/* map the multicast object for `device` (the sender); stores to the returned range reach every bound pool */
+int kvbm_mc_group_map(kvbm_mc_group* g, int device, void** multicast_ptr);
+void kvbm_mc_group_destroy(kvbm_mc_group* g);
 
 /* accounting for the bench */
 uint64_t kvbm_manager_bytes_moved(kvbm_transfer_manager* m);

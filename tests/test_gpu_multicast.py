@@ -1,0 +1,138 @@
+"""NVLS multicast replicate (needs >= 2 GPUs behind an NVSwitch with multicast support): identical KV blocks written
+ONCE by the source GPU land in every pool bound to the multicast group, byte-exact with the oracle's transfer --
+the replacement of the grouped ncclBcast per region (lib/kvbm-engine/src/collectives/nccl.rs:421-462)."""
+import numpy as np
+import pytest
+import torch
+
+from dynamo_b200 import kernels as K
+from dynamo_b200.physical import (BlockDimension, KvbmError, LayoutConfig, MulticastGroup, StorageKind, TransferManager,
+                                  TransferOptions, multicast_supported)
+from oracle import oracle as O
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu, pytest.mark.timeout(200)]
+
+NB, NL, NO, PAGE, INNER, DT = 64, 4, 2, 16, 1024, 2
+REGION = PAGE * INNER * DT
+PER_LAYER = NO * NB * REGION
+TOTAL = NL * PER_LAYER
+
+
+class _Raw:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def _view(ptr, nbytes, dev):
+    with torch.cuda.device(dev):
+        return torch.as_tensor(_Raw(ptr, nbytes), device=f"cuda:{dev}")
+
+
+@pytest.fixture(scope="module")
+def group():
+    ndev = torch.cuda.device_count()
+    if ndev < 2 or not all(multicast_supported(d) for d in range(ndev)):
+        pytest.skip("needs >= 2 GPUs with NVLink multicast support")
+    for d in range(ndev):
+        torch.zeros(1, device=f"cuda:{d}")
+    torch.cuda.set_device(0)
+    g = MulticastGroup.create(ndev, TOTAL)
+    for d in range(ndev):
+        g.add_device(d)
+    pools = []
+    for d in range(ndev):
+        t = _view(g.bind_local(d), TOTAL, d)
+        t.zero_()
+        pools.append(t)
+    for d in range(ndev):
+        torch.cuda.synchronize(d)
+    mc = g.map(0)
+    yield g, pools, mc
+    for d in range(ndev):
+        torch.cuda.synchronize(d)
+    del pools
+    g.close()   # note: tearing a multicast object down takes the driver tens of seconds; one group serves the module
+
+
+def _src_pool(seed):
+    gen = torch.Generator(device="cuda:0").manual_seed(seed)
+    return [torch.randint(0, 256, (PER_LAYER,), dtype=torch.uint8, device="cuda:0", generator=gen) for _ in range(NL)]
+
+
+def _twin(bufs=None):
+    t = O.Layout(O.LW, NB, NL, NO, PAGE, INNER, DT, block_dim=O.BLOCK_IS_SECOND_DIM)
+    if bufs is not None:
+        for hb, db in zip(t.buffers, bufs):
+            hb[:] = db.cpu().numpy()
+    return t
+
+
+def _cfg():
+    return LayoutConfig(NB, NL, NO, PAGE, INNER, dtype_width_bytes=DT)
+
+
+def _expect(src, sid, did, layers=None):
+    want = _twin()
+    O.execute_memcpy_transfer(_twin(src), want, sid, did, layer_range=layers)
+    return np.concatenate(want.buffers)
+
+
+def _reset(pools):
+    for d, p in enumerate(pools):
+        p.zero_()
+        torch.cuda.synchronize(d)
+
+
+def test_manager_multicast_transfer_reaches_every_bound_pool(group):
+    g, pools, mc = group
+    _reset(pools)
+    mgr = TransferManager(device=0, worker_id=7)
+    src = _src_pool(11)
+    h_src = mgr.register_layer_separate(_cfg(), [b.data_ptr() for b in src], [b.numel() for b in src],
+                                        BlockDimension.BlockIsSecondDim, StorageKind.Device, 0)
+    h_mc = mgr.register_layer_separate(_cfg(), [mc + l * PER_LAYER for l in range(NL)], [PER_LAYER] * NL,
+                                       BlockDimension.BlockIsSecondDim, StorageKind.Device, 0)
+    rng = np.random.default_rng(5)
+    n = 24
+    sid, did = rng.permutation(NB)[:n].tolist(), rng.permutation(NB)[:n].tolist()
+    mgr.execute_transfer(h_src, sid, h_mc, did, TransferOptions(multicast=1)).wait()
+    want = _expect(src, sid, did)
+    for d, p in enumerate(pools):
+        torch.cuda.synchronize(d)
+        assert np.array_equal(p.cpu().numpy(), want), f"pool on cuda:{d} differs from the oracle"
+    # a cast cannot ride on the multicast path: loud error, nothing launched
+    with pytest.raises(KvbmError):
+        mgr.execute_transfer(h_src, sid, h_mc, did, TransferOptions(multicast=1, cast_mode=K.CastMode.FP8E4M3_TO_BF16)).wait()
+    mgr.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_kernel_abi_multicast_with_per_receiver_flags_and_layer_range(group, mode):
+    g, pools, mc = group
+    _reset(pools)
+    ndev = len(pools)
+    mgr = TransferManager(device=0, worker_id=8)
+    for d in range(1, ndev):
+        mgr.enable_peer_access(d)
+    src = _src_pool(12)
+    sbase = torch.tensor([b.data_ptr() for b in src], dtype=torch.int64, device="cuda:0")
+    dbase = torch.tensor([mc + l * PER_LAYER for l in range(NL)], dtype=torch.int64, device="cuda:0")
+    s_desc = K.PagedLayout(sbase.data_ptr(), REGION, REGION * NB, REGION, NL, NO, NB)
+    d_desc = K.PagedLayout(dbase.data_ptr(), REGION, REGION * NB, REGION, NL, NO, NB)
+    rng = np.random.default_rng(6)
+    n = 31
+    sid, did = rng.permutation(NB)[:n], rng.permutation(NB)[:n]
+    s_t = torch.tensor(sid, dtype=torch.int32, device="cuda:0")
+    d_t = torch.tensor(did, dtype=torch.int32, device="cuda:0")
+    flags = [torch.zeros(1 + NL, dtype=torch.int32, device=f"cuda:{d}") for d in range(ndev)]
+    ws = torch.zeros(NL + 2, dtype=torch.int32, device="cuda:0")
+    dsts = [K.PagedDst(d_desc, s_t.data_ptr(), d_t.data_ptr(), f.data_ptr(), f[1:].data_ptr()) for f in flags]
+    opts = K.PagedCopyOpts(epoch=3, sync_workspace=ws.data_ptr(), multicast=mode)
+    K.check(K.paged_copy(s_desc, dsts, n, 1, 3, 0, opts, int(torch.cuda.current_stream().cuda_stream)), "paged_copy")
+    torch.cuda.synchronize(0)
+    want = _expect(src, sid, did, layers=range(1, 3))
+    for d, p in enumerate(pools):
+        torch.cuda.synchronize(d)
+        assert flags[d].tolist() == [3, 0, 3, 3, 0], f"flags on cuda:{d}"
+        assert np.array_equal(p.cpu().numpy(), want), f"pool on cuda:{d} differs from the oracle (multicast={mode})"
+    mgr.close()

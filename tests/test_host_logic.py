@@ -323,3 +323,15 @@ def test_metadata_roundtrip_same_process_and_version_check(mgr):
         mgr.import_metadata(blob[:20])
     with pytest.raises(KvbmError):
         mgr.import_metadata(b"x" * len(blob))
+
+
+def test_multicast_group_fails_loudly_without_a_driver():
+    """No GPU / no libcuda here: the NVLS entry points must say so instead of pretending (no CPU fallback)."""
+    from dynamo_b200.physical import KvbmError, MulticastGroup, multicast_supported
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    assert multicast_supported(0) is False
+    with pytest.raises(KvbmError) as ei:
+        MulticastGroup.create(2, 1 << 21)
+    assert "driver" in str(ei.value).lower() or "cuda" in str(ei.value).lower()

@@ -93,3 +93,32 @@ def test_two_process_gloo_handoff():
         p.join(timeout=30)
     assert results[0][0] == "ok" and results[1][0] == "ok", results
     assert results[0][1] == 8 * NL * NO * REGION
+
+
+def _fd_worker(rank, world, name, path, q):
+    from dynamo_b200.disagg import share_fd
+    if rank == 0:
+        fd = os.open(path, os.O_RDONLY)
+        share_fd(0, world, fd, name)
+        q.put((0, "sent"))
+    else:
+        fd = share_fd(rank, world, None, name)
+        q.put((rank, os.pread(fd, 64, 0)))
+
+
+def test_share_fd_hands_a_descriptor_to_every_rank(tmp_path):
+    """The multicast object's shareable handle is a POSIX fd: it has to cross processes over SCM_RIGHTS."""
+    import multiprocessing as mp
+    p = tmp_path / "token"
+    p.write_bytes(b"multicast-handle-standin")
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    name = f"test-{os.getpid()}"
+    procs = [ctx.Process(target=_fd_worker, args=(r, 3, name, str(p), q)) for r in range(3)]
+    for pr in procs:
+        pr.start()
+    got = dict(q.get(timeout=30) for _ in range(3))
+    for pr in procs:
+        pr.join(30)
+        assert pr.exitcode == 0
+    assert got[0] == "sent" and got[1] == got[2] == b"multicast-handle-standin"
