@@ -102,6 +102,11 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_first_sample(self, timeout_s):
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout_s:
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
@@ -356,10 +361,13 @@ def run_ours(args):
         K.check(K.wait_flag(flag_buf.data_ptr(), W, sp))
         stream.synchronize()
     torch.cuda.synchronize()
-    barrier()
+    # the clock sampler (an nvidia-smi child) starts BEFORE the barrier that opens the timed region: spawning it takes
+    # ~0.1 s on an 8-GPU box, which the destination ranks -- already timing -- would otherwise count as transfer time
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample(2.0)
+    barrier()
     e0, e1 = ev(), ev()
     launches0 = K.launch_count()
     e0.record(stream)
