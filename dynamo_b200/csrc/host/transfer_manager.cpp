@@ -5,8 +5,10 @@
 #include <atomic>
 #include <chrono>
 #include <cstring>
+#include <algorithm>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -17,6 +19,7 @@
 #include <unistd.h>
 
 #include "layout.hpp"
+#include "serialized_layout.hpp"
 
 namespace kvbm_host {
 
@@ -171,6 +174,8 @@ struct kvbm_transfer_manager {
   // CUDA IPC mappings opened by import_metadata, keyed by the 64-byte handle: an allocation shared by several
   // imported layouts (e.g. two tensors in one allocator segment) is mapped once; closed when the manager dies.
   std::unordered_map<std::string, void*> ipc_cache;
+  // (agent name, worker id) of every SerializedLayout imported so far (manager/mod.rs:572-584 refuses a second load)
+  std::set<std::pair<std::string, uint64_t>> loaded_remotes;
 
   Layout* find(kvbm_layout_handle h)
   {
@@ -838,3 +843,232 @@ extern "C" int kvbm_notification_wait(kvbm_transfer_manager* m, kvbm_notificatio
 
 extern "C" uint64_t kvbm_manager_bytes_moved(kvbm_transfer_manager* m) { return m ? m->bytes_moved.load() : 0; }
 extern "C" uint64_t kvbm_manager_h2d_bytes(kvbm_transfer_manager* m) { return m ? m->h2d_bytes.load() : 0; }
+
+// =====================================================================================================
+// SerializedLayout / LayoutDescriptor in the reference's wire formats; codec in serialized_layout.hpp
+// =====================================================================================================
+namespace kvbm_host {
+
+static const char kTransportMagic[8] = {'K', 'V', 'B', 'M', 'I', 'P', 'C', '1'};
+
+static std::string agent_name_of(uint64_t worker_id) { return "kvbm-b200-ipc-" + std::to_string(worker_id); }
+
+// PhysicalLayout::to_descriptor (layout/physical.rs:163-187)
+static kvbm_wire::Descriptor to_wire(const Layout& L, const std::string& agent)
+{
+  kvbm_wire::Descriptor d;
+  d.version = 1;
+  d.num_blocks = L.cfg.num_blocks;
+  d.num_layers = L.cfg.num_layers;
+  d.outer_dim = L.cfg.outer_dim;
+  d.page_size = L.cfg.page_size;
+  d.inner_dim = L.cfg.inner_dim;
+  d.alignment = L.cfg.alignment == 0 ? 1 : L.cfg.alignment;
+  d.dtype_width_bytes = L.cfg.dtype_width_bytes;
+  d.has_num_heads = L.cfg.num_heads != 0;
+  d.num_heads = L.cfg.num_heads;
+  switch (L.storage) {
+    case KVBM_STORAGE_PINNED: d.location = kvbm_wire::kPinned; break;
+    case KVBM_STORAGE_DEVICE:
+      d.location = kvbm_wire::kDevice;
+      d.location_arg = static_cast<uint64_t>(L.device_id);
+      break;
+    case KVBM_STORAGE_DISK: d.location = kvbm_wire::kDisk; break;
+    default: d.location = kvbm_wire::kSystem;
+  }
+  d.agent_name = agent;
+  d.mem_type = L.storage == KVBM_STORAGE_DEVICE ? kvbm_wire::kVram : L.storage == KVBM_STORAGE_DISK ? kvbm_wire::kFile : kvbm_wire::kDram;
+  d.nixl_device_id = L.storage == KVBM_STORAGE_DEVICE ? static_cast<uint64_t>(L.device_id) : 0;
+  for (const Allocation& a : L.allocs) d.regions.push_back({a.addr, a.size});
+  d.fully_contiguous = L.fully_contiguous;
+  d.block_dim = L.block_dim == KVBM_BLOCK_IS_SECOND_DIM ? 1u : 0u;
+  d.kv_block_layout = kvbm_wire::kKvUnknown;
+  return d;
+}
+
+static kvbm_layout_config config_of(const kvbm_wire::Descriptor& d)
+{
+  kvbm_layout_config c{};
+  c.num_blocks = d.num_blocks;
+  c.num_layers = d.num_layers;
+  c.outer_dim = d.outer_dim;
+  c.page_size = d.page_size;
+  c.inner_dim = d.inner_dim;
+  c.alignment = d.alignment;
+  c.dtype_width_bytes = d.dtype_width_bytes;
+  c.num_heads = d.has_num_heads ? d.num_heads : 0;
+  c.allow_fp8 = d.dtype_width_bytes == 1;
+  return c;
+}
+
+// the structural checks of PhysicalLayout::from_descriptor (layout/physical.rs:203-262)
+static int check_descriptor(const kvbm_wire::Descriptor& d)
+{
+  if (d.version > 1) return fail(KVBM_ERR_VERSION, "Unsupported serialization version: " + std::to_string(d.version) + ". Maximum supported: 1");
+  if (d.fully_contiguous && d.regions.size() != 1)
+    return fail(KVBM_ERR_CONFIG, "FullyContiguous layout requires exactly 1 memory region, got " + std::to_string(d.regions.size()));
+  if (!d.fully_contiguous && d.regions.size() != d.num_layers)
+    return fail(KVBM_ERR_CONFIG, "LayerSeparate layout requires " + std::to_string(d.num_layers) + " memory regions (one per layer), got " +
+                                     std::to_string(d.regions.size()));
+  return KVBM_OK;
+}
+
+static int copy_out(const void* data, size_t need, void* buf, size_t cap, size_t* len)
+{
+  *len = need;
+  if (!buf) return KVBM_OK;
+  if (cap < need) return fail(KVBM_ERR, "buffer too small");
+  std::memcpy(buf, data, need);
+  return KVBM_OK;
+}
+
+}  // namespace kvbm_host
+
+extern "C" int kvbm_layout_descriptor_json(kvbm_transfer_manager* m, kvbm_layout_handle h, char* buf, size_t cap, size_t* len)
+{
+  if (!m || !len) return fail(KVBM_ERR, "null argument");
+  std::string js;
+  {
+    std::lock_guard<std::mutex> lk(m->mu);
+    Layout* L = m->find(h);
+    if (!L) return fail(KVBM_ERR_HANDLE, "invalid handle");
+    js = kvbm_wire::descriptor_to_json(to_wire(*L, agent_name_of(m->worker_id)));
+  }
+  return copy_out(js.data(), js.size(), buf, cap, len);
+}
+
+extern "C" int kvbm_manager_import_descriptor_json(kvbm_transfer_manager* m, const char* json, size_t len, kvbm_layout_handle* out)
+{
+  if (!m || !json || !out) return fail(KVBM_ERR, "null argument");
+  kvbm_wire::Descriptor d;
+  std::string why;
+  if (!kvbm_wire::descriptor_from_json(json, len, &d, &why)) return fail(KVBM_ERR, why);
+  int rc = check_descriptor(d);
+  if (rc) return rc;
+  const kvbm_layout_config cfg = config_of(d);
+  Layout L;
+  if (d.fully_contiguous) {
+    rc = make_fully_contiguous(cfg, static_cast<uintptr_t>(d.regions[0].addr), d.regions[0].size, &L, &why);
+  } else {
+    std::vector<uintptr_t> bases;
+    std::vector<size_t> sizes;
+    for (const auto& g : d.regions) {
+      bases.push_back(static_cast<uintptr_t>(g.addr));
+      sizes.push_back(g.size);
+    }
+    rc = make_layer_separate(cfg, bases.data(), sizes.data(), bases.size(), d.block_dim ? KVBM_BLOCK_IS_SECOND_DIM : KVBM_BLOCK_IS_FIRST_DIM, &L, &why);
+  }
+  if (rc) return fail(rc, why);
+  const int storage = d.location == kvbm_wire::kDevice ? KVBM_STORAGE_DEVICE
+                      : d.location == kvbm_wire::kPinned ? KVBM_STORAGE_PINNED
+                      : d.location == kvbm_wire::kDisk   ? KVBM_STORAGE_DISK
+                                                         : KVBM_STORAGE_SYSTEM;
+  return finish_register(m, std::move(L), storage, d.location == kvbm_wire::kDevice ? static_cast<int>(d.location_arg) : 0, out);
+}
+
+// TransferManager::export_metadata (manager/mod.rs:112, registry :519-556): every local host / device layout, one blob.
+// `nixl_metadata` carries this library's transport records instead of a NIXL agent's: per layout one KVBMLAY1 blob with a
+// CUDA IPC handle per allocation, so the importing process can map the pools and reach them over NVLink.
+extern "C" int kvbm_manager_export_serialized_layout(kvbm_transfer_manager* m, void* buf, size_t cap, size_t* len)
+{
+  if (!m || !len) return fail(KVBM_ERR, "null argument");
+  std::vector<kvbm_layout_handle> handles;
+  kvbm_wire::Bundle b;
+  b.worker_id = m->worker_id;
+  b.agent_name = agent_name_of(m->worker_id);
+  {
+    std::lock_guard<std::mutex> lk(m->mu);
+    for (auto& kv : m->layouts)
+      if (!kv.second->remote && kv.second->storage != KVBM_STORAGE_DISK) handles.push_back(kv.first);
+    std::sort(handles.begin(), handles.end());
+    for (kvbm_layout_handle h : handles) {
+      kvbm_wire::Logical l;
+      l.worker_id = m->worker_id;
+      l.layout_id = static_cast<uint16_t>(h & 0xffff);
+      l.logical_type = kvbm_wire::kG2;  // LocalLayoutDescriptor::new_with_default_type (manager/metadata.rs:70-76)
+      l.layout = to_wire(*m->find(h), b.agent_name);
+      b.layouts.push_back(std::move(l));
+    }
+  }
+  kvbm_wire::Writer t;
+  t.raw(kTransportMagic, 8);
+  t.le(handles.size(), 4);
+  for (kvbm_layout_handle h : handles) {
+    size_t need = 0;
+    int rc = kvbm_manager_export_metadata(m, h, nullptr, 0, &need);
+    if (rc) return rc;
+    std::vector<uint8_t> one(need);
+    rc = kvbm_manager_export_metadata(m, h, one.data(), one.size(), &need);
+    if (rc) return rc;
+    t.le(one.size(), 4);
+    t.raw(one.data(), one.size());
+  }
+  b.nixl_metadata = std::move(t.out);
+  const std::vector<uint8_t> bytes = kvbm_wire::encode_bundle(b);
+  return copy_out(bytes.data(), bytes.size(), buf, cap, len);
+}
+
+// TransferManager::import_metadata (manager/mod.rs:130, registry :572-633)
+extern "C" int kvbm_manager_import_serialized_layout(kvbm_transfer_manager* m, const void* buf, size_t len, kvbm_layout_handle* out, size_t cap,
+                                                     size_t* n_out)
+{
+  if (!m || !buf || !n_out) return fail(KVBM_ERR, "null argument");
+  kvbm_wire::Bundle b;
+  std::string why;
+  if (!kvbm_wire::decode_bundle(buf, len, &b, &why)) return fail(KVBM_ERR, why);
+  const auto key = std::make_pair(b.agent_name, b.worker_id);
+  {
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (m->loaded_remotes.count(key))
+      return fail(KVBM_ERR, "Remote worker already loaded: " + b.agent_name + " (worker_id=" + std::to_string(b.worker_id) + ")");
+  }
+  *n_out = b.layouts.size();
+  if (!out) return KVBM_OK;  // size query
+  if (cap < b.layouts.size()) return fail(KVBM_ERR, "handle array too small");
+  // transport records
+  const std::vector<uint8_t>& t = b.nixl_metadata;
+  if (t.size() < 12 || std::memcmp(t.data(), kTransportMagic, 8) != 0)
+    return fail(KVBM_ERR_UNSUPPORTED, "failed to load remote NIXL metadata: the blob carries no KVBM IPC transport records (a NIXL agent's "
+                                      "metadata cannot be used by this library)");
+  uint32_t count;
+  std::memcpy(&count, t.data() + 8, 4);
+  if (count != b.layouts.size()) return fail(KVBM_ERR, "transport record count does not match the layout count");
+  size_t off = 12;
+  std::vector<kvbm_layout_handle> done;
+  auto rollback = [&](int rc) {
+    const std::string msg = kvbm_last_error();
+    for (kvbm_layout_handle h : done) kvbm_manager_unregister(m, h);
+    return fail(rc, msg);
+  };
+  for (size_t i = 0; i < b.layouts.size(); ++i) {
+    const kvbm_wire::Descriptor& d = b.layouts[i].layout;
+    int rc = check_descriptor(d);
+    if (rc) return rollback(rc);
+    uint32_t blen;
+    if (t.size() - off < 4) return rollback(fail(KVBM_ERR, "transport records truncated"));
+    std::memcpy(&blen, t.data() + off, 4);
+    off += 4;
+    if (t.size() - off < blen) return rollback(fail(KVBM_ERR, "transport records truncated"));
+    kvbm_layout_handle h = 0;
+    rc = kvbm_manager_import_metadata(m, t.data() + off, blen, &h);
+    off += blen;
+    if (rc) return rollback(rc);
+    done.push_back(h);
+    // the descriptor and its transport record must describe the same layout
+    bool same;
+    {
+      std::lock_guard<std::mutex> lk(m->mu);
+      const Layout* L = m->find(h);
+      const kvbm_layout_config c = config_of(d);
+      same = L && L->cfg.num_blocks == c.num_blocks && L->cfg.num_layers == c.num_layers && L->cfg.outer_dim == c.outer_dim &&
+             L->cfg.page_size == c.page_size && L->cfg.inner_dim == c.inner_dim && L->cfg.dtype_width_bytes == c.dtype_width_bytes &&
+             L->fully_contiguous == d.fully_contiguous && L->allocs.size() == d.regions.size() &&
+             (d.fully_contiguous || (L->block_dim == KVBM_BLOCK_IS_SECOND_DIM) == (d.block_dim == 1));
+    }
+    if (!same) return rollback(fail(KVBM_ERR_INCOMPATIBLE, "failed to reconstruct layout: descriptor and transport record disagree"));
+  }
+  for (size_t i = 0; i < done.size(); ++i) out[i] = done[i];
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->loaded_remotes.insert(key);
+  return KVBM_OK;
+}

@@ -18,7 +18,7 @@ from __future__ import annotations
 import ctypes as C
 import enum
 from dataclasses import dataclass
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 from . import _lib, kernels
 
@@ -170,6 +170,8 @@ EXPORTED_SYMBOLS = [
     "kvbm_manager_export_metadata", "kvbm_manager_import_metadata", "kvbm_manager_execute_transfer",
     "kvbm_manager_execute_fanout", "kvbm_notification_is_complete", "kvbm_notification_wait",
     "kvbm_manager_bytes_moved", "kvbm_manager_h2d_bytes",
+    "kvbm_manager_export_serialized_layout", "kvbm_manager_import_serialized_layout", "kvbm_layout_descriptor_json",
+    "kvbm_manager_import_descriptor_json",
     "kvbm_mc_supported", "kvbm_mc_group_create", "kvbm_mc_group_export_fd", "kvbm_mc_group_import_fd",
     "kvbm_mc_group_size", "kvbm_mc_group_add_device", "kvbm_mc_group_bind_local", "kvbm_mc_group_map",
     "kvbm_mc_group_destroy",
@@ -210,6 +212,10 @@ def lib() -> C.CDLL:
         L.kvbm_manager_bytes_moved.restype = u64
         L.kvbm_manager_h2d_bytes.argtypes = [vp]
         L.kvbm_manager_h2d_bytes.restype = u64
+        L.kvbm_manager_export_serialized_layout.argtypes = [vp, vp, sz, P(sz)]
+        L.kvbm_manager_import_serialized_layout.argtypes = [vp, vp, sz, P(u64), sz, P(sz)]
+        L.kvbm_layout_descriptor_json.argtypes = [vp, u64, vp, sz, P(sz)]
+        L.kvbm_manager_import_descriptor_json.argtypes = [vp, C.c_char_p, sz, P(u64)]
         L.kvbm_mc_supported.argtypes = [i]
         L.kvbm_mc_group_create.argtypes = [i, sz, i, P(vp)]
         L.kvbm_mc_group_export_fd.argtypes = [vp, P(i)]
@@ -353,6 +359,40 @@ class TransferManager:
         out = C.c_uint64()
         buf = C.create_string_buffer(blob, len(blob))
         _check(lib().kvbm_manager_import_metadata(self._h, buf, len(blob), C.byref(out)))
+        return out.value
+
+    # -- the reference's wire formats ----------------------------------------------
+    def export_serialized_layout(self) -> bytes:
+        """`TransferManager::export_metadata()` (manager/mod.rs:112): every local host/device layout in ONE
+        `SerializedLayout` blob (bincode 2 over `RdmaLayoutDescriptors`, manager/metadata.rs:87-134)."""
+        n = C.c_size_t()
+        _check(lib().kvbm_manager_export_serialized_layout(self._h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(max(1, n.value))
+        _check(lib().kvbm_manager_export_serialized_layout(self._h, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def import_serialized_layout(self, blob: bytes) -> List[int]:
+        """`TransferManager::import_metadata()` (manager/mod.rs:130): handles of the imported remote layouts."""
+        buf = C.create_string_buffer(blob, len(blob))
+        n = C.c_size_t()
+        _check(lib().kvbm_manager_import_serialized_layout(self._h, buf, len(blob), None, 0, C.byref(n)))
+        out = (C.c_uint64 * max(1, n.value))()
+        _check(lib().kvbm_manager_import_serialized_layout(self._h, buf, len(blob), out, n.value, C.byref(n)))
+        return [int(out[i]) for i in range(n.value)]
+
+    def layout_descriptor_json(self, handle: int) -> str:
+        """`LayoutDescriptor::to_json` (layout/serialize.rs:96-103) of a registered layout."""
+        n = C.c_size_t()
+        _check(lib().kvbm_layout_descriptor_json(self._h, handle, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(max(1, n.value))
+        _check(lib().kvbm_layout_descriptor_json(self._h, handle, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value].decode()
+
+    def import_descriptor_json(self, text: str) -> int:
+        """`LayoutDescriptor::from_json` + `PhysicalLayout::from_descriptor` (layout/physical.rs:203-262)."""
+        raw = text.encode()
+        out = C.c_uint64()
+        _check(lib().kvbm_manager_import_descriptor_json(self._h, raw, len(raw), C.byref(out)))
         return out.value
 
     # -- transfers ----------------------------------------------------------------------------------

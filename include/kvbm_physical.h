@@ -152,6 +152,23 @@ int kvbm_manager_export_metadata(kvbm_transfer_manager* m, kvbm_layout_handle h,
                                  size_t* len);
 int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void* buf, size_t len, kvbm_layout_handle* out);
 
+/* The reference's own wire formats for the handshake:
+ *   kvbm_manager_export_serialized_layout / import_serialized_layout = TransferManager::export_metadata / import_metadata
+ *   (manager/mod.rs:112,130): ONE blob for every local host/device layout, encoded exactly as SerializedLayout::pack
+ *   (manager/metadata.rs:120-134: bincode 2 standard config over RdmaLayoutDescriptors).  Its `nixl_metadata` byte
+ *   field carries this library's CUDA-IPC transport records instead of a NIXL agent's metadata; a second import of
+ *   the same (agent, worker_id) fails like the reference ("Remote worker already loaded").  import with out == NULL
+ *   returns the number of layouts in *n_out.
+ *   kvbm_layout_descriptor_json / kvbm_manager_import_descriptor_json = LayoutDescriptor::to_json / from_json +
+ *   PhysicalLayout::from_descriptor (layout/serialize.rs:96-137, layout/physical.rs:203-262); JSON-imported layouts
+ *   keep the addresses as written (same address space).  Handles on the wire are the reference's u128
+ *   (worker_id | layout_id << 64, manager/handle.rs:16-24); this ABI's 64-bit handle is (worker_id << 16) | layout_id. */
+int kvbm_manager_export_serialized_layout(kvbm_transfer_manager* m, void* buf, size_t cap, size_t* len);
+int kvbm_manager_import_serialized_layout(kvbm_transfer_manager* m, const void* buf, size_t len, kvbm_layout_handle* out,
+                                          size_t cap, size_t* n_out);
+int kvbm_layout_descriptor_json(kvbm_transfer_manager* m, kvbm_layout_handle h, char* buf, size_t cap, size_t* len);
+int kvbm_manager_import_descriptor_json(kvbm_transfer_manager* m, const char* json, size_t len, kvbm_layout_handle* out);
+
 /* execute_transfer (manager/mod.rs:227-303).  ids are host arrays, consumed before return. */
 int kvbm_manager_execute_transfer(kvbm_transfer_manager* m, kvbm_layout_handle src, const size_t* src_ids,
                                   kvbm_layout_handle dst, const size_t* dst_ids, size_t n,
