@@ -42,3 +42,14 @@ extern "C" cudaError_t standin_attention_layer(const void* in, void* out, size_t
                                                    value, counter, fma_iters);
   return cudaGetLastError();
 }
+
+// Bench-only: what the v1 block manager's D2D path and UCX cuda_ipc do -- one cudaMemcpyAsync per (block, layer, outer)
+// chunk (lib/llm/src/block_manager/block/transfer/cuda.rs:299-391).  Host arrays of addresses.
+extern "C" cudaError_t memcpy_per_chunk(void* const* src, void* const* dst, size_t n, size_t bytes, cudaStream_t stream)
+{
+  for (size_t i = 0; i < n; ++i) {
+    cudaError_t e = cudaMemcpyAsync(dst[i], src[i], bytes, cudaMemcpyDefault, stream);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
