@@ -23,6 +23,7 @@ ap.add_argument("--layers", type=int, default=32)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--ctas", type=int, default=0)
 ap.add_argument("--modes", default="1,2")
+ap.add_argument("--sweep", action="store_true", help="grid over CTAs / warps / stages / tile for the multicast modes (tuning)")
 ap.add_argument("--out", default="gpurun_out/mc_bench.json")
 a = ap.parse_args()
 
@@ -80,9 +81,10 @@ sp = int(torch.cuda.current_stream().cuda_stream)
 payload = n * NL * NO * REGION
 
 
-def run_mc(mode):
+def run_mc(mode, ctas=None, warps=0, stages=0, tile=0):
     K.check(K.paged_copy(s_desc, [K.PagedDst(mc_desc, sid.data_ptr(), did.data_ptr(), 0, 0)], n, 0, NL, 0,
-                         K.PagedCopyOpts(multicast=mode, max_ctas=a.ctas), sp))
+                         K.PagedCopyOpts(multicast=mode, max_ctas=a.ctas if ctas is None else ctas, warps_per_cta=warps,
+                                         stages=stages, tile_bytes=tile), sp))
 
 
 def run_unicast(receivers):
@@ -134,6 +136,21 @@ for mode, name in ((1, "multicast_st"), (2, "multicast_tma")):
         print(name, "FAILED", repr(e), flush=True)
         break
     print(name, res[name], flush=True)
+if a.sweep:
+    res["sweep"] = []
+    for mode in (1, 2):
+        for ctas in (16, 32, 48, 74, 111, 148):
+            for warps, stages, tile in ((4, 3, 16384), (8, 3, 8192), (8, 4, 4096), (4, 6, 8192), (2, 3, 32768)):
+                fn = lambda: run_mc(mode, ctas, warps, stages, tile)  # noqa: E731
+                try:
+                    ms = t_ms(fn)
+                except Exception as e:  # noqa: BLE001
+                    print("sweep point failed", mode, ctas, warps, stages, tile, repr(e), flush=True)
+                    continue
+                row = {"mode": mode, "ctas": ctas, "warps": warps, "stages": stages, "tile": tile, "ms": ms, "egress_GBps": payload / ms / 1e6}
+                res["sweep"].append(row)
+                print(row, flush=True)
+    verify("after sweep")
 recv = list(range(1, nd))[:7]
 run_unicast(recv)
 torch.cuda.synchronize()
