@@ -463,7 +463,7 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
     dd[d].layout = descriptor(*D[d]);
     dd[d].src_block_ids = dev_src[d];
     dd[d].dst_block_ids = dev_dst[d];
-    dd[d].done_flag = nullptr;
+    dd[d].done_flag = (d == 0) ? o.done_flag : nullptr;
     dd[d].layer_done_flags = (d == 0) ? o.layer_done_flags : nullptr;
   }
   kvbm_paged_copy_opts ko{};

@@ -96,6 +96,7 @@ class _COptions(C.Structure):
         ("epoch", C.c_uint32),
         ("gate_timeout_ms", C.c_int),
         ("multicast", C.c_int),
+        ("done_flag", C.c_void_p),
     ]
 
 
@@ -139,6 +140,7 @@ class TransferOptions:
     epoch: int = 0
     gate_timeout_ms: int = 0
     multicast: int = 0                    # destination layout lives in a MulticastGroup.map() range (NVLS)
+    done_flag: int = 0                    # word on the destination GPU that receives `epoch` on completion (cf. nixl_write_notification)
 
     @staticmethod
     def from_layer_range(layer_range: Optional[range]) -> "TransferOptions":
@@ -149,7 +151,7 @@ class TransferOptions:
         return _COptions(int(lr is not None), lr.start if lr is not None else 0, lr.stop if lr is not None else 0,
                          self.cuda_stream or 0, int(self.cuda_stream is not None), int(self.cast_mode), self.max_ctas,
                          self.layer_ready_flags, self.layer_done_flags, self.epoch, self.gate_timeout_ms,
-                         int(self.multicast))
+                         int(self.multicast), self.done_flag)
 
 
 @dataclass

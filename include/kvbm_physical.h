@@ -104,6 +104,9 @@ typedef struct kvbm_transfer_options {
   uint32_t epoch;
   int gate_timeout_ms;               /* 0 = 10 s; see kvbm_paged_copy_opts.gate_timeout_ms */
   int multicast;                     /* non-zero: the destination layout is registered over a kvbm_mc_group_map() range */
+  uint32_t* done_flag;               /* nullable: word in the DESTINATION GPU's memory that receives `epoch` once every byte of
+                                        the transfer has landed -- the role of TransferOptions::nixl_write_notification
+                                        (options.rs:36-43: "delivered to the remote node after the RDMA write completes") */
 } kvbm_transfer_options;
 
 typedef struct kvbm_transfer_manager kvbm_transfer_manager;

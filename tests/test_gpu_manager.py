@@ -223,3 +223,20 @@ def test_layer_streaming_with_ready_and_done_flags(mgr):
     O.execute_memcpy_transfer(src.twin, ref, sid, did)
     for got, want in zip(dst.bytes(), ref.buffers):
         assert np.array_equal(got, want)
+
+
+def test_done_flag_option_delivers_the_epoch_to_destination_memory(mgr):
+    """TransferOptions::nixl_write_notification (options.rs:36-43) restated for peer stores: a word in the destination's
+    memory receives the value once every byte has landed."""
+    src, dst = Pool(mgr, "LWs", 8, StorageKind.Device), Pool(mgr, "LWs", 8, StorageKind.Device)
+    src.twin.fill_blocks([0, 1, 2], -1)
+    src.upload()
+    flag = torch.zeros(4, dtype=torch.int32, device="cuda")
+    note = mgr.execute_transfer(src.h, [0, 1, 2], dst.h, [5, 6, 7], TransferOptions(done_flag=flag[1:].data_ptr(), epoch=77))
+    note.wait(20.0)
+    torch.cuda.synchronize()
+    assert flag.tolist() == [0, 77, 0, 0]
+    ref = O.Layout(dst.twin.kind, 8, 2, 2, 16, 128, 2, block_dim=dst.twin.c.block_dim)
+    O.execute_memcpy_transfer(src.twin, ref, [0, 1, 2], [5, 6, 7])
+    for got, want in zip(dst.bytes(), ref.buffers):
+        assert np.array_equal(got, want)
