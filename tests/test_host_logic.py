@@ -335,3 +335,24 @@ def test_multicast_group_fails_loudly_without_a_driver():
     with pytest.raises(KvbmError) as ei:
         MulticastGroup.create(2, 1 << 21)
     assert "driver" in str(ei.value).lower() or "cuda" in str(ei.value).lower()
+
+
+def test_public_headers_are_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/*.h must compile as C99 (no C++-isms, no torch types), and a C caller can
+    name every struct a binding needs."""
+    import shutil
+    gcc = shutil.which("gcc")
+    cuda_inc = "/usr/local/cuda/include"
+    if not gcc or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime_api.h")):
+        pytest.skip("gcc or the CUDA headers are not installed")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "kvbm_kernels.h"\n#include "kvbm_physical.h"\n#include "kvbm_router.h"\n'
+                   "int main(void) {\n"
+                   "  static kvbm_paged_layout l; static kvbm_paged_dst d; static kvbm_paged_copy_opts o;\n"
+                   "  static kvbm_layout_config c; static kvbm_transfer_options t; static kvbm_transfer_plan p;\n"
+                   "  (void)l; (void)d; (void)o; (void)c; (void)t; (void)p;\n"
+                   "  return kvbm_kernels_is_stub_build() ? 1 : 0;\n}\n")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"),
+                        "-I", cuda_inc, str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
