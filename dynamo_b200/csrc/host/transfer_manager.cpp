@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <memory>
@@ -233,22 +234,70 @@ static kvbm_paged_layout descriptor(const Layout& L)
 }
 
 // memcpy.rs:98-165
+// executor/memcpy.rs:30-165.  The reference copies chunk after chunk on the calling thread; here the chunk list is
+// resolved (and fully validated) first and large requests are split over host threads -- destination blocks are
+// unique (validate_block_transfer), so the pieces are disjoint.  Still synchronous: returns when every byte is written.
+struct HostCopy {
+  void* dst;
+  const void* src;
+  size_t bytes;
+};
+
+static unsigned memcpy_threads()
+{
+  static const unsigned n = [] {
+    if (const char* e = std::getenv("KVBM_MEMCPY_THREADS")) {
+      const long v = std::atol(e);
+      if (v >= 1) return static_cast<unsigned>(std::min<long>(v, 256));
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(hw ? hw : 1u, 32u));   // memory-bound: more threads than memory channels buys nothing
+  }();
+  return n;
+}
+
+static void run_host_copies(const std::vector<HostCopy>& cs)
+{
+  size_t total = 0;
+  for (const HostCopy& c : cs) total += c.bytes;
+  const unsigned want = memcpy_threads();
+  constexpr size_t kParallelFrom = 8u << 20;   // below this the thread start-up costs more than it saves
+  if (want <= 1 || total < kParallelFrom || cs.size() < 2) {
+    for (const HostCopy& c : cs) std::memcpy(c.dst, c.src, c.bytes);
+    return;
+  }
+  const unsigned T = static_cast<unsigned>(std::min<size_t>(want, cs.size()));
+  auto work = [&](unsigned t) {
+    const size_t lo = cs.size() * t / T, hi = cs.size() * (t + 1) / T;
+    for (size_t i = lo; i < hi; ++i) std::memcpy(cs[i].dst, cs[i].src, cs[i].bytes);
+  };
+  std::vector<std::thread> th;
+  th.reserve(T - 1);
+  for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+}
+
 static int host_memcpy_transfer(const Layout& S, const Layout& D, const size_t* sid, const size_t* did, size_t n,
                                 bool has_range, size_t lb, size_t le)
 {
   const bool full = !has_range || (lb == 0 && le == S.cfg.num_layers);
   std::string why;
+  std::vector<HostCopy> cs;
   if (full && S.fully_contiguous && D.fully_contiguous) {  // can_use_whole_block_transfer, transfer/mod.rs:150-173
     const size_t bytes = bytes_per_block(S.cfg);
+    cs.reserve(n);
     for (size_t i = 0; i < n; ++i) {
       uintptr_t s, d;
       int rc;
       if ((rc = S.memory_region(sid[i], 0, 0, &s, nullptr, &why))) return fail(rc, why);
       if ((rc = D.memory_region(did[i], 0, 0, &d, nullptr, &why))) return fail(rc, why);
-      std::memcpy(reinterpret_cast<void*>(d), reinterpret_cast<const void*>(s), bytes);
+      cs.push_back({reinterpret_cast<void*>(d), reinterpret_cast<const void*>(s), bytes});
     }
+    run_host_copies(cs);
     return KVBM_OK;
   }
+  cs.reserve(n * (le - lb) * S.cfg.outer_dim);
   for (size_t i = 0; i < n; ++i)
     for (size_t l = lb; l < le; ++l)
       for (size_t o = 0; o < S.cfg.outer_dim; ++o) {
@@ -261,8 +310,9 @@ static int host_memcpy_transfer(const Layout& S, const Layout& D, const size_t* 
           return fail(KVBM_ERR_INCOMPATIBLE, "Memory region size mismatch at block=(" + std::to_string(sid[i]) + "," + std::to_string(did[i]) +
                                                  "), layer=" + std::to_string(l) + ", outer=" + std::to_string(o) + ": src=" + std::to_string(ss) +
                                                  ", dst=" + std::to_string(ds));
-        std::memcpy(reinterpret_cast<void*>(d), reinterpret_cast<const void*>(s), ss);
+        cs.push_back({reinterpret_cast<void*>(d), reinterpret_cast<const void*>(s), ss});
       }
+  run_host_copies(cs);
   return KVBM_OK;
 }
 

@@ -356,3 +356,27 @@ def test_public_headers_are_plain_c(tmp_path):
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"),
                         "-I", cuda_inc, str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.parametrize("kinds", [("LWs", "LWs"), ("FC", "FC"), ("LWs", "FC")])
+def test_config1_sized_host_transfer_is_bit_exact_when_split_over_threads(mgr, kinds):
+    """BASELINE configs[0] geometry (Llama-3-8B: 32 layers x K/V x 32 KiB regions), 96 of 192 blocks = 192 MiB: large enough
+    that the Memcpy strategy splits the chunk list over host threads; BLAKE3 per block must equal the oracle's copy."""
+    nb, n = 192, 96
+    kw = dict(nl=32, no=2, page=16, inner=1024, dt=2)
+    hs, src = host_layout(mgr, kinds[0], nb, **kw)
+    hd, dst = host_layout(mgr, kinds[1], nb, **kw)
+    _, ref = host_layout(mgr, kinds[1], nb, **kw)
+    rng = np.random.default_rng(1234)
+    for b in src.buffers:
+        b[:] = rng.integers(0, 256, b.size, dtype=np.uint8)
+    sid = np.random.default_rng(0).permutation(nb)[:n]
+    did = np.random.default_rng(1).permutation(nb)[:n]
+    note = mgr.execute_transfer(hs, sid.astype(np.uint64), hd, did.astype(np.uint64))
+    assert note.is_complete()          # memcpy.rs:91-92: synchronous, already complete
+    O.execute_memcpy_transfer(src, ref, sid, did)
+    for got, want in zip(dst.buffers, ref.buffers):
+        assert np.array_equal(got, want)
+    # BLAKE3 by position (local_transfers.rs:108-171): destination block i carries the checksum of source block i
+    want, got = src.block_checksums(sid.tolist()), dst.block_checksums(did.tolist())
+    assert [got[int(d)] for d in did] == [want[int(s)] for s in sid]
