@@ -173,3 +173,32 @@ def test_pull_direction_decode_side_reads_prefill_pool():
     for a, b in zip(_twin(dst).buffers, ref.buffers):
         assert np.array_equal(a, b)
     mgr.close()
+
+
+def test_pull_with_fused_upcast_ships_fp8_over_nvlink():
+    """Receiver-side up-cast: the decode GPU pulls the prefill GPU's fp8 pool and widens it to bf16 while
+    storing locally, so only HALF the bytes cross NVLink.  Same kernel, launched on the destination, cast mode 1."""
+    mgr = TransferManager(device=1, worker_id=3)
+    mgr.enable_peer_access(0)
+    region8 = PAGE * INNER          # fp8 source regions are half the size
+    src = [torch.zeros(NO * NB * region8, dtype=torch.uint8, device="cuda:0") for _ in range(NL)]
+    g = torch.Generator(device="cuda:0").manual_seed(10)
+    for b in src:
+        b.copy_(torch.randint(0, 256, b.shape, dtype=torch.uint8, device="cuda:0", generator=g))
+    dst = _pool(1)
+    cfg8 = LayoutConfig(NB, NL, NO, PAGE, INNER, dtype_width_bytes=1, allow_fp8=True)
+    h_src = mgr.register_layer_separate(cfg8, [b.data_ptr() for b in src], [b.numel() for b in src],
+                                        BlockDimension.BlockIsSecondDim, StorageKind.Device, 0)
+    h_dst = _register(mgr, dst, 1)
+    rng = np.random.default_rng(5)
+    sid, did = list(map(int, rng.permutation(NB)[:30])), list(map(int, rng.permutation(NB)[:30]))
+    torch.cuda.synchronize(0)
+    mgr.execute_transfer(h_src, sid, h_dst, did, TransferOptions(cast_mode=K.CastMode.FP8E4M3_TO_BF16)).wait()
+    src_t = O.Layout(O.LW, NB, NL, NO, PAGE, INNER, 1, block_dim=O.BLOCK_IS_SECOND_DIM, allow_fp8=True)
+    for hb, db in zip(src_t.buffers, src):
+        hb[:] = db.cpu().numpy()
+    ref = O.Layout(O.LW, NB, NL, NO, PAGE, INNER, DT, block_dim=O.BLOCK_IS_SECOND_DIM)
+    O.execute_memcpy_transfer(src_t, ref, sid, did, cast_mode=1)
+    for a, b in zip(_twin(dst).buffers, ref.buffers):
+        assert np.array_equal(a, b)
+    mgr.close()
