@@ -47,12 +47,52 @@ static int fail_cuda(cudaError_t e, const char* what)
 // ---------------------------------------------------------------------------------------------------
 // validation.rs
 // ---------------------------------------------------------------------------------------------------
+// Fast path of the three checks below for the common case (every id in range): one bitmap over the destination's
+// block ids instead of a hash set -- 256 ids cost ~0.3 us instead of ~10 us, which is a tenth of a whole 512 MiB
+// same-GPU transfer.  Returns false when anything is wrong (or an id is out of range); the reference-ordered slow
+// path then produces the exact error.
+static bool validate_fast(const size_t* src_ids, const size_t* dst_ids, size_t n, size_t src_blocks, size_t dst_blocks,
+                          bool same_layout)
+{
+  thread_local std::vector<uint64_t> bits;
+  const size_t words = (dst_blocks + 63) / 64;
+  if (words > (1u << 20)) return false;  // absurdly large pools: take the general path
+  if (bits.size() < words) bits.resize(words, 0);
+  bool ok = true;
+  size_t marked = 0;
+  for (; marked < n; ++marked) {
+    const size_t d = dst_ids[marked];
+    if (d >= dst_blocks || src_ids[marked] >= src_blocks) {
+      ok = false;
+      break;
+    }
+    uint64_t& w = bits[d >> 6];
+    const uint64_t m = 1ull << (d & 63);
+    if (w & m) {
+      ok = false;
+      break;
+    }
+    w |= m;
+  }
+  if (ok && same_layout)
+    for (size_t i = 0; i < n; ++i) {
+      const size_t v = src_ids[i];
+      if (v < dst_blocks && (bits[v >> 6] >> (v & 63)) & 1) {
+        ok = false;
+        break;
+      }
+    }
+  for (size_t i = 0; i < marked; ++i) bits[dst_ids[i] >> 6] = 0;  // leave the scratch bitmap clean
+  return ok;
+}
+
 static int validate_block_transfer(const size_t* src_ids, size_t n_src, const size_t* dst_ids, size_t n_dst,
                                    size_t src_blocks, size_t dst_blocks, bool same_layout)
 {
   if (n_src != n_dst)  // validation.rs:177-183
     return fail(KVBM_ERR_LENGTH_MISMATCH, "Block ID lists have mismatched lengths: src=" + std::to_string(n_src) +
                                               ", dst=" + std::to_string(n_dst) + ", bounce=None");
+  if (n_src == 0 || validate_fast(src_ids, dst_ids, n_src, src_blocks, dst_blocks, same_layout)) return KVBM_OK;
   std::unordered_set<size_t> seen;
   seen.reserve(n_dst * 2);
   for (size_t i = 0; i < n_dst; ++i)  // validate_dst_unique, validation.rs:55-70
