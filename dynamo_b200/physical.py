@@ -180,8 +180,13 @@ EXPORTED_SYMBOLS = [
 ]
 
 
+_LIB: Optional[C.CDLL] = None
+
+
 def lib() -> C.CDLL:
-    global _configured
+    global _configured, _LIB
+    if _LIB is not None:      # hot path: every transfer goes through here twice
+        return _LIB
     kernels.lib()  # dependency (resolved through $ORIGIN rpath as well)
     L = _lib.load(_lib.PHYSICAL_SO)
     if not _configured:
@@ -206,7 +211,8 @@ def lib() -> C.CDLL:
         L.kvbm_manager_enable_peer_access.argtypes = [vp, i]
         L.kvbm_manager_export_metadata.argtypes = [vp, u64, vp, sz, P(sz)]
         L.kvbm_manager_import_metadata.argtypes = [vp, vp, sz, P(u64)]
-        L.kvbm_manager_execute_transfer.argtypes = [vp, u64, P(sz), u64, P(sz), sz, P(_COptions), P(u64)]
+        # the id lists are `const size_t*`; declared void* so a raw address (numpy buffer) passes without a ctypes cast
+        L.kvbm_manager_execute_transfer.argtypes = [vp, u64, vp, u64, vp, sz, P(_COptions), P(u64)]
         L.kvbm_manager_execute_fanout.argtypes = [vp, u64, i, P(u64), P(P(sz)), P(P(sz)), sz, i, P(_COptions), P(u64)]
         L.kvbm_notification_is_complete.argtypes = [vp, u64]
         L.kvbm_notification_wait.argtypes = [vp, u64, C.c_int64]
@@ -230,6 +236,7 @@ def lib() -> C.CDLL:
         L.kvbm_mc_group_destroy.argtypes = [vp]
         L.kvbm_mc_group_destroy.restype = None
         _configured = True
+    _LIB = L
     return L
 
 
@@ -238,24 +245,33 @@ def _check(rc: int) -> None:
         raise KvbmError(rc, lib().kvbm_last_error().decode(errors="replace"))
 
 
+try:
+    import numpy as _np
+    _NP_ID_DTYPES = (_np.dtype(_np.uint64), _np.dtype(_np.int64))
+except ImportError:  # pragma: no cover
+    _np = None
+    _NP_ID_DTYPES = ()
+
+
 def _size_array(ids: Sequence[int]):
     """Host block-id list -> `const size_t*`.  numpy int64/uint64 arrays are passed without copying."""
     n = len(ids)
-    try:
-        import numpy as np
-        if isinstance(ids, np.ndarray) and ids.dtype in (np.uint64, np.int64) and ids.flags.c_contiguous:
-            return _NpView(ids), n
-    except ImportError:  # pragma: no cover
-        pass
+    if _np is not None and isinstance(ids, _np.ndarray) and ids.dtype in _NP_ID_DTYPES and ids.flags.c_contiguous:
+        return _NpView(ids), n
     return (C.c_size_t * max(1, n))(*[int(x) for x in ids]), n
 
 
 class _NpView:
-    """Keeps the numpy array alive and presents it as a ctypes pointer argument."""
+    """Keeps the numpy array alive and presents its buffer as a pointer argument."""
+    __slots__ = ("arr", "addr")
 
     def __init__(self, arr):
         self.arr = arr
-        self._as_parameter_ = arr.ctypes.data_as(C.POINTER(C.c_size_t))
+        self.addr = arr.__array_interface__["data"][0]
+
+    @property
+    def _as_parameter_(self):     # only the fan-out / validation paths need a typed pointer
+        return C.cast(self.addr, C.POINTER(C.c_size_t))
 
 
 def select_direct_strategy(src: StorageKind, dst: StorageKind, allow_gds: bool = False,
@@ -407,8 +423,11 @@ class TransferManager:
         s, n = _size_array(src_block_ids)
         d, _ = _size_array(dst_block_ids)
         tok = C.c_uint64()
-        o = (options or TransferOptions())._c()
-        _check(lib().kvbm_manager_execute_transfer(self._h, src, s, dst, d, n, C.byref(o), C.byref(tok)))
+        o = options._c() if options is not None else _COptions()
+        rc = lib().kvbm_manager_execute_transfer(self._h, src, s.addr if type(s) is _NpView else s, dst,
+                                                 d.addr if type(d) is _NpView else d, n, C.byref(o), C.byref(tok))
+        if rc:
+            _check(rc)
         return TransferCompleteNotification(self, tok.value)
 
     def execute_fanout(self, src: int, dsts: Sequence[int], src_block_ids: Sequence[Sequence[int]],
@@ -422,7 +441,7 @@ class TransferManager:
         s_arrays = [_size_array(x)[0] for x in (src_block_ids if not replicate else [src_block_ids[0]] * nd)]
         d_arrays = [_size_array(x)[0] for x in dst_block_ids]
         PP = C.POINTER(C.c_size_t)
-        as_ptr = lambda a: a._as_parameter_ if isinstance(a, _NpView) else C.cast(a, PP)
+        as_ptr = lambda a: a._as_parameter_ if isinstance(a, _NpView) else C.cast(a, PP)  # noqa: E731
         sp = (PP * nd)(*[as_ptr(a) for a in s_arrays])
         dp = (PP * nd)(*[as_ptr(a) for a in d_arrays])
         tok = C.c_uint64()
