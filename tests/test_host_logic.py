@@ -380,3 +380,28 @@ def test_config1_sized_host_transfer_is_bit_exact_when_split_over_threads(mgr, k
     # BLAKE3 by position (local_transfers.rs:108-171): destination block i carries the checksum of source block i
     want, got = src.block_checksums(sid.tolist()), dst.block_checksums(did.tolist())
     assert [got[int(d)] for d in did] == [want[int(s)] for s in sid]
+
+
+@pytest.mark.parametrize("as_numpy", [True, False])
+@pytest.mark.parametrize("replicate", [True, False])
+def test_fanout_over_host_layouts_matches_oracle(mgr, as_numpy, replicate):
+    """execute_fanout / CollectiveOps::broadcast semantics on the Memcpy strategy (host pools): every destination gets its own
+    (src, dst) table -- or the same source blocks when replicating -- and equals the oracle's copy."""
+    nb, n, nd = 24, 9, 3
+    hs, src = host_layout(mgr, "LWs", nb)
+    rng = np.random.default_rng(77)
+    for b in src.buffers:
+        b[:] = rng.integers(0, 256, b.size, dtype=np.uint8)
+    dsts = [host_layout(mgr, "LWs", nb) for _ in range(nd)]
+    refs = [host_layout(mgr, "LWs", nb)[1] for _ in range(nd)]
+    sids = [rng.permutation(nb)[:n] for _ in range(nd)]
+    if replicate:
+        sids = [sids[0]] * nd
+    dids = [rng.permutation(nb)[:n] for _ in range(nd)]
+    conv = (lambda a: a.astype(np.uint64)) if as_numpy else (lambda a: [int(x) for x in a])
+    note = mgr.execute_fanout(hs, [h for h, _ in dsts], [conv(s) for s in sids], [conv(d) for d in dids], replicate)
+    assert note.is_complete()
+    for (h, twin), ref, s, d in zip(dsts, refs, sids, dids):
+        O.execute_memcpy_transfer(src, ref, s, d)
+        for got, want in zip(twin.buffers, ref.buffers):
+            assert np.array_equal(got, want)
