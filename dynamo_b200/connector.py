@@ -206,13 +206,21 @@ class KvConnectorWorker:
         first = kv_caches[0][1]
         shape = list(first.shape)
         block_dim = device_layout_type if isinstance(device_layout_type, BlockDimension) else layer_separate_auto(shape, num_device_blocks)
-        od = outer_dim if outer_dim is not None else (shape[1] if block_dim == BlockDimension.BlockIsFirstDim else shape[0])
+        if outer_dim is not None and inner_dim is not None:                          # explicit dims: use as they are
+            od, inner = outer_dim, inner_dim
+        else:
+            # distributed/worker.rs:554-578: outer_dim is encoded in the shape when the candidate axis is <= 2
+            # ([outer, n_blocks, page, inner] / [n_blocks, outer, page, inner]); otherwise the tensor has no K/V
+            # axis (MLA: [n_blocks, page, latent]) -> outer_dim = 1 and inner_dim from every dim after n_blocks
+            candidate = shape[1] if block_dim == BlockDimension.BlockIsFirstDim else shape[0]
+            tail = shape[2:] if candidate <= 2 else (shape[1:] if block_dim == BlockDimension.BlockIsFirstDim else shape[2:])
+            per_block = 1
+            for s in tail:
+                per_block *= int(s)
+            od = outer_dim if outer_dim is not None else (candidate if candidate <= 2 else 1)
+            inner = inner_dim if inner_dim is not None else per_block // page_size
         if od not in (1, 2):
             raise ValueError(f"outer_dim must be 1 or 2, got {od}")
-        per_block = 1
-        for s in shape[2:]:
-            per_block *= int(s)
-        inner = inner_dim if inner_dim is not None else per_block // page_size
         cfg = LayoutConfig(num_device_blocks, len(kv_caches), od, page_size, inner, dtype_width_bytes=dtype_width_bytes,
                            allow_fp8=dtype_width_bytes == 1)
         on_device = bool(getattr(first, "is_cuda", False))
@@ -379,3 +387,96 @@ class KvConnectorWorker:
             else:
                 rest.append((note, cr))
         self._inflight = rest
+
+
+class TrtllmKvConnectorWorker(KvConnectorWorker):
+    """The TRT-LLM flavour of the worker (`PyTrtllmKvConnectorWorker`,
+    /root/reference/lib/bindings/kvbm/src/block_manager/vllm/connector/trtllm_worker.rs:31-60,555-645): ONE
+    FullyContiguous KV tensor `[num_blocks, num_layers, outer, page, inner...]` (distributed/worker.rs:528-549), method
+    names `bind_connector_meta` / `start_load_kv` / `execute_offload_operations` / `save_kv_layer(layer_idx)` /
+    `submit_offload_on_event`, loads enqueued by `start_load_kv` instead of at bind time (:371-380)."""
+
+    def __init__(self, drt=None, trtllm_rank: str = "0", host_blocks: int = 0):
+        super().__init__(drt, trtllm_rank, host_blocks)
+        self.onboarding_operations: List[WorkerTransferRequest] = []
+
+    def register_kv_caches(self, num_device_blocks: int, page_size: int, device_id: int, dtype_width_bytes: int,
+                           kv_cache_tensor, raw_event_handles: Sequence[int]) -> None:
+        if self.mgr is not None:
+            raise RuntimeError("kvbm worker already registered")                    # trtllm_worker.rs:231-234
+        shape = [int(x) for x in kv_cache_tensor.shape]
+        if len(shape) < 4 or shape[0] < num_device_blocks:
+            raise ValueError(f"Unsupported kv cache layout. Got shape: {shape}")   # distributed/worker.rs:517-526
+        nl, od = shape[1], shape[2]
+        per = 1
+        for x in shape[3:]:
+            per *= x
+        cfg = LayoutConfig(num_device_blocks, nl, od, page_size, per // page_size, dtype_width_bytes=dtype_width_bytes,
+                           allow_fp8=dtype_width_bytes == 1)
+        on_device = bool(getattr(kv_cache_tensor, "is_cuda", False))
+        self.mgr = TransferManager(device=device_id if on_device else -1, worker_id=hash(self.worker_id) & 0xffff)
+        self.kv_cache_layers = [(f"layer_{l}", kv_cache_tensor) for l in range(nl)]
+        self.layer_events = [int(h) for h in raw_event_handles]
+        self.pools[DEVICE] = self.mgr.register_fully_contiguous(
+            cfg, int(kv_cache_tensor.data_ptr()), int(kv_cache_tensor.numel() * kv_cache_tensor.element_size()),
+            StorageKind.Device if on_device else StorageKind.System, device_id)
+        self.device_config = cfg
+        if self._host_blocks:
+            import torch
+            hcfg = LayoutConfig(self._host_blocks, nl, od, page_size, cfg.inner_dim, dtype_width_bytes=dtype_width_bytes,
+                                allow_fp8=cfg.allow_fp8)
+            self._host_mem = torch.zeros(hcfg.required_bytes(), dtype=torch.uint8)
+            if on_device:
+                self._host_mem = self._host_mem.pin_memory()
+            self.pools[HOST] = self.mgr.register_fully_contiguous(hcfg, self._host_mem.data_ptr(), self._host_mem.numel(),
+                                                                  StorageKind.Pinned if on_device else StorageKind.System)
+        if on_device:
+            import torch
+            self._ready_flags = torch.zeros(nl, dtype=torch.int32, device=f"cuda:{device_id}")
+            self._helper_stream = torch.cuda.Stream(device=device_id, priority=-1)
+
+    def bind_connector_meta(self, metadata: bytes) -> None:
+        """trtllm_worker.rs:282-346: like the vLLM bind, but loads are only recorded here and enqueued by start_load_kv."""
+        md = ConnectorMetadata.from_bytes(metadata)
+        self.bound = True
+        self.iteration = md.iteration
+        self.layers_complete = 0
+        self.worker_iteration += 1
+        if self.worker_iteration != md.iteration:
+            raise AssertionError(f"iteration mismatch: worker {self.worker_iteration} vs metadata {md.iteration}")
+        for sl in md.new_slots:
+            if sl["request_id"] in self.slots:
+                raise AssertionError("slot already exists")
+            self.slots[sl["request_id"]] = _Slot(int(sl["expected_immediate_ops"]))
+        self.onboarding_operations = [op for op in md.operations if op.transfer_type == LOAD]
+        self.offloading_operations = [op for op in md.operations if op.transfer_type == STORE]
+        self._epoch += 1
+
+    bind_connector_metadata = bind_connector_meta
+
+    def start_load_kv(self) -> None:
+        for op in self.onboarding_operations:                                        # :371-380 (the list is cloned, not taken)
+            self._enqueue(op)
+            self.maybe_finished_onboarding.add(op.request_id)
+
+    def execute_offload_operations(self) -> None:
+        ops, self.offloading_operations = self.offloading_operations, []
+        for op in ops:
+            self._enqueue(op)
+        self._run_ready()
+
+    def save_kv_layer(self, layer_idx: int, kv_layer=None) -> None:                  # :357-369; the index is ignored there too
+        super().save_kv_layer(f"layer_{self.layers_complete}", kv_layer)
+
+    def submit_offload_on_event(self, event: int) -> None:
+        """:526-553: the offload is tied to ONE event instead of per-layer calls.  Here the helper stream waits that event
+        and releases every layer's ready flag, then the stores are enqueued -- still without blocking the host."""
+        if self._ready_flags is not None:
+            if event:
+                K.check(K.stream_wait_event(int(self._helper_stream.cuda_stream), int(event)), "stream_wait_event")
+            K.check(K.set_flags(self._ready_flags.data_ptr(), 0, len(self.kv_cache_layers), self._epoch,
+                                int(self._helper_stream.cuda_stream)), "set_flags")
+        for l in range(len(self.kv_cache_layers)):
+            self._completed_layers.add((l, self.worker_iteration))
+        self.layers_complete = len(self.kv_cache_layers)
+        self.execute_offload_operations()

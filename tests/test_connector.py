@@ -152,3 +152,68 @@ def test_iteration_mismatch_and_duplicate_slot_are_rejected():
         w2.bind_connector_metadata(md2.to_bytes())
     w.close()
     w2.close()
+
+
+def test_mla_shaped_caches_fall_back_to_outer_dim_one():
+    """distributed/worker.rs:554-578: when the candidate K/V axis is > 2 the tensor has no K/V split (MLA:
+    [n_blocks, page, latent]) -> outer_dim = 1, inner_dim from every dim after n_blocks."""
+    latent = 576
+    caches = [(f"l{l}", torch.zeros(NB, PAGE, latent, dtype=torch.bfloat16)) for l in range(NL)]
+    w = KvConnectorWorker(None, "mla")
+    w.register_kv_caches(NB, PAGE, 0, 2, caches, [0] * NL)
+    c = w.device_config
+    assert (c.outer_dim, c.inner_dim, c.num_layers, c.num_blocks) == (1, latent, NL, NB)
+    w.close()
+    # explicit dims (what Python passes via KvTensorLayout) win over inference
+    w = KvConnectorWorker(None, "explicit")
+    w.register_kv_caches(NB, PAGE, 0, 2, caches, [0] * NL, outer_dim=1, inner_dim=latent)
+    assert (w.device_config.outer_dim, w.device_config.inner_dim) == (1, latent)
+    w.close()
+
+
+def test_trtllm_worker_one_fully_contiguous_tensor_and_its_protocol():
+    """trtllm_worker.rs:222-380,526-553: one FullyContiguous tensor, loads enqueued by start_load_kv, stores by the last
+    save_kv_layer (or one submit_offload_on_event), bytes checked against the oracle."""
+    from dynamo_b200.connector import TrtllmKvConnectorWorker
+    kv = torch.zeros(NB, NL, 2, PAGE, HEADS * HD, dtype=torch.bfloat16)
+    w = TrtllmKvConnectorWorker(None, "rank0", host_blocks=8)
+    w.register_kv_caches(NB, PAGE, 0, 2, kv, [0] * NL)
+    assert (w.device_config.num_layers, w.device_config.outer_dim, w.device_config.inner_dim) == (NL, 2, HEADS * HD)
+    with pytest.raises(RuntimeError):
+        w.register_kv_caches(NB, PAGE, 0, 2, kv, [0] * NL)
+    dev = O.Layout(O.FC, NB, NL, 2, PAGE, HEADS * HD, 2, bases=[kv.data_ptr()])
+    dev.fill_blocks(range(NB), -1)
+    host = O.Layout(O.FC, 8, NL, 2, PAGE, HEADS * HD, 2, bases=[w._host_mem.data_ptr()])
+    u_store, u_load = str(uuid.uuid4()), str(uuid.uuid4())
+    md = ConnectorMetadata(1)
+    md.create_slot("r-store", 0)
+    md.create_slot("r-load", 0)
+    md.add_operations([WorkerTransferRequest("r-store", u_store, STORE, SCHEDULED), WorkerTransferRequest("r-load", u_load, LOAD, SCHEDULED)])
+    w.bind_connector_meta(md.to_bytes())
+    assert w.slots["r-load"].operations == [] and w.slots["r-store"].operations == []     # nothing enqueued at bind (:320-345)
+    w.handle_block_transfer(BlockTransferRequest(DEVICE, HOST, [(3, 0)], LeaderTransferRequest("r-store", u_store, SchedulerRequirement("IterationComplete", 1), SCHEDULED)))
+    w.start_load_kv()
+    assert w.slots["r-load"].operations == [u_load] and "r-load" in w.maybe_finished_onboarding
+    for l in range(NL):
+        w.save_kv_layer(l)
+    assert w.slots["r-store"].operations == [u_store]                                     # enqueued with the last layer (:357-369)
+    w.clear_connector_metadata()
+    assert host.block_checksum(0) == dev.block_checksum(3)
+    # the load: host block 0 -> device block 9
+    w.handle_block_transfer(BlockTransferRequest(HOST, DEVICE, [(0, 9)], LeaderTransferRequest("r-load", u_load, None, SCHEDULED)))
+    off, on = w.get_finished(["r-store"])
+    assert off == {"r-store"} and on == {"r-load"}
+    assert dev.block_checksum(9) == dev.block_checksum(3)
+    # second iteration driven by ONE event instead of per-layer calls
+    u2 = str(uuid.uuid4())
+    md = ConnectorMetadata(2)
+    md.create_slot("r2", 0)
+    md.add_operations([WorkerTransferRequest("r2", u2, STORE, SCHEDULED)])
+    w.bind_connector_meta(md.to_bytes())
+    w.handle_block_transfer(BlockTransferRequest(DEVICE, HOST, [(5, 1)], LeaderTransferRequest("r2", u2, SchedulerRequirement("LayerComplete", 2, NL - 1), SCHEDULED)))
+    w.submit_offload_on_event(0)
+    assert w.slots["r2"].operations == [u2]
+    assert w.get_finished(["r2"])[0] == {"r2"}
+    assert host.block_checksum(1) == dev.block_checksum(5)
+    w.clear_connector_metadata()
+    w.close()
