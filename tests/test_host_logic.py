@@ -405,3 +405,22 @@ def test_fanout_over_host_layouts_matches_oracle(mgr, as_numpy, replicate):
         O.execute_memcpy_transfer(src, ref, s, d)
         for got, want in zip(twin.buffers, ref.buffers):
             assert np.array_equal(got, want)
+
+
+def test_c_program_drives_the_host_abi(tmp_path):
+    """tests/c/host_abi_smoke.c: a C99 program (no Python, no torch) registers pools, transfers, exchanges the
+    SerializedLayout handshake and sees errors as codes -- the drop-in boundary used the way a cgo/JNI/Rust binding would."""
+    import shutil
+    gcc = shutil.which("gcc")
+    cuda_inc = "/usr/local/cuda/include"
+    if not gcc or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime_api.h")):
+        pytest.skip("gcc or the CUDA headers are not installed")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "dynamo_b200")
+    exe = tmp_path / "host_abi_smoke"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), "-I", cuda_inc,
+                        os.path.join(root, "tests", "c", "host_abi_smoke.c"), "-o", str(exe), "-L", libdir, "-lkvbm_physical",
+                        "-lkvbm_kernels", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "host ABI ok" in r.stdout, r.stdout + r.stderr
