@@ -31,6 +31,19 @@ from . import kernels as K
 from .physical import (BlockDimension, KvbmError, LayoutConfig, StorageKind, TransferCompleteNotification,
                        TransferManager, TransferOptions)
 
+def stable_worker_id(worker_id) -> int:
+    """Deterministic 48-bit id for a worker name (the reference's worker_id is a u64 the caller supplies,
+    lib/kvbm-physical/src/manager/handle.rs:16-50).  Integers (or decimal strings) are used as they are; anything else
+    is digested with BLAKE2b -- never Python's per-process randomised hash()."""
+    if isinstance(worker_id, int):
+        return worker_id & 0xFFFFFFFFFFFF
+    text = str(worker_id)
+    if text.isdigit():
+        return int(text) & 0xFFFFFFFFFFFF
+    import hashlib
+    return int.from_bytes(hashlib.blake2b(text.encode(), digest_size=6).digest(), "little")
+
+
 LOAD, STORE = "Load", "Store"
 SCHEDULED, IMMEDIATE = "Scheduled", "Immediate"
 DEVICE, HOST, DISK = "Device", "Host", "Disk"
@@ -149,11 +162,12 @@ class _Slot:
 
     def __init__(self, expected_immediate_ops: int):
         self.operations: List[str] = []
-        self.completed = 0
+        self.completed: Set[str] = set()        # uuids whose bytes have landed (a set: a retry can never double-count)
+        self.failed: Dict[str, str] = {}        # uuid -> error text of transfers that aborted
         self.expected_immediate_ops = expected_immediate_ops
 
     def is_complete(self) -> bool:
-        return self.completed == len(self.operations)
+        return all(u in self.completed or u in self.failed for u in self.operations)
 
 
 def layer_separate_auto(shape: Sequence[int], num_device_blocks: int) -> BlockDimension:
@@ -188,6 +202,9 @@ class KvConnectorWorker:
         self._completed_layers: Set[Tuple[int, int]] = set()
         self._pending: List[Tuple[BlockTransferRequest, Optional[TransferOptions]]] = []   # waiting for their requirement
         self._inflight: List[Tuple[TransferCompleteNotification, Optional[LeaderTransferRequest]]] = []
+        self._enqueued: Dict[Tuple[str, str], int] = {}      # (request_id, uuid) -> epoch at worker-side enqueue
+        self._early: Set[Tuple[str, str]] = set()             # offloads launched (gated) before the last layer was saved
+        self.failures: List[Tuple[Optional[str], Optional[str], str]] = []   # transfers that aborted: (request_id, uuid, error)
         self._ready_flags = None
         self._helper_stream = None
         self._epoch = 0
@@ -224,7 +241,7 @@ class KvConnectorWorker:
         cfg = LayoutConfig(num_device_blocks, len(kv_caches), od, page_size, inner, dtype_width_bytes=dtype_width_bytes,
                            allow_fp8=dtype_width_bytes == 1)
         on_device = bool(getattr(first, "is_cuda", False))
-        self.mgr = TransferManager(device=device_id if on_device else -1, worker_id=hash(self.worker_id) & 0xffff)
+        self.mgr = TransferManager(device=device_id if on_device else -1, worker_id=stable_worker_id(self.worker_id))
         bases = [int(t.data_ptr()) for _, t in kv_caches]
         sizes = [int(t.numel() * t.element_size()) for _, t in kv_caches]
         self.pools[DEVICE] = self.mgr.register_layer_separate(cfg, bases, sizes, block_dim,
@@ -348,6 +365,10 @@ class KvConnectorWorker:
         if op.request_id not in self.slots:
             raise AssertionError("slot does not exist")                              # scheduler.rs:220-228
         self.slots[op.request_id].operations.append(op.uuid)
+        # the worker half of the two-sided hand-shake (scheduler.rs:462-477, try_prepare_controller :539-570): a Scheduled
+        # transfer runs only once BOTH this enqueue and the leader's request have arrived.  The epoch at enqueue time is
+        # the one this iteration's per-layer ready flags carry.
+        self._enqueued.setdefault((op.request_id, op.uuid), self._epoch)
 
     def _requirement_met(self, req: Optional[SchedulerRequirement]) -> bool:
         if req is None:
@@ -363,27 +384,66 @@ class KvConnectorWorker:
         return False
 
     def _run_ready(self) -> None:
-        still = []
-        for req, options in self._pending:
+        pending, self._pending = self._pending, []
+        for i, (req, options) in enumerate(pending):
             cr = req.connector_req
-            if cr is not None and cr.request_type == SCHEDULED and not self._requirement_met(cr.requirement):
-                still.append((req, options))
-                continue
-            if req.from_pool not in self.pools or req.to_pool not in self.pools:
-                raise KvbmError(8, f"pool {req.from_pool}->{req.to_pool} is not registered on this worker")
-            src_ids = [a for a, _ in req.blocks]
-            dst_ids = [b for _, b in req.blocks]
-            note = self.mgr.execute_transfer(self.pools[req.from_pool], src_ids, self.pools[req.to_pool], dst_ids, options)
+            if cr is not None and cr.request_type == SCHEDULED:
+                # scheduler.rs:539-570: wait for the worker-side enqueue of the same uuid (for offloads that is the last
+                # save_kv_layer), and for the SchedulerRequirement when the leader attached one
+                enq = (cr.request_id, cr.uuid) in self._enqueued
+                if not enq and self._ready_flags is not None and req.from_pool == DEVICE and self.bound and \
+                        any(op.uuid == cr.uuid and op.request_id == cr.request_id for op in self.offloading_operations):
+                    # B200 path: an offload announced for the iteration that is running can be launched NOW -- the copy is
+                    # gated layer by layer on this iteration's ready flags, so it streams behind the forward pass instead
+                    # of starting after the last layer.  (It still counts for the slot only once save_kv_layer enqueues it.)
+                    self._enqueued[(cr.request_id, cr.uuid)] = self._epoch
+                    self._early.add((cr.request_id, cr.uuid))
+                    enq = True
+                elif not self._requirement_met(cr.requirement):
+                    enq = False
+                if not enq:
+                    self._pending.append((req, options))
+                    continue
+            try:
+                if req.from_pool not in self.pools or req.to_pool not in self.pools:
+                    raise KvbmError(8, f"pool {req.from_pool}->{req.to_pool} is not registered on this worker")
+                src_ids = [a for a, _ in req.blocks]
+                dst_ids = [b for _, b in req.blocks]
+                if options is None and req.from_pool == DEVICE and self._ready_flags is not None:
+                    # The reference blocks the host on the last layer's event before it enqueues an offload (worker.rs:341).
+                    # Here nothing blocks: the copy itself is gated on the per-layer ready flags that save_kv_layer's
+                    # helper stream releases behind the forward pass, so device blocks are never read before they are
+                    # written.  A request that is not tied to an iteration (no connector_req) reads the current epoch.
+                    epoch = self._enqueued.get((cr.request_id, cr.uuid), self._epoch) if cr is not None else self._epoch
+                    if epoch > 0:
+                        options = TransferOptions(layer_ready_flags=self.ready_flags_ptr(), epoch=epoch)
+                note = self.mgr.execute_transfer(self.pools[req.from_pool], src_ids, self.pools[req.to_pool], dst_ids, options)
+            except KvbmError as e:
+                self._fail(cr, str(e))                       # the request is dropped; everything behind it stays queued
+                self._pending.extend(pending[i + 1:])
+                raise
             self._inflight.append((note, cr))
-        self._pending = still
         self._poll()
 
+    def _fail(self, cr: Optional[LeaderTransferRequest], why: str) -> None:
+        if cr is not None and cr.request_id in self.slots:
+            self.slots[cr.request_id].failed[cr.uuid] = why
+        self.failures.append((cr.request_id if cr else None, cr.uuid if cr else None, why))
+
     def _poll(self) -> None:
+        """Exception-safe: a transfer that aborted (gate timeout -> rc -2) or whose notification is unknown is dropped from
+        the in-flight list, recorded on its slot as failed (so the request can still finish and be cleaned up) and in
+        `self.failures`; completions are per-uuid sets, so a retry can never count one twice."""
         rest = []
         for note, cr in self._inflight:
-            if note.is_complete():
+            try:
+                done = note.is_complete()
+            except KvbmError as e:
+                self._fail(cr, str(e))
+                continue
+            if done:
                 if cr is not None and cr.request_id in self.slots:
-                    self.slots[cr.request_id].completed += 1
+                    self.slots[cr.request_id].completed.add(cr.uuid)
             else:
                 rest.append((note, cr))
         self._inflight = rest
@@ -414,7 +474,7 @@ class TrtllmKvConnectorWorker(KvConnectorWorker):
         cfg = LayoutConfig(num_device_blocks, nl, od, page_size, per // page_size, dtype_width_bytes=dtype_width_bytes,
                            allow_fp8=dtype_width_bytes == 1)
         on_device = bool(getattr(kv_cache_tensor, "is_cuda", False))
-        self.mgr = TransferManager(device=device_id if on_device else -1, worker_id=hash(self.worker_id) & 0xffff)
+        self.mgr = TransferManager(device=device_id if on_device else -1, worker_id=stable_worker_id(self.worker_id))
         self.kv_cache_layers = [(f"layer_{l}", kv_cache_tensor) for l in range(nl)]
         self.layer_events = [int(h) for h in raw_event_handles]
         self.pools[DEVICE] = self.mgr.register_fully_contiguous(

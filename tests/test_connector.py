@@ -217,3 +217,77 @@ def test_trtllm_worker_one_fully_contiguous_tensor_and_its_protocol():
     assert host.block_checksum(1) == dev.block_checksum(5)
     w.clear_connector_metadata()
     w.close()
+
+
+def test_scheduled_request_waits_for_the_worker_side_enqueue():
+    """scheduler.rs:539-570 (try_prepare_controller): a Scheduled transfer needs BOTH halves -- the leader's request and the
+    worker's enqueue of the same uuid -- even when the leader attached no SchedulerRequirement.  Offload enqueues happen on
+    the last save_kv_layer (worker.rs:329-350), i.e. after the forward pass produced the blocks."""
+    w, caches = make_worker()
+    twin = fill_sequential(caches)
+    u = str(uuid.uuid4())
+    md = ConnectorMetadata(1)
+    md.create_slot("req-S", 0)
+    md.add_operations([WorkerTransferRequest("req-S", u, STORE, SCHEDULED)])
+    w.bind_connector_metadata(md.to_bytes())
+    w.handle_block_transfer(BlockTransferRequest(DEVICE, HOST, [(4, 2)], LeaderTransferRequest("req-S", u, None, SCHEDULED)))
+    host = O.Layout(O.FC, 8, NL, 2, PAGE, HEADS * HD, 2, bases=[w._host_mem.data_ptr()])
+    before = host.block_checksum(2)
+    assert len(w._pending) == 1 and not w._inflight                      # requirement=None must NOT fire immediately
+    for l in range(NL - 1):
+        w.save_kv_layer(caches[l][0])
+        assert len(w._pending) == 1 and host.block_checksum(2) == before
+    w.save_kv_layer(caches[NL - 1][0])                                     # last layer: the worker half arrives -> runs
+    assert not w._pending
+    w.clear_connector_metadata()
+    assert w.get_finished(["req-S"])[0] == {"req-S"}
+    assert host.block_checksum(2) == twin.block_checksum(4)
+    w.close()
+
+
+def test_poll_survives_a_failed_transfer_and_never_double_counts():
+    from dynamo_b200.physical import KvbmError
+    w, caches = make_worker()
+
+    class _Note:
+        def __init__(self, outcome):
+            self.outcome, self.polls = outcome, 0
+
+        def is_complete(self):
+            self.polls += 1
+            if self.outcome == "raise":
+                raise KvbmError(1, "transfer aborted (gate timeout)")
+            return self.outcome
+
+    md = ConnectorMetadata(1)
+    md.create_slot("r", 0)
+    w.bind_connector_metadata(md.to_bytes())
+    ua, ub, uc = (str(uuid.UUID(int=i)) for i in (1, 2, 3))
+    for u_ in (ua, ub, uc):
+        w._enqueue(WorkerTransferRequest("r", u_, STORE, SCHEDULED))
+    ok, bad, slow = _Note(True), _Note("raise"), _Note(False)
+    w._inflight = [(ok, LeaderTransferRequest("r", ua, None, SCHEDULED)), (bad, LeaderTransferRequest("r", ub, None, SCHEDULED)),
+                   (slow, LeaderTransferRequest("r", uc, None, SCHEDULED))]
+    for _ in range(3):                                                     # repeated polls: no exception escapes, no over-count
+        assert not w.is_complete("r")
+    assert w.slots["r"].completed == {ua} and list(w.slots["r"].failed) == [ub]
+    assert [n for n, _ in w._inflight] == [slow] and bad.polls == 1 and ok.polls == 1
+    assert len(w.failures) == 1 and w.failures[0][:2] == ("r", ub)
+    slow.outcome = True
+    assert w.is_complete("r")                                              # a failed op no longer blocks the request from finishing
+    w.clear_connector_metadata()
+    w.close()
+
+
+def test_worker_id_is_stable_across_processes():
+    """LayoutHandle carries worker_id (manager/handle.rs:16-50): it has to be the same number in every process."""
+    import subprocess
+    import sys
+    from dynamo_b200.connector import stable_worker_id
+    assert stable_worker_id("7") == 7 and stable_worker_id(9) == 9
+    a = stable_worker_id("decode-worker-3")
+    assert a == stable_worker_id("decode-worker-3") and a != stable_worker_id("decode-worker-4") and a < 2 ** 48
+    out = subprocess.run([sys.executable, "-c", "from dynamo_b200.connector import stable_worker_id as f; print(f('decode-worker-3'))"],
+                         capture_output=True, text=True, env={"PYTHONHASHSEED": "12345", "PATH": "/usr/bin:/bin",
+                                                              "PYTHONPATH": __import__("os").path.dirname(__import__("os").path.dirname(__file__))})
+    assert int(out.stdout.strip()) == a, out.stderr
