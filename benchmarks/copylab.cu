@@ -69,10 +69,7 @@ __device__ __forceinline__ void item_addr(const Job& j, uint32_t item, uint64_t&
   d = __ldg(j.dst.layer_base + layer) + static_cast<uint64_t>(__ldg(j.did + blk)) * j.dst.block_stride + o * j.dst.outer_stride + off;
 }
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
+using kvbm::ptx::mbar_arrive;
 
 // ------------------------------------------------------------------------------------------------------------
 // ws: R rings per CTA, each = 1 producer warp + 1 consumer warp, S slots of `tile` bytes.
@@ -676,6 +673,65 @@ int main(int argc, char** argv)
       CK(cudaStreamSynchronize(st));
       const unsigned long long bad = verify();
       report("ref_k1", "", time_it(launch, st, iters), bad);
+    }
+  }
+
+  // ---------------- K2 / K3 (block stacks <-> universal), ours vs the reference kernels ----------------
+  if (only == "perm" || only.empty()) {
+    typedef cudaError_t (*perm_fn)(void* const*, const void* const*, size_t, size_t, size_t, size_t, size_t, size_t, int, int, cudaStream_t);
+    typedef cudaError_t (*perm_fn2)(const void* const*, void* const*, size_t, size_t, size_t, size_t, size_t, size_t, int, int, cudaStream_t);
+    const size_t nb = 64, nh = 8, nl_ = 80, no_ = 2, nt = 16, hd = 128, el = 2;
+    const size_t chunk_bytes = nh * nt * hd * el, block_bytes = chunk_bytes * nl_ * no_;
+    uint8_t *uni, *chunks, *back;
+    CK(cudaMalloc(&uni, nb * block_bytes));
+    CK(cudaMalloc(&chunks, nb * block_bytes));
+    CK(cudaMalloc(&back, nb * block_bytes));
+    fill_kernel<<<1024, 256>>>(reinterpret_cast<uint4*>(chunks), nb * block_bytes / 16, 99u);
+    std::vector<void*> up(nb), cp(nb * nl_ * no_), bp(nb * nl_ * no_);
+    // chunk order shuffled so that chunks are NOT laid out like the universal tensor
+    std::vector<size_t> order(nb * nl_ * no_);
+    std::iota(order.begin(), order.end(), 0);
+    std::mt19937 rr(7);
+    std::shuffle(order.begin(), order.end(), rr);
+    for (size_t b = 0; b < nb; ++b) up[b] = uni + b * block_bytes;
+    for (size_t i = 0; i < cp.size(); ++i) {
+      cp[i] = chunks + order[i] * chunk_bytes;
+      bp[i] = back + order[i] * chunk_bytes;
+    }
+    void **d_up, **d_cp, **d_bp;
+    CK(cudaMalloc(&d_up, up.size() * 8));
+    CK(cudaMalloc(&d_cp, cp.size() * 8));
+    CK(cudaMalloc(&d_bp, bp.size() * 8));
+    CK(cudaMemcpy(d_up, up.data(), up.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_cp, cp.data(), cp.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_bp, bp.data(), bp.size() * 8, cudaMemcpyHostToDevice));
+    const double pbytes = static_cast<double>(nb * block_bytes);
+    for (const char* which : {"ours", "ref"}) {
+      const std::string path = std::string(which) == "ours" ? root + "/../dynamo_b200/libkvbm_kernels.so" : root + "/../oracle/_ref/libkvbm_kernels_ref.so";
+      void* h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+      if (!h) {
+        fprintf(stderr, "perm %s: %s\n", which, dlerror());
+        continue;
+      }
+      perm_fn k2 = reinterpret_cast<perm_fn>(dlsym(h, "kvbm_kernels_launch_universal_from_block"));
+      perm_fn2 k3 = reinterpret_cast<perm_fn2>(dlsym(h, "kvbm_kernels_launch_block_from_universal"));
+      for (int layout = 0; layout < 2; ++layout) {
+        CK(cudaMemset(uni, 0, nb * block_bytes));
+        CK(cudaMemset(back, 0, nb * block_bytes));
+        auto l2 = [&]() { CK(k2(d_up, reinterpret_cast<const void* const*>(d_cp), nb, nh, nl_, no_, nt, hd, 1, layout, st)); };
+        auto l3 = [&]() { CK(k3(reinterpret_cast<const void* const*>(d_up), d_bp, nb, nh, nl_, no_, nt, hd, 1, layout, st)); };
+        Timing t2 = time_it(l2, st, iters);
+        Timing t3 = time_it(l3, st, iters);
+        CK(cudaStreamSynchronize(st));
+        // round trip must reproduce the chunks
+        std::vector<uint8_t> a(1 << 20), c(1 << 20);
+        CK(cudaMemcpy(a.data(), chunks + (nb * block_bytes / 2), a.size(), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(c.data(), back + (nb * block_bytes / 2), c.size(), cudaMemcpyDeviceToHost));
+        const int same = memcmp(a.data(), c.data(), a.size()) == 0;
+        printf("{\"name\":\"perm_%s\",\"layout\":\"%s\",\"k2_ms\":%.5f,\"k3_ms\":%.5f,\"k2_gbs_rw\":%.1f,\"k3_gbs_rw\":%.1f,\"roundtrip_ok\":%d}\n", which,
+               layout == 0 ? "NHD" : "HND", t2.med_ms, t3.med_ms, 2 * pbytes / t2.med_ms / 1e6, 2 * pbytes / t3.med_ms / 1e6, same);
+        fflush(stdout);
+      }
     }
   }
   return 0;

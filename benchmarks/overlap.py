@@ -66,7 +66,7 @@ sid = torch.from_numpy(np.random.default_rng(0).permutation(nbp)[:n].astype(np.i
 did = torch.from_numpy(np.random.default_rng(1).permutation(nbp)[:n].astype(np.int32)).cuda()
 ready = torch.zeros(nl, dtype=torch.int32, device="cuda:0")
 done = torch.zeros(nl, dtype=torch.int32, device=ddev)
-ws = torch.zeros(nl + 2, dtype=torch.int32, device="cuda:0")
+ws = torch.zeros(nl + 4, dtype=torch.int32, device="cuda:0")
 main = torch.cuda.current_stream()
 side = torch.cuda.Stream(priority=-1)   # the persistent transfer CTAs should win SM slots as compute CTAs retire
 mp, sp = int(main.cuda_stream), int(side.cuda_stream)

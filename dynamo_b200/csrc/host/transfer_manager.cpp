@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <memory>
 #include <mutex>
+#include <random>
 #include <set>
 #include <string>
 #include <thread>
@@ -25,6 +26,20 @@
 namespace kvbm_host {
 
 static thread_local std::string g_last_error;
+
+// Identity of this address space for layout blobs: the pid alone collides across PID namespaces (two containers can
+// both be pid 1), so a per-process random nonce rides in the upper 32 bits of the header's pid field.
+static uint64_t process_identity()
+{
+  static const uint64_t id = [] {
+    std::random_device rd;
+    uint64_t nonce = (static_cast<uint64_t>(rd()) << 32 | rd()) ^
+                     static_cast<uint64_t>(std::chrono::steady_clock::now().time_since_epoch().count());
+    nonce ^= nonce >> 29;
+    return (static_cast<uint64_t>(getpid()) & 0xffffffffull) | ((nonce & 0xffffffffull) << 32);
+  }();
+  return id;
+}
 
 static int fail(int code, const std::string& msg)
 {
@@ -159,7 +174,7 @@ struct Slot {
   uint32_t* dev_ws = nullptr;     // sync workspace (zeroed, kernel leaves it zeroed)
   size_t ws_cap = 0;
   cudaEvent_t ev = nullptr;
-  uint64_t seq = 0;               // owner
+  std::atomic<uint64_t> seq{0};   // owner (read lock-free by kvbm_notification_is_complete)
   bool in_flight = false;
   bool owns_ids = false;          // false: pinned_ids / dev_ids point into the manager's arenas
   bool owns_ws = false;
@@ -251,13 +266,20 @@ static int upload_layer_base(kvbm_transfer_manager* m, Layout* L)
   return KVBM_OK;
 }
 
+// LayoutHandle = (worker_id, layout_id: u16) (manager/handle.rs:16-50).  Ids of unregistered layouts are reused; a live
+// layout is never overwritten: 0 = "the 16-bit id space of this worker is exhausted".
 static kvbm_layout_handle add_layout(kvbm_transfer_manager* m, Layout&& L)
 {
   std::lock_guard<std::mutex> lk(m->mu);
-  const uint16_t id = m->next_layout_id++;
-  const kvbm_layout_handle h = (m->worker_id << 16) | id;
-  m->layouts[h] = std::make_unique<Layout>(std::move(L));
-  return h;
+  for (uint32_t tries = 0; tries < 65535; ++tries) {
+    uint16_t id = m->next_layout_id++;
+    if (id == 0) id = m->next_layout_id++;
+    const kvbm_layout_handle h = (m->worker_id << 16) | id;
+    if (m->layouts.find(h) != m->layouts.end()) continue;
+    m->layouts[h] = std::make_unique<Layout>(std::move(L));
+    return h;
+  }
+  return 0;
 }
 
 static kvbm_paged_layout descriptor(const Layout& L)
@@ -431,7 +453,10 @@ static int acquire_slot(kvbm_transfer_manager* m, size_t ids_needed, size_t ws_n
   }
   int rc = ensure_slot(sl, ids_needed, ws_needed);
   if (rc) return rc;
-  sl.seq = s;
+  // the previous owner has completed: clear its completion word (an abort marker must not be mistaken for ours) BEFORE
+  // the new owner is published
+  __atomic_store_n(sl.host_flag, 0u, __ATOMIC_RELAXED);
+  sl.seq.store(s, std::memory_order_release);
   *out = &sl;
   *seq = s;
   return KVBM_OK;
@@ -466,10 +491,12 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
   std::lock_guard<std::mutex> lk(m->mu);
   Layout* S = m->find(src_h);
   if (!S) return fail(KVBM_ERR_HANDLE, "invalid source handle");
+  if (S->unmapped) return fail(KVBM_ERR_UNSUPPORTED, "source layout is a descriptor of another process's host memory: not addressable from this process");
   std::vector<Layout*> D(nd);
   for (int d = 0; d < nd; ++d) {
     D[d] = m->find(dst_h[d]);
     if (!D[d]) return fail(KVBM_ERR_HANDLE, "invalid destination handle");
+    if (D[d]->unmapped) return fail(KVBM_ERR_UNSUPPORTED, "destination layout is a descriptor of another process's host memory: not addressable from this process");
     int rc = check_compat(*S, *D[d], o.cast_mode);
     if (rc) return rc;
     if (n && (!src_ids || !dst_ids || !src_ids[d] || !dst_ids[d])) return fail(KVBM_ERR, "null block id list");
@@ -524,7 +551,7 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
   const size_t lists = replicate ? static_cast<size_t>(nd) + 1 : 2 * static_cast<size_t>(nd);
   Slot* sl;
   uint64_t seq;
-  int rc = acquire_slot(m, lists * n, S->cfg.num_layers + 2, &sl, &seq);
+  int rc = acquire_slot(m, lists * n, S->cfg.num_layers + 4, &sl, &seq);
   if (rc) return rc;
   auto narrow = [&](const size_t* ids, int32_t* dstp) { for (size_t i = 0; i < n; ++i) dstp[i] = static_cast<int32_t>(ids[i]); };
   std::vector<const int32_t*> dev_src(nd), dev_dst(nd);
@@ -661,7 +688,12 @@ static int finish_register(kvbm_transfer_manager* m, Layout&& L, int storage_kin
   L.device_id = device_id;
   int rc = upload_layer_base(m, &L);
   if (rc) return rc;
+  uint64_t* dev_table = L.dev_layer_base;
   *out = add_layout(m, std::move(L));
+  if (*out == 0) {
+    if (dev_table) cudaFree(dev_table);
+    return fail(KVBM_ERR, "layout id space exhausted: 65535 layouts are registered on this worker");
+  }
   return KVBM_OK;
 }
 
@@ -786,7 +818,7 @@ extern "C" int kvbm_manager_export_metadata(kvbm_transfer_manager* m, kvbm_layou
   hd.device_id = L->device_id;
   hd.n_allocs = static_cast<uint32_t>(L->allocs.size());
   hd.worker_id = m->worker_id;
-  hd.pid = static_cast<uint64_t>(getpid());
+  hd.pid = process_identity();
   const kvbm_layout_config& c = L->cfg;
   const uint64_t cfg[9] = {c.num_blocks, c.num_layers, c.outer_dim, c.page_size, c.inner_dim, c.alignment, c.dtype_width_bytes, c.num_heads,
                            static_cast<uint64_t>(c.allow_fp8)};
@@ -838,17 +870,24 @@ extern "C" int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void
   cfg.dtype_width_bytes = hd.cfg[6];
   cfg.num_heads = hd.cfg[7];
   cfg.allow_fp8 = static_cast<int>(hd.cfg[8]);
-  const bool same_process = hd.pid == static_cast<uint64_t>(getpid());
+  const bool same_process = hd.pid == process_identity();
   std::vector<uintptr_t> bases(hd.n_allocs);
   std::vector<size_t> sizes(hd.n_allocs);
+  bool unmapped = false;
   const auto* pa = static_cast<const unsigned char*>(buf) + sizeof(BlobHeader);
   DeviceGuard g(m->device);
   for (uint32_t i = 0; i < hd.n_allocs; ++i) {
     BlobAlloc ba;
     std::memcpy(&ba, pa + i * sizeof(BlobAlloc), sizeof(ba));
     sizes[i] = ba.size;
-    if (same_process || !ba.has_ipc) {
+    if (same_process) {
       bases[i] = ba.addr;  // same address space (peer access is enabled with kvbm_manager_enable_peer_access)
+    } else if (!ba.has_ipc) {
+      // Another process's System / Pinned pool (or device memory that could not be exported): its virtual addresses mean
+      // nothing here.  The layout is registered as a DESCRIPTOR (geometry, handle, memory_region arithmetic) that no
+      // transfer may touch -- the role NIXL's remote-descriptor-only entries play (manager/mod.rs:519-633).
+      bases[i] = ba.addr;
+      unmapped = true;
     } else {
       if (m->device < 0) return fail(KVBM_ERR_CUDA, "importing a device layout needs a CUDA manager");
       cudaIpcMemHandle_t ih;
@@ -875,6 +914,7 @@ extern "C" int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void
                                : make_layer_separate(cfg, bases.data(), sizes.data(), hd.n_allocs, static_cast<int>(hd.block_dim), &L, &why);
   if (rc) return fail(rc, why);
   L.remote = !same_process;
+  L.unmapped = unmapped;
   return finish_register(m, std::move(L), static_cast<int>(hd.storage), hd.device_id, out);
 }
 
@@ -905,9 +945,13 @@ extern "C" int kvbm_notification_is_complete(kvbm_transfer_manager* m, kvbm_noti
 {
   if (!m) return -1;
   if (n == 0) return 1;
+  // Lock-free against execute() recycling the slot: the owner word is atomic, the completion word lives at a fixed
+  // address for the manager's lifetime, and the owner is re-checked after the completion word was read.
   Slot& sl = m->slots[(n - 1) % kSlots];
-  if (sl.seq != n) return sl.seq > n ? 1 : -1;  // slot recycled by a later transfer => ours completed
-  const uint32_t v = *reinterpret_cast<volatile uint32_t*>(sl.host_flag);
+  const uint64_t s1 = sl.seq.load(std::memory_order_acquire);
+  if (s1 != n) return s1 > n ? 1 : -1;  // slot recycled by a later transfer => ours completed
+  const uint32_t v = __atomic_load_n(sl.host_flag, __ATOMIC_ACQUIRE);
+  if (sl.seq.load(std::memory_order_acquire) != n) return 1;
   if (v == 0xFFFFFFFFu) return -2;  // the gated kernel gave up waiting for a layer_ready flag
   return v == static_cast<uint32_t>(n) ? 1 : 0;
 }

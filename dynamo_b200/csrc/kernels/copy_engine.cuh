@@ -1,13 +1,18 @@
-// The warp-level TMA ring that every KV transfer kernel in this library is built from.
+// The warp-specialised TMA ring that every paged KV transfer kernel in this library is built from.
 //
-// One warp owns `S` shared-memory slots of `tile` bytes and walks its share of the work items:
+//     HBM (paged source) --cp.async.bulk--> smem slot --cp.async.bulk--> HBM / NVLink peer (1..N) / multicast
 //
-//     HBM (paged source) --cp.async.bulk--> smem slot --cp.async.bulk--> HBM / NVLink peer (1..N)
-//
-// Lane 0 drives both directions asynchronously (loads complete on per-slot mbarriers, stores are
-// tracked by bulk async-groups); the other lanes only work for pieces that cannot use TMA (pointer
-// or size not a multiple of 16 B -> vectorised SIMT ladder) and for the fused fp8<->bf16 cast.
-// A CTA is W such warps, each with a private ring, so a single SM keeps W*(S-1) tiles in flight.
+// A ring is TWO warps sharing S shared-memory slots of `tile` bytes:
+//   * the PRODUCER warp claims work from a grid-wide dynamic tile scheduler (atomic tickets, guided batch size),
+//     turns the claimed items into addresses with all 32 lanes at once (block-table lookups are SIMD), waits for the
+//     layer's ready flag when the transfer is gated, and issues the bulk loads (completion counted in bytes on the
+//     slot's `full` mbarrier).  It never waits for data.
+//   * the CONSUMER warp waits for `full`, issues the bulk stores (or converts fp8<->bf16 / stores SIMT / multimem),
+//     hands the slot back through the `empty` mbarrier once the store has read it, and publishes per-layer and
+//     whole-transfer completion.  It never computes an address.
+// A CTA holds R such rings.  Why dynamic scheduling: SMs of a B200 do not move bytes at the same rate (two dies, L2
+// slice distance) -- with a static split the slowest ring finished 80-100 us after the fastest on a 170 us copy
+// (benchmarks/copylab.cu, profiles/r02_copylab_n1.jsonl); with tickets all rings finish within ~5 us.
 #pragma once
 #include "ptx.cuh"
 
@@ -15,6 +20,7 @@ namespace kvbm {
 
 constexpr int kMaxDst = 8;
 constexpr int kMaxStages = 16;
+constexpr int kMaxBatch = 32;  // items claimed per ticket (one per producer lane)
 
 // One unit of work: `bytes` (of source) from `src` to each of dst[0..ndst).
 struct Piece {
@@ -28,45 +34,50 @@ struct Piece {
 // ------------------------------------------------------------------------------------------
 // SIMT ladder for pieces TMA cannot take.  Same alignment contract as the reference K1 kernel
 // (/root/reference/lib/kvbm-kernels/cuda/tensor_kernels.cu:511-540): the widest vector both
-// pointers allow, byte tail.  Whole warp cooperates, 4 independent 16 B loads in flight per lane.
+// pointers allow, byte tail.  `tid`/`nthr` = the cooperating group (a warp or a whole CTA);
+// 8 independent 16 B loads in flight per thread on the aligned path.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_copy_simt(uint8_t* dst, const uint8_t* src, uint32_t bytes,
-                                               int lane)
+__device__ __forceinline__ void group_copy_simt(uint8_t* dst, const uint8_t* src, size_t bytes, uint32_t tid, uint32_t nthr)
 {
   const uintptr_t both = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src);
-  uint32_t done = 0;
+  size_t done = 0;
   if ((both & 15) == 0) {
-    const uint32_t n = bytes >> 4;
+    const size_t n = bytes >> 4;
     const uint4* s = reinterpret_cast<const uint4*>(src);
     uint4* d = reinterpret_cast<uint4*>(dst);
-    uint32_t i = lane;
-    for (; i + 96 < n; i += 128) {
-      uint4 a = ptx::ld_stream_v4(s + i), b = ptx::ld_stream_v4(s + i + 32);
-      uint4 c = ptx::ld_stream_v4(s + i + 64), e = ptx::ld_stream_v4(s + i + 96);
-      ptx::st_stream_v4(d + i, a);
-      ptx::st_stream_v4(d + i + 32, b);
-      ptx::st_stream_v4(d + i + 64, c);
-      ptx::st_stream_v4(d + i + 96, e);
+    size_t i = tid;
+    constexpr int U = 8;
+    for (; i + static_cast<size_t>(U - 1) * nthr < n; i += static_cast<size_t>(U) * nthr) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = ptx::ld_stream_v4(s + i + static_cast<size_t>(u) * nthr);
+#pragma unroll
+      for (int u = 0; u < U; ++u) ptx::st_stream_v4(d + i + static_cast<size_t>(u) * nthr, v[u]);
     }
-    for (; i < n; i += 32) ptx::st_stream_v4(d + i, ptx::ld_stream_v4(s + i));
+    for (; i < n; i += nthr) ptx::st_stream_v4(d + i, ptx::ld_stream_v4(s + i));
     done = n << 4;
   } else if ((both & 7) == 0) {
-    const uint32_t n = bytes >> 3;
+    const size_t n = bytes >> 3;
     const uint2* s = reinterpret_cast<const uint2*>(src);
     uint2* d = reinterpret_cast<uint2*>(dst);
 #pragma unroll 4
-    for (uint32_t i = lane; i < n; i += 32) d[i] = s[i];
+    for (size_t i = tid; i < n; i += nthr) d[i] = s[i];
     done = n << 3;
   } else if ((both & 3) == 0) {
-    const uint32_t n = bytes >> 2;
+    const size_t n = bytes >> 2;
     const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
     uint32_t* d = reinterpret_cast<uint32_t*>(dst);
 #pragma unroll 4
-    for (uint32_t i = lane; i < n; i += 32) d[i] = s[i];
+    for (size_t i = tid; i < n; i += nthr) d[i] = s[i];
     done = n << 2;
   }
 #pragma unroll 4
-  for (uint32_t i = done + lane; i < bytes; i += 32) dst[i] = src[i];
+  for (size_t i = done + tid; i < bytes; i += nthr) dst[i] = src[i];
+}
+
+__device__ __forceinline__ void warp_copy_simt(uint8_t* dst, const uint8_t* src, uint32_t bytes, int lane)
+{
+  group_copy_simt(dst, src, bytes, static_cast<uint32_t>(lane), 32u);
 }
 
 __device__ __forceinline__ bool piece_tma_ok(const Piece& p)
@@ -78,18 +89,21 @@ __device__ __forceinline__ bool piece_tma_ok(const Piece& p)
   return (m & 15) == 0 && p.bytes != 0;
 }
 
-// Layer-streaming hooks shared by the rings.  All members may be null.
+// Layer-streaming / completion hooks shared by the rings.  All pointers may be null.
+// `ctl` is three zeroed words the launch owns: [0] rings finished, [1] abort, [2] scheduler tickets.  They are left
+// zeroed by the last ring to finish, so the same words serve the next launch.
 struct StreamSync {
   const uint32_t* layer_ready;  // wait until layer_ready[l] >= epoch before reading layer l
-  uint32_t* workspace;          // [num_layers + 1] zeroed counters (last = whole transfer)
+  uint32_t* layer_counters;     // [num_layers] zeroed: items of layer l that have landed
+  uint32_t* ctl;                // see above; null = static tile schedule, no completion signals
   uint32_t* done_flag[kMaxDst];
   uint32_t* layer_done[kMaxDst];
   uint32_t* completion_flag;    // extra whole-transfer flag (host-mapped memory allowed)
   uint32_t completion_value;
   uint32_t epoch;
-  uint32_t total_warps;
+  uint32_t total_rings;
+  uint32_t items_per_layer;
   int ndst;
-  int num_layers;  // counters per layer live at workspace[l]; whole-transfer counter at [num_layers]
   int layer_begin, layer_end;
   uint64_t gate_timeout_ns;  // a gated wait longer than this aborts the transfer instead of spinning forever
   bool gate;         // layer_ready present: reads of a layer wait for its flag
@@ -99,21 +113,43 @@ struct StreamSync {
 
 // Ring geometry / behaviour of one launch (uniform across the grid).
 struct RingParams {
-  int S;              // input slots per warp
-  int P;              // byte-exact ring: stores allowed to keep draining (loads ahead A = S - P)
+  int S;              // slots per ring
+  int P;              // TMA stores allowed to keep draining their slot (loads ahead = S - P)
+  int batch;          // largest ticket (items), <= kMaxBatch
   uint32_t tile_in;   // source bytes per slot
-  uint32_t tile_out;  // cast rings: bytes per output slot (2 of them)
+  uint32_t tile_out;  // cast rings: bytes per output buffer (2 of them)
   bool allow_tma;
+  bool static_schedule;  // diagnostics: round-robin batches even when control words exist
   int cache_hint;     // bit0 evict_first loads, bit1 evict_first stores
   int variant;        // 0 = TMA load + TMA store; 1 = TMA load + SIMT store from smem; 4 = TMA load + multimem.st (NVLS);
                       // 2 = loads only (diagnostic), 3 = stores only (diagnostic)
 };
 
+// Per-slot control block the producer fills before it arms the slot's `full` barrier.
+struct SlotCtl {
+  uint64_t src;
+  uint64_t dst[kMaxDst];
+  uint32_t bytes;  // bit31: the payload arrives in the slot by TMA; otherwise the consumer moves it SIMT from `src`
+  uint32_t layer;  // bit31: end of this ring's stream
+};
+constexpr uint32_t kSlotTma = 0x80000000u;
+constexpr uint32_t kSlotEnd = 0x80000000u;
+
+// shared memory of one ring: [full[S] | empty[S]] mbarriers (16 * kMaxStages bytes), SlotCtl[kMaxStages]
+__host__ __device__ constexpr uint32_t ring_ctl_bytes() { return 16u * kMaxStages + static_cast<uint32_t>(sizeof(SlotCtl)) * kMaxStages; }
+
+struct RingSmem {
+  uint32_t full0, empty0;  // shared-space addresses of the barrier arrays
+  SlotCtl* ctl;
+  uint32_t in0;   // S * tile_in
+  uint32_t out0;  // 2 * tile_out (cast only)
+};
+
 // Flag polls are relaxed loads; one acquire fence follows a successful probe (an ld.acquire.sys per poll would
 // invalidate L1 every time and, measured, slowed the co-resident compute kernel).
-// Returns false when the flag was not released within gate_timeout_ns: a spinning kernel that waits for work
-// which can never be submitted (e.g. because a lazy module load is itself waiting for this kernel) must not hang
-// the GPU; the warp then records the abort in the workspace and stops.
+// Returns false when the flag was not released within gate_timeout_ns or another ring already gave up: a spinning
+// kernel that waits for work which can never be submitted (e.g. because a lazy module load is itself waiting for this
+// kernel) must not hang the GPU; the ring then records the abort and stops claiming work.
 __device__ __forceinline__ bool wait_layer_ready(const StreamSync& ss, int layer, int lane)
 {
   uint32_t ok = 1;
@@ -122,10 +158,16 @@ __device__ __forceinline__ bool wait_layer_ready(const StreamSync& ss, int layer
     uint32_t polls = 0;
     while (ptx::ld_relaxed_sys(ss.layer_ready + layer) < ss.epoch) {
       __nanosleep(128);
-      if ((++polls & 1023u) == 0 && ptx::globaltimer_ns() - t0 > ss.gate_timeout_ns) {
-        ok = 0;
-        if (ss.workspace != nullptr) atomicExch(ss.workspace + ss.num_layers + 1, 1u);
-        break;
+      if ((++polls & 255u) == 0) {
+        if (ptx::ld_relaxed_sys(ss.ctl + 1) != 0) {
+          ok = 0;
+          break;
+        }
+        if (ptx::globaltimer_ns() - t0 > ss.gate_timeout_ns) {
+          ok = 0;
+          atomicExch(ss.ctl + 1, 1u);
+          break;
+        }
       }
     }
     ptx::fence_acq_rel_sys();
@@ -134,68 +176,43 @@ __device__ __forceinline__ bool wait_layer_ready(const StreamSync& ss, int layer
   return ok != 0;
 }
 
-// non-blocking probe, warp-uniform result
-__device__ __forceinline__ bool layer_is_ready(const StreamSync& ss, int layer, int lane)
+// `count` more items of `layer` have landed (stores complete, ordered before this call by the caller).
+__device__ __forceinline__ void arrive_layer(const StreamSync& ss, int layer, uint32_t count)
 {
-  uint32_t v = 0;
-  if (lane == 0) {
-    v = ptx::ld_relaxed_sys(ss.layer_ready + layer);
-    if (v >= ss.epoch) ptx::fence_acq_rel_sys();
-  }
-  v = __shfl_sync(0xffffffffu, v, 0);
-  return v >= ss.epoch;
-}
-
-// This warp has *completed* (stores landed) everything it owns in layers [from, to).
-__device__ __forceinline__ void arrive_layers(const StreamSync& ss, int from, int to, int lane)
-{
-  if (lane != 0 || !ss.want_layers) return;
-  for (int l = from; l < to; ++l) {
-    uint32_t old = ptx::atom_add_acq_rel_gpu(ss.workspace + l, 1u);
-    if (old == ss.total_warps - 1) {
-      ss.workspace[l] = 0;  // leave the workspace zeroed for the next launch
-      ptx::fence_acq_rel_sys();  // once per layer for the whole grid: everything acquired above is released below
+  const uint32_t old = ptx::atom_add_acq_rel_gpu(ss.layer_counters + layer, count);
+  if (old + count == ss.items_per_layer) {
+    ss.layer_counters[layer] = 0;  // leave the workspace zeroed for the next launch
+    ptx::fence_acq_rel_sys();      // once per layer for the whole grid: everything acquired above is released below
 #pragma unroll
-      for (int d = 0; d < kMaxDst; ++d)
-        if (d < ss.ndst && ss.layer_done[d] != nullptr) ptx::st_release_sys(ss.layer_done[d] + l, ss.epoch);
-    }
+    for (int d = 0; d < kMaxDst; ++d)
+      if (d < ss.ndst && ss.layer_done[d] != nullptr) ptx::st_release_sys(ss.layer_done[d] + layer, ss.epoch);
   }
 }
 
-__device__ __forceinline__ void arrive_transfer(const StreamSync& ss, int lane)
+// This ring is finished (its stores have landed).  The last ring to get here re-zeroes the control words and
+// publishes the whole-transfer signals.
+__device__ __forceinline__ void arrive_transfer(const StreamSync& ss)
 {
-  if (lane != 0 || !ss.want_done) return;
-  uint32_t old = ptx::atom_add_acq_rel_gpu(ss.workspace + ss.num_layers, 1u);
-  if (old == ss.total_warps - 1) {
-    ss.workspace[ss.num_layers] = 0;
-    const bool aborted = ss.gate && atomicExch(ss.workspace + ss.num_layers + 1, 0u) != 0;
-    if (aborted)  // warps that gave up skipped their layer arrivals: leave every counter zeroed for the next launch
-      for (int l = ss.layer_begin; l < ss.layer_end; ++l) ss.workspace[l] = 0;
-    ptx::fence_acq_rel_sys();
-    if (!aborted) {
+  if (ss.ctl == nullptr) return;
+  const uint32_t old = ptx::atom_add_acq_rel_gpu(ss.ctl, 1u);
+  if (old != ss.total_rings - 1) return;
+  ss.ctl[0] = 0;
+  ss.ctl[2] = 0;
+  const bool aborted = atomicExch(ss.ctl + 1, 0u) != 0;
+  if (aborted && ss.layer_counters != nullptr)  // partial layer counts must not leak into the next launch
+    for (int l = ss.layer_begin; l < ss.layer_end; ++l) ss.layer_counters[l] = 0;
+  if (!ss.want_done) return;
+  ptx::fence_acq_rel_sys();
+  if (!aborted) {
 #pragma unroll
-      for (int d = 0; d < kMaxDst; ++d)
-        if (d < ss.ndst && ss.done_flag[d] != nullptr) ptx::st_release_sys(ss.done_flag[d], ss.epoch);
-    }
-    // 0xFFFFFFFF = "this transfer gave up waiting for a layer": destinations are NOT told it completed
-    if (ss.completion_flag != nullptr) ptx::st_release_sys(ss.completion_flag, aborted ? 0xFFFFFFFFu : ss.completion_value);
+    for (int d = 0; d < kMaxDst; ++d)
+      if (d < ss.ndst && ss.done_flag[d] != nullptr) ptx::st_release_sys(ss.done_flag[d], ss.epoch);
   }
+  // 0xFFFFFFFF = "this transfer gave up waiting for a layer": destinations are NOT told it completed
+  if (ss.completion_flag != nullptr) ptx::st_release_sys(ss.completion_flag, aborted ? 0xFFFFFFFFu : ss.completion_value);
 }
 
-// Every store this warp issued so far has landed and is ordered before the arrive that follows:
-// lane 0 waits for its bulk groups and crosses the async->generic proxy; __syncwarp orders the other lanes'
-// SIMT stores before lane 0's release atomic (which is cumulative).  No per-lane MEMBAR.SYS: on an SM shared
-// with a compute kernel those stalled both kernels.
-__device__ __forceinline__ void drain_stores(int lane)
-{
-  if (lane == 0) {
-    ptx::bulk_wait<0>();
-    ptx::fence_proxy_async_global();
-  }
-  __syncwarp();
-}
-
-// smem -> global by the whole warp (variant 1): 16 B per lane, 4 independent stores in flight
+// smem -> global by the whole warp (variant 1): 16 B per lane
 __device__ __forceinline__ void warp_store_from_smem(uint8_t* dst, uint32_t src_smem, uint32_t bytes, int lane)
 {
   uint4* d = reinterpret_cast<uint4*>(dst);
@@ -239,223 +256,259 @@ template <bool UP>
 __device__ __forceinline__ void warp_cast_simt(uint8_t* dst, const uint8_t* src, uint32_t src_bytes, int lane);
 
 // ------------------------------------------------------------------------------------------
-// Per-warp descriptor ring.  Address generation (a handful of integer divisions and two dependent
-// table loads per item) is far too slow for the single instruction stream that drives the TMA
-// pipeline -- with one warp per scheduler every dependent instruction costs its full latency, which
-// measured ~2 us per item.  So the 32 lanes generate the descriptors of 32 consecutive items at
-// once (SIMD), park them in shared memory, and the pipeline reads them back with 3-4 LDS per item.
-// Layout (SoA, kDescRing entries each):  src[u64] | meta[u32 bytes|ok<<31, i32 layer] | dst[d][u64]...
-// ------------------------------------------------------------------------------------------
-constexpr int kDescRing = 64;
-__host__ __device__ constexpr uint32_t desc_bytes_per_warp(int ndst) { return kDescRing * (16u + 8u * static_cast<uint32_t>(ndst)); }
-
-struct DescRing {
-  uint64_t* src;
-  uint2* meta;
-  uint64_t* dst;  // [ndst][kDescRing]
-  __device__ __forceinline__ DescRing(uint8_t* mem)
-      : src(reinterpret_cast<uint64_t*>(mem)),
-        meta(reinterpret_cast<uint2*>(mem + kDescRing * 8)),
-        dst(reinterpret_cast<uint64_t*>(mem + kDescRing * 16))
-  {
-  }
-  __device__ __forceinline__ void put(uint32_t j, const Piece& p, bool ok) const
-  {
-    const uint32_t i = j & (kDescRing - 1);
-    src[i] = reinterpret_cast<uint64_t>(p.src);
-    meta[i] = make_uint2(p.bytes | (ok ? 0x80000000u : 0u), static_cast<uint32_t>(p.layer));
-#pragma unroll
-    for (int d = 0; d < kMaxDst; ++d)
-      if (d < p.ndst) dst[d * kDescRing + i] = reinterpret_cast<uint64_t>(p.dst[d]);
-  }
-  // returns eligibility; fills src/bytes/layer (+dst when want_dst)
-  __device__ __forceinline__ bool get(uint32_t j, int ndst, Piece& p, bool want_dst) const
-  {
-    const uint32_t i = j & (kDescRing - 1);
-    const uint2 m = meta[i];
-    p.src = reinterpret_cast<const uint8_t*>(src[i]);
-    p.bytes = m.x & 0x7fffffffu;
-    p.layer = static_cast<int>(m.y);
-    p.ndst = ndst;
-    if (want_dst) {
-#pragma unroll
-      for (int d = 0; d < kMaxDst; ++d)
-        if (d < ndst) p.dst[d] = reinterpret_cast<uint8_t*>(dst[d * kDescRing + i]);
-    }
-    return (m.x & 0x80000000u) != 0;
-  }
-};
-
-// ------------------------------------------------------------------------------------------
-// The ring.  CAST: 0 byte-exact, 1 fp8->bf16, 2 bf16->fp8.  Gen::get(item, Piece&) is warp-uniform.
-//   first/stride/total : this warp's arithmetic progression of item indices
-//   in_slots           : S * tile_in bytes private to this warp;  out_slots: 2 * tile_out (cast only)
-//   bars               : S mbarriers private to this warp (initialised, count 1)
-// Loads are issued ahead without ever blocking on a layer's ready flag: when the item to be stored next
-// is itself gated, the warp first drains and publishes the layers it has finished (so a consumer that
-// releases layer l+1 only after seeing layer l done cannot deadlock), then blocks.
+// Producer warp.  Gen::get(item, Piece&) is called by up to `batch` lanes at once (one item each).
+// Work is claimed in ITEMS: the first ticket of every ring is static (ring r takes items [r*B, (r+1)*B) -- no atomic
+// on the ramp), later tickets come from ss.ctl[2] and shrink towards the end of the transfer (guided self-scheduling)
+// so that all rings run dry together.  Without control words the schedule is a static round-robin of batches.
 // ------------------------------------------------------------------------------------------
 template <int CAST, class Gen>
-__device__ __forceinline__ void warp_ring(const Gen& gen, uint32_t first, uint32_t stride, uint32_t total,
-                                          uint8_t* in_slots, uint8_t* out_slots, uint64_t* bars,
-                                          uint8_t* desc_mem, int ndst, const RingParams& rp,
-                                          const StreamSync& ss)
+__device__ __forceinline__ void ring_producer(const Gen& gen, uint32_t total, uint32_t my_ring, uint32_t nrings,
+                                              const RingSmem& sm, int ndst, const RingParams& rp, const StreamSync& ss)
 {
   const int lane = threadIdx.x & 31;
   const int S = rp.S;
-  const DescRing ring(desc_mem);
-  uint32_t filled = 0;  // descriptors exist for this warp's items [max(0, filled - kDescRing), filled)
-  const bool sync_slot = CAST != 0 || rp.variant == 1 || rp.variant == 2 || rp.variant == 4;  // input slot is released synchronously
-  const uint32_t ahead = sync_slot ? static_cast<uint32_t>(S) : static_cast<uint32_t>(S - rp.P);
-  const uint32_t n_my = total > first ? (total - first + stride - 1) / stride : 0;
-  const uint32_t in0 = ptx::smem_addr(in_slots);
-  const uint32_t out0 = ptx::smem_addr(out_slots);
-  const uint32_t bar0 = ptx::smem_addr(bars);
+  const uint32_t B = static_cast<uint32_t>(rp.batch);
   const uint64_t policy = rp.cache_hint ? ptx::policy_evict_first() : 0;
-  uint32_t phase = 0;       // bit s = parity the next wait on slot s expects
-  uint32_t next_load = 0;   // items [0, next_load) have had their load issued (or need none)
+  const bool dynamic = ss.ctl != nullptr && !rp.static_schedule;
   int ready_layer = ss.gate ? ss.layer_begin - 1 : 0x7fffffff;
-  int open_layer = ss.layer_begin;  // lowest layer this warp has not yet arrived for
+  uint32_t q = 0;          // items this ring has issued
+  uint32_t k = 0;          // tickets taken
+  uint32_t last_start = 0;
   bool aborted = false;
 
-  auto eligible = [&](const Piece& p) {
-    bool ok = rp.allow_tma && piece_tma_ok(p);
-    if (CAST != 0) ok = ok && (p.bytes & 31) == 0;  // both sides whole 16 B vectors
-    return ok;
-  };
-  // Descriptor generation is software-pipelined: the table loads of the NEXT batch of 32 items are issued
-  // kPrefetchLead items early (results stay in registers, nothing waits on them) and only written to the ring
-  // when the batch is actually needed, so their DRAM/L2 latency never drains the TMA pipeline.
-  constexpr uint32_t kPrefetchLead = 16;
-  Piece pre;
-  bool pre_valid = false;
-  auto prefetch = [&]() {  // all 32 lanes
-    const uint32_t j = filled + lane;
-    pre.bytes = 0;
-    pre.ndst = 0;
-    pre.layer = 0;
-    pre.src = nullptr;
-    if (j < n_my) gen.get(first + j * stride, pre);
-    pre_valid = true;
-  };
-  auto fill = [&]() {  // all 32 lanes: publish the prefetched descriptors of the next 32 items
-    if (!pre_valid) prefetch();
-    __syncwarp();  // lanes that ran ahead must not overwrite entries a slower lane still reads
-    const uint32_t j = filled + lane;
-    if (j < n_my) ring.put(j, pre, eligible(pre));
-    filled += 32;
-    pre_valid = false;
+  while (!aborted) {
+    uint32_t item0, cnt;
+    if (k == 0) {
+      item0 = my_ring * B;
+      cnt = B;
+    } else if (dynamic) {
+      const uint32_t remaining = total > last_start ? total - last_start : 0;
+      uint32_t want = remaining / (4u * nrings);
+      want = want < 1u ? 1u : (want > B ? B : want);
+      uint32_t t = 0;
+      if (lane == 0) t = atomicAdd(ss.ctl + 2, want);
+      item0 = nrings * B + __shfl_sync(0xffffffffu, t, 0);
+      cnt = want;
+    } else {
+      item0 = (my_ring + k * nrings) * B;
+      cnt = B;
+    }
+    ++k;
+    last_start = item0;
+    if (item0 >= total) break;
+    cnt = min(cnt, total - item0);
+
+    Piece p;
+    p.src = nullptr;
+    p.bytes = 0;
+    p.ndst = ndst;
+    p.layer = 0;
+    bool ok = false;
+    if (static_cast<uint32_t>(lane) < cnt) {
+      gen.get(item0 + lane, p);
+      ok = rp.allow_tma && piece_tma_ok(p);
+      if (CAST != 0) ok = ok && (p.bytes & 31) == 0;  // both sides whole 16 B vectors
+    }
+    for (uint32_t i = 0; i < cnt; ++i, ++q) {
+      const uint64_t src_i = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(p.src), i);
+      const uint32_t bytes_i = __shfl_sync(0xffffffffu, p.bytes, i);
+      const int layer_i = __shfl_sync(0xffffffffu, p.layer, i);
+      const bool ok_i = __shfl_sync(0xffffffffu, static_cast<int>(ok), i) != 0;
+      uint64_t dst_i[kMaxDst];
+#pragma unroll
+      for (int d = 0; d < kMaxDst; ++d)
+        if (d < ndst) dst_i[d] = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(p.dst[d]), i);
+      if (layer_i > ready_layer) {
+        if (!wait_layer_ready(ss, layer_i, lane)) {  // gate timeout: abandon the rest (the abort is recorded)
+          aborted = true;
+          break;
+        }
+        ready_layer = layer_i;
+      }
+      if (lane == 0) {
+        const int slot = q % S;
+        ptx::mbar_wait(sm.empty0 + 8 * slot, ((q / S) & 1) ^ 1);
+        SlotCtl& c = sm.ctl[slot];
+        c.src = src_i;
+#pragma unroll
+        for (int d = 0; d < kMaxDst; ++d)
+          if (d < ndst) c.dst[d] = dst_i[d];
+        c.layer = static_cast<uint32_t>(layer_i);
+        const bool load = ok_i && rp.variant != 3;
+        c.bytes = bytes_i | (ok_i ? kSlotTma : 0u);
+        if (load) {
+          ptx::mbar_arrive_expect_tx(sm.full0 + 8 * slot, bytes_i);
+          if (rp.cache_hint & 1)
+            ptx::bulk_g2s_hint(sm.in0 + slot * rp.tile_in, reinterpret_cast<const void*>(src_i), bytes_i, sm.full0 + 8 * slot, policy);
+          else
+            ptx::bulk_g2s(sm.in0 + slot * rp.tile_in, reinterpret_cast<const void*>(src_i), bytes_i, sm.full0 + 8 * slot);
+        } else {
+          ptx::mbar_arrive(sm.full0 + 8 * slot);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // end of this ring's stream
+  if (lane == 0) {
+    const int slot = q % S;
+    ptx::mbar_wait(sm.empty0 + 8 * slot, ((q / S) & 1) ^ 1);
+    sm.ctl[slot].layer = kSlotEnd;
+    sm.ctl[slot].bytes = 0;
+    ptx::mbar_arrive(sm.full0 + 8 * slot);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Consumer warp.  CAST: 0 byte-exact, 1 fp8->bf16, 2 bf16->fp8.
+// Layer completion is published eagerly: whenever the consumer would stall on an empty ring, or moves to another
+// layer, it drains its stores and adds what it finished to the layer's counter -- so a receiver that releases
+// layer l+1 only after seeing layer l done can never dead-lock against a producer blocked on l+1's gate.
+// ------------------------------------------------------------------------------------------
+template <int CAST>
+__device__ __forceinline__ void ring_consumer(const RingSmem& sm, int ndst, const RingParams& rp, const StreamSync& ss)
+{
+  const int lane = threadIdx.x & 31;
+  const int S = rp.S;
+  const int P = rp.P;
+  const uint64_t policy = rp.cache_hint ? ptx::policy_evict_first() : 0;
+  const bool deferred_release = CAST == 0 && rp.variant == 0;  // TMA stores read the input slot asynchronously
+  uint32_t deferred = 0;  // bit (q & 31): item q's slot is handed back once its bulk store has read it
+  int cur_layer = -1;
+  uint32_t unpublished = 0;
+
+  // every store issued so far has landed and is ordered before the atomics that follow
+  auto drain = [&]() {
+    if (lane == 0) {
+      ptx::bulk_wait<0>();
+      ptx::fence_proxy_async_global();
+    }
     __syncwarp();
   };
-  auto pump = [&](uint32_t limit) {
-    while (next_load < n_my && next_load < limit) {
-      Piece p;
-      const bool ok = ring.get(next_load, ndst, p, false);
-      if (p.layer > ready_layer) {
-        if (!layer_is_ready(ss, p.layer, lane)) break;
-        ready_layer = p.layer;
-      }
-      if (rp.variant != 3 && ok && lane == 0) {
-        const int s = next_load % S;
-        ptx::mbar_arrive_expect_tx(bar0 + 8 * s, p.bytes);
-        if (rp.cache_hint & 1)
-          ptx::bulk_g2s_hint(in0 + s * rp.tile_in, p.src, p.bytes, bar0 + 8 * s, policy);
-        else
-          ptx::bulk_g2s(in0 + s * rp.tile_in, p.src, p.bytes, bar0 + 8 * s);
-      }
-      ++next_load;
+  auto release_upto = [&](uint32_t q_end) {  // lane 0: hand back every deferred slot of items < q_end (all within 32 items)
+    while (deferred != 0) {
+      const int b = __ffs(static_cast<int>(deferred)) - 1;
+      // bit b belongs to the youngest item j < q_end with (j & 31) == b
+      const uint32_t j = ((q_end - 1 - static_cast<uint32_t>(b)) & ~31u) + static_cast<uint32_t>(b);
+      ptx::mbar_arrive(sm.empty0 + 8 * (j % S));
+      deferred &= deferred - 1;
     }
   };
-  auto publish_upto = [&](int layer) {
-    drain_stores(lane);
-    arrive_layers(ss, open_layer, layer, lane);
-    open_layer = layer;
+  auto publish = [&](uint32_t q_now) {
+    drain();
+    if (lane == 0) {
+      if (deferred_release) release_upto(q_now);
+      arrive_layer(ss, cur_layer, unpublished);
+    }
+    unpublished = 0;
   };
 
-  for (uint32_t q = 0; q < n_my; ++q) {
-    while (filled < n_my && filled <= q + ahead) fill();
-    if (!pre_valid && filled < n_my && filled <= q + ahead + kPrefetchLead) prefetch();
-    pump(q + ahead);
-    Piece p;
-    const bool ok = ring.get(q, ndst, p, true);
-    if (next_load <= q) {  // this item's layer has not been released yet: publish what is finished, then block
-      if (ss.want_layers) publish_upto(p.layer);
-      if (!wait_layer_ready(ss, p.layer, lane)) {  // gate timeout: abandon the rest (the abort is recorded)
-        aborted = true;
-        break;
-      }
-      ready_layer = p.layer;
-      pump(q + ahead);
-    } else if (ss.want_layers && p.layer > open_layer) {
-      publish_upto(p.layer);
+  uint32_t q = 0;
+  for (;; ++q) {
+    const int slot = q % S;
+    const uint32_t parity = (q / S) & 1;
+    if (ss.want_layers && unpublished != 0) {
+      uint32_t ready = 0;
+      if (lane == 0) ready = ptx::mbar_try_wait(sm.full0 + 8 * slot, parity) ? 1u : 0u;
+      ready = __shfl_sync(0xffffffffu, ready, 0);
+      if (!ready) publish(q);
     }
-    const int s = q % S;
-    const uint32_t slot = in0 + s * rp.tile_in;
-    if (ok) {
-      if (CAST == 0 && rp.variant == 0) {
+    ptx::mbar_wait(sm.full0 + 8 * slot, parity);  // every lane observes the slot (control block + landed bytes)
+    const SlotCtl& c = sm.ctl[slot];
+    const uint32_t meta_layer = c.layer;
+    if (meta_layer & kSlotEnd) break;
+    const uint32_t meta_bytes = c.bytes;
+    const uint32_t bytes = meta_bytes & ~kSlotTma;
+    const bool tma = (meta_bytes & kSlotTma) != 0;
+    const int layer = static_cast<int>(meta_layer);
+    const uint32_t in = sm.in0 + slot * rp.tile_in;
+    if (ss.want_layers && unpublished != 0 && layer != cur_layer) publish(q);
+    cur_layer = layer;
+
+    if (!tma) {
+      // SIMT from global to global; the slot carries only the addresses
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(c.src);
+      for (int d = 0; d < ndst; ++d) {
+        uint8_t* dst = reinterpret_cast<uint8_t*>(c.dst[d]);
+        if (CAST == 0 && rp.variant == 4)
+          warp_copy_simt_mc(dst, src, bytes, lane);
+        else if (CAST == 0)
+          warp_copy_simt(dst, src, bytes, lane);
+        else
+          warp_cast_simt<CAST == 1>(dst, src, bytes, lane);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(sm.empty0 + 8 * slot);
+        ptx::bulk_commit();  // always one group per item (possibly empty) so the wait_group counts hold
+      }
+    } else if (CAST == 0 && rp.variant == 0) {
+      if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < kMaxDst; ++d)
+          if (d < ndst) {
+            if (rp.cache_hint & 2)
+              ptx::bulk_s2g_hint(reinterpret_cast<void*>(c.dst[d]), in, bytes, policy);
+            else
+              ptx::bulk_s2g(reinterpret_cast<void*>(c.dst[d]), in, bytes);
+          }
+        ptx::bulk_commit();
+        deferred |= 1u << (q & 31);
+      }
+    } else if (CAST == 0) {  // variants 1, 2, 3, 4: the slot is released synchronously
+      if (rp.variant == 1) {
+        for (int d = 0; d < ndst; ++d) warp_store_from_smem(reinterpret_cast<uint8_t*>(c.dst[d]), in, bytes, lane);
+      } else if (rp.variant == 4) {
+        warp_store_from_smem_mc(reinterpret_cast<uint8_t*>(c.dst[0]), in, bytes, lane);
+      } else if (rp.variant == 3) {  // stores only: whatever is in the slot
         if (lane == 0) {
-          ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);
 #pragma unroll
           for (int d = 0; d < kMaxDst; ++d)
-            if (d < p.ndst) {
-              if (rp.cache_hint & 2)
-                ptx::bulk_s2g_hint(p.dst[d], slot, p.bytes, policy);
-              else
-                ptx::bulk_s2g(p.dst[d], slot, p.bytes);
-            }
+            if (d < ndst) ptx::bulk_s2g(reinterpret_cast<void*>(c.dst[d]), in, bytes);
+          ptx::bulk_commit();
+          ptx::bulk_wait_read<0>();
         }
-        phase ^= 1u << s;
-      } else if (CAST == 0 && rp.variant == 3) {  // stores only: whatever is in the slot
-        if (lane == 0) {
-#pragma unroll
-          for (int d = 0; d < kMaxDst; ++d)
-            if (d < p.ndst) ptx::bulk_s2g(p.dst[d], slot, p.bytes);
-        }
-      } else if (CAST == 0) {  // variants 1, 2: every lane observes the landed tile
-        ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);
-        phase ^= 1u << s;
-        if (rp.variant == 1) {
-          for (int d = 0; d < p.ndst; ++d) warp_store_from_smem(p.dst[d], slot, p.bytes, lane);
-        } else if (rp.variant == 4) {
-          warp_store_from_smem_mc(p.dst[0], slot, p.bytes, lane);
-        }
-        __syncwarp();
-      } else {
-        const uint32_t dst_bytes = CAST == 1 ? p.bytes * 2 : p.bytes / 2;
-        const uint32_t ob = out0 + (q & 1) * rp.tile_out;
-        if (lane == 0) ptx::bulk_wait_read<1>();  // store q-2 (same out buffer) has been read out
-        __syncwarp();
-        ptx::mbar_wait(bar0 + 8 * s, (phase >> s) & 1u);  // every lane reads the slot
-        phase ^= 1u << s;
-        convert_smem<CAST == 1>(slot, ob, p.bytes, lane);
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int d = 0; d < kMaxDst; ++d)
-            if (d < p.ndst) ptx::bulk_s2g(p.dst[d], ob, dst_bytes);
-        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(sm.empty0 + 8 * slot);
+        if (rp.variant != 3) ptx::bulk_commit();
       }
     } else {
-      for (int d = 0; d < p.ndst; ++d) {
-        if (CAST == 0 && rp.variant == 4)
-          warp_copy_simt_mc(p.dst[d], p.src, p.bytes, lane);
-        else if (CAST == 0)
-          warp_copy_simt(p.dst[d], p.src, p.bytes, lane);
-        else
-          warp_cast_simt<CAST == 1>(p.dst[d], p.src, p.bytes, lane);
+      const uint32_t dst_bytes = CAST == 1 ? bytes * 2 : bytes / 2;
+      const uint32_t ob = sm.out0 + (q & 1) * rp.tile_out;
+      if (lane == 0) ptx::bulk_wait_read<1>();  // store q-2 (same out buffer) has been read out
+      __syncwarp();
+      convert_smem<CAST == 1>(in, ob, bytes, lane);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(sm.empty0 + 8 * slot);  // the input slot is free as soon as it has been converted
+#pragma unroll
+        for (int d = 0; d < kMaxDst; ++d)
+          if (d < ndst) ptx::bulk_s2g(reinterpret_cast<void*>(c.dst[d]), ob, dst_bytes);
+        ptx::bulk_commit();
       }
     }
-    if (lane == 0) {
-      ptx::bulk_commit();  // always one group per item (possibly empty) so the counts hold
-      // byte-exact TMA ring: stores q-P+1..q may still drain; store q-P has left slot (q-P)%S == (q+A)%S
-      if (!sync_slot) ptx::bulk_wait_read_n(rp.P);
+    if (deferred_release && lane == 0) {
+      // stores q-P+1..q may still be reading their slots; everything older has left shared memory
+      ptx::bulk_wait_read_n(P);
+      if (q >= static_cast<uint32_t>(P)) {
+        const uint32_t j = q - P;
+        if (deferred & (1u << (j & 31))) {
+          ptx::mbar_arrive(sm.empty0 + 8 * (j % S));
+          deferred &= ~(1u << (j & 31));
+        }
+      }
     }
+    ++unpublished;
   }
 
-  drain_stores(lane);
-  if (!aborted) arrive_layers(ss, open_layer, ss.layer_end, lane);  // never publish layers that were not copied
-  arrive_transfer(ss, lane);
+  drain();
+  if (lane == 0) {
+    if (ss.want_layers && unpublished != 0) arrive_layer(ss, cur_layer, unpublished);
+    arrive_transfer(ss);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -519,6 +572,46 @@ __device__ __forceinline__ void warp_cast_simt(uint8_t* dst, const uint8_t* src,
     for (uint32_t i = lane; i < elems; i += 32)
       dst[i] = static_cast<uint8_t>(ptx::bf16x2_to_e4m3x2(s[i]) & 0xff);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// One CTA = R rings.  Shared memory: [R x ring_ctl_bytes()] [R x S x tile_in] [R x 2 x tile_out]
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t cta_smem_bytes(int R, int S, uint32_t tile_in, uint32_t tile_out)
+{
+  return static_cast<uint32_t>(R) * (ring_ctl_bytes() + static_cast<uint32_t>(S) * tile_in + 2u * tile_out);
+}
+
+template <int CAST, class Gen>
+__device__ __forceinline__ void run_rings(uint8_t* smem, const Gen& gen, uint32_t total, int ndst, const RingParams& rp,
+                                          const StreamSync& ss)
+{
+  const int warp = threadIdx.x >> 5;
+  const int R = blockDim.x >> 6;
+  const int ring = warp >> 1;
+  const bool producer = (warp & 1) == 0;
+  uint8_t* ctl = smem + ring * ring_ctl_bytes();
+  RingSmem sm;
+  sm.full0 = ptx::smem_addr(ctl);
+  sm.empty0 = sm.full0 + 8 * kMaxStages;
+  sm.ctl = reinterpret_cast<SlotCtl*>(ctl + 16 * kMaxStages);
+  uint8_t* in_base = smem + R * ring_ctl_bytes();
+  sm.in0 = ptx::smem_addr(in_base + static_cast<size_t>(ring) * rp.S * rp.tile_in);
+  sm.out0 = ptx::smem_addr(in_base + static_cast<size_t>(R) * rp.S * rp.tile_in + static_cast<size_t>(ring) * 2 * rp.tile_out);
+  if (producer && (threadIdx.x & 31) == 0) {
+    for (int s = 0; s < rp.S; ++s) {
+      ptx::mbar_init(sm.full0 + 8 * s, 1);
+      ptx::mbar_init(sm.empty0 + 8 * s, 1);
+    }
+    ptx::mbar_fence_init();
+  }
+  __syncthreads();
+  const uint32_t nrings = gridDim.x * R;
+  const uint32_t my_ring = blockIdx.x * R + ring;
+  if (producer)
+    ring_producer<CAST>(gen, total, my_ring, nrings, sm, ndst, rp, ss);
+  else
+    ring_consumer<CAST>(sm, ndst, rp, ss);
 }
 
 }  // namespace kvbm

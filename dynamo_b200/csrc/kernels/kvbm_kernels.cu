@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <cstdio>
 #include <vector>
 
@@ -55,127 +56,160 @@ static int default_ctas(const DeviceInfo& di) { return (di.sm_count + 1) / 2; }
 
 // Ring geometry of one launch.
 struct RingCfg {
-  int warps;        // W
-  int stages;       // S (input slots per warp)
-  int pending;      // P (stores allowed to keep draining their slot); loads ahead A = S - P
+  int rings;        // R rings per CTA (2 warps each)
+  int stages;       // S (input slots per ring)
+  int pending;      // P (TMA stores allowed to keep draining their slot); loads ahead = S - P
+  int batch;        // largest scheduler ticket, items
   uint32_t tile;    // source bytes per slot
   uint32_t smem;    // dynamic shared memory bytes
   uint32_t out_tile;  // cast only
 };
 
-constexpr uint32_t kBarBytesPerWarp = kMaxStages * 8;
-// defaults tuned on B200 (profiles/r01_sweep_*.json)
-constexpr int kDefaultWarps = 4;
-constexpr int kDefaultStages = 3;
+// defaults measured on B200 (benchmarks/copylab.cu -> profiles/r02_copylab_*.jsonl): 74 CTAs x 2 rings x 6 slots x
+// 16 KiB with guided tickets of <= 8 items copy 512 MiB HBM->HBM in 0.1704 ms (cudaMemcpy 0.1731, reference K1 0.1783)
+constexpr int kDefaultRings = 2;
+constexpr int kDefaultStages = 6;
 constexpr uint32_t kDefaultTile = 16384;
+constexpr int kDefaultBatch = 8;
 
 static uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 
-// cast: 0 none, 1 up (out = 2x), 2 down (out = x/2)
-static RingCfg make_ring(const DeviceInfo& di, uint32_t unit_bytes, int warps, int stages, int tile,
-                         int cast, int pending = 0, int ndst = 1)
+// cast: 0 none, 1 up (out = 2x), 2 down (out = x/2).  `warps` is the legacy knob: 2 warps make one ring.
+static RingCfg make_ring(const DeviceInfo& di, uint32_t unit_bytes, int warps, int stages, int tile, int cast, int pending = 0)
 {
   RingCfg c{};
-  c.warps = warps > 0 ? std::min(warps, 16) : kDefaultWarps;
+  c.rings = warps > 0 ? std::max(1, std::min(warps, 16) / 2) : kDefaultRings;
+  c.batch = kDefaultBatch;
   // default tile: the whole unit when it is small, else kDefaultTile pieces
   uint32_t t = tile > 0 ? static_cast<uint32_t>(tile) : std::min<uint32_t>(std::max<uint32_t>(unit_bytes, 16), kDefaultTile);
   t = round_up(t, 32);
   const uint32_t budget = static_cast<uint32_t>(di.max_smem_optin) - 1024;
   for (;;) {
     const uint32_t out = cast == 1 ? 2 * t : (cast == 2 ? t / 2 : 0);
-    const uint32_t fixed = c.warps * (kBarBytesPerWarp + desc_bytes_per_warp(ndst) + 2 * out);
-    int s = stages > 0 ? stages : kDefaultStages;
-    s = std::min(s, kMaxStages);
-    while (s > 2 && fixed + c.warps * s * t > budget) --s;
-    if (fixed + c.warps * s * t <= budget) {
+    // default depth: ~96 KiB of slots per ring (small tiles get more slots), at least 3, at most 12
+    int s = stages > 0 ? stages : std::max(3, std::min<int>(12, static_cast<int>(kDefaultStages * kDefaultTile / t)));
+    s = std::max(2, std::min(s, kMaxStages));  // one slot cannot overlap a load with a store
+    while (s > 2 && cta_smem_bytes(c.rings, s, t, out) > budget) --s;
+    if (cta_smem_bytes(c.rings, s, t, out) <= budget) {
       c.stages = s;
-      c.pending = pending > 0 ? std::min(pending, s - 1) : std::max(1, s / 2);
+      c.pending = pending > 0 ? std::min(pending, s - 1) : std::max(1, s / 3);
       c.tile = t;
       c.out_tile = out;
-      c.smem = fixed + c.warps * s * t;
+      c.smem = cta_smem_bytes(c.rings, s, t, out);
       return c;
     }
     if (t > 1024)
       t = round_up(t / 2, 32);
-    else if (c.warps > 1)
-      c.warps /= 2;
+    else if (c.rings > 1)
+      c.rings /= 2;
     else {
       c.stages = 2;
       c.pending = 1;
       c.tile = t;
       c.out_tile = out;
-      c.smem = fixed + 2 * t;
+      c.smem = cta_smem_bytes(1, 2, t, out);
       return c;
     }
   }
 }
 
-// shared-memory carve-up: [bars: W * kMaxStages * 8][descriptor rings: W * desc][in slots: W * S * tile][out slots: W * 2 * out_tile]
-struct SmemView {
-  uint64_t* bars;
-  uint8_t* desc;
-  uint8_t* in;
-  uint8_t* out;
+// ------------------------------------------------------------------------------------------------
+// Scheduler words for launches that bring no workspace (legacy callers, opts == NULL): a small per-device pool of
+// zeroed 4-word slots.  A slot is handed to one launch at a time: an event recorded behind the launch tells when it
+// may be reused (the kernel leaves the words zeroed).  No free slot, or a stream that is being captured into a
+// graph, simply means a static tile schedule for that launch -- never a wait.
+// ------------------------------------------------------------------------------------------------
+struct SchedPool {
+  static constexpr int kSlots = 64;
+  std::mutex mu;
+  uint32_t* words = nullptr;  // kSlots * 4
+  cudaEvent_t ev[kSlots] = {};
+  bool used[kSlots] = {};
+  int next = 0;
+  bool failed = false;
 };
+static SchedPool g_pools[64];
 
-__device__ __forceinline__ SmemView carve(uint8_t* base, int W, int S, uint32_t tile, uint32_t out_tile, int ndst)
+static uint32_t* sched_acquire(int dev, cudaStream_t stream, int* slot_out)
 {
-  const int warp = threadIdx.x >> 5;
-  SmemView v;
-  v.bars = reinterpret_cast<uint64_t*>(base) + warp * kMaxStages;
-  const uint32_t db = desc_bytes_per_warp(ndst);
-  v.desc = base + W * kBarBytesPerWarp + warp * db;
-  uint8_t* in0 = base + W * (kBarBytesPerWarp + db);
-  v.in = in0 + static_cast<size_t>(warp) * S * tile;
-  v.out = in0 + static_cast<size_t>(W) * S * tile + static_cast<size_t>(warp) * 2 * out_tile;
-  return v;
+  *slot_out = -1;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  SchedPool& p = g_pools[dev];
+  std::lock_guard<std::mutex> lk(p.mu);
+  if (p.failed) return nullptr;
+  if (!p.words) {
+    if (cudaMalloc(&p.words, SchedPool::kSlots * 16) != cudaSuccess || cudaMemset(p.words, 0, SchedPool::kSlots * 16) != cudaSuccess) {
+      (void)cudaGetLastError();
+      p.failed = true;
+      p.words = nullptr;
+      return nullptr;
+    }
+    for (int i = 0; i < SchedPool::kSlots; ++i)
+      if (cudaEventCreateWithFlags(&p.ev[i], cudaEventDisableTiming) != cudaSuccess) {
+        (void)cudaGetLastError();
+        p.failed = true;
+        return nullptr;
+      }
+  }
+  for (int n = 0; n < SchedPool::kSlots; ++n) {
+    const int i = (p.next + n) % SchedPool::kSlots;
+    if (p.used[i]) {
+      if (cudaEventQuery(p.ev[i]) != cudaSuccess) {
+        (void)cudaGetLastError();
+        continue;
+      }
+      p.used[i] = false;
+    }
+    p.used[i] = true;  // busy until sched_release records its event (and that event completes)
+    p.next = (i + 1) % SchedPool::kSlots;
+    *slot_out = i;
+    return p.words + 4 * i;
+  }
+  return nullptr;
 }
 
-__device__ __forceinline__ void init_bars(uint64_t* bars, int S)
+static void sched_release(int dev, int slot, cudaStream_t stream)
 {
-  if ((threadIdx.x & 31) == 0) {
-    for (int s = 0; s < S; ++s) ptx::mbar_init(ptx::smem_addr(bars + s), 1);
-    ptx::mbar_fence_init();
+  if (slot < 0) return;
+  SchedPool& p = g_pools[dev];
+  std::lock_guard<std::mutex> lk(p.mu);
+  if (cudaEventRecord(p.ev[slot], stream) != cudaSuccess) {
+    (void)cudaGetLastError();
+    // cannot tell when the launch ends: retire the slot for good rather than risk sharing it
   }
-  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: pointer-pair copy (legacy ABI).  item = (pair, tile-within-pair)
+// K1: pointer-pair copy (legacy ABI).  Hardware-scheduled SIMT: one CTA per (pair, 32 KiB chunk) -- or one warp per
+// pair when pairs are small -- 8 independent 16 B loads in flight per thread, the alignment ladder of the reference.
+// The CTA scheduler is the dynamic load balancer here, so the ABI needs no workspace and the library no state.
 // ------------------------------------------------------------------------------------------------
-struct PairGen {
-  void* const* src_ptrs;
-  void* const* dst_ptrs;
-  size_t copy_size;
-  uint32_t tiles_per_pair;
-  uint32_t tile;
-  __device__ __forceinline__ void get(uint32_t item, Piece& p) const
-  {
-    const uint32_t pair = item / tiles_per_pair;
-    const uint32_t t = item - pair * tiles_per_pair;
-    const size_t off = static_cast<size_t>(t) * tile;
-    p.src = static_cast<const uint8_t*>(src_ptrs[pair]) + off;
-    p.dst[0] = static_cast<uint8_t*>(dst_ptrs[pair]) + off;
-    const size_t left = copy_size - off;
-    p.bytes = left < tile ? static_cast<uint32_t>(left) : tile;
-    p.ndst = 1;
-    p.layer = 0;
-  }
-};
+constexpr uint32_t kPairChunk = 32768;
+constexpr uint32_t kPairSmall = 4096;
 
-__global__ void __launch_bounds__(512, 1)
-kvbm_pair_copy_kernel(PairGen gen, uint32_t total, int S, int P, uint32_t tile, int allow_tma)
+__global__ void __launch_bounds__(256)
+kvbm_pair_copy_kernel(void* const* __restrict__ src_ptrs, void* const* __restrict__ dst_ptrs, size_t copy_size,
+                      uint32_t chunks_per_pair, uint64_t num_pairs)
 {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int W = blockDim.x >> 5;
-  SmemView v = carve(smem, W, S, tile, 0, 1);
-  init_bars(v.bars, S);
-  StreamSync ss{};
-  ss.layer_end = 1;
-  RingParams rp{S, P, tile, 0, allow_tma != 0, 0, 0};
-  // interleave warps of different CTAs over neighbouring items: item i -> CTA (i % grid), warp (i / grid) % W
-  const uint32_t first = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
-  warp_ring<0>(gen, first, gridDim.x * W, total, v.in, v.out, v.bars, v.desc, 1, rp, ss);
+  const uint64_t bid = blockIdx.x + static_cast<uint64_t>(gridDim.x) * blockIdx.y;
+  if (copy_size <= kPairSmall) {  // warp per pair
+    const uint64_t pair = bid * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pair >= num_pairs) return;
+    group_copy_simt(static_cast<uint8_t*>(dst_ptrs[pair]), static_cast<const uint8_t*>(src_ptrs[pair]), copy_size, threadIdx.x & 31, 32);
+    return;
+  }
+  const uint64_t pair = bid / chunks_per_pair;
+  if (pair >= num_pairs) return;
+  const uint32_t chunk = static_cast<uint32_t>(bid - pair * chunks_per_pair);
+  const size_t off = static_cast<size_t>(chunk) * kPairChunk;
+  const size_t left = copy_size - off;
+  // chunk boundaries are multiples of 32 KiB, so the alignment class of (src, dst) is the same for every chunk
+  group_copy_simt(static_cast<uint8_t*>(dst_ptrs[pair]) + off, static_cast<const uint8_t*>(src_ptrs[pair]) + off,
+                  left < kPairChunk ? left : kPairChunk, threadIdx.x, blockDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -259,32 +293,33 @@ struct PagedGen {
 
 struct PagedSyncArgs {
   const uint32_t* layer_ready;
-  uint32_t* workspace;
+  uint32_t* layer_counters;  // [num_layers] (user workspace) or null
+  uint32_t* ctl;             // 3 control words: rings finished, abort, scheduler tickets; null = static schedule
   uint32_t* done_flag[kMaxDst];
   uint32_t* layer_done[kMaxDst];
   uint32_t* completion_flag;
   uint32_t completion_value;
   uint32_t epoch;
-  int num_layers_total;
   uint64_t gate_timeout_ns;
   int num_flag_dsts;  // destinations that get flags (== data destinations unless multicast)
 };
 
-__device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const PagedArgs& a, int W)
+__device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const PagedArgs& a, uint32_t total, int R)
 {
   StreamSync ss{};
   ss.gate = s.layer_ready != nullptr;
   ss.want_layers = false;
-  ss.want_done = s.completion_flag != nullptr || s.layer_ready != nullptr;  // gated launches always count their warps (abort cleanup)
+  ss.want_done = s.completion_flag != nullptr;
   ss.layer_ready = s.layer_ready;
-  ss.workspace = s.workspace;
+  ss.layer_counters = s.layer_counters;
+  ss.ctl = s.ctl;
   ss.epoch = s.epoch;
   ss.gate_timeout_ns = s.gate_timeout_ns;
   ss.completion_flag = s.completion_flag;
   ss.completion_value = s.completion_value;
-  ss.total_warps = gridDim.x * W;
+  ss.total_rings = gridDim.x * R;
+  ss.items_per_layer = total / a.n_layers;
   ss.ndst = s.num_flag_dsts;
-  ss.num_layers = s.num_layers_total;
   ss.layer_begin = static_cast<int>(a.layer_begin);
   ss.layer_end = static_cast<int>(a.layer_begin + a.n_layers);
 #pragma unroll
@@ -294,25 +329,22 @@ __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const Pa
     if (d < s.num_flag_dsts && s.layer_done[d] != nullptr) ss.want_layers = true;
     if (d < s.num_flag_dsts && s.done_flag[d] != nullptr) ss.want_done = true;
   }
+  if (ss.layer_counters == nullptr) ss.want_layers = false;
   return ss;
 }
 
 template <int CAST>
 __global__ void __launch_bounds__(512, 1)
 kvbm_paged_copy_kernel(const __grid_constant__ PagedGen gen, const __grid_constant__ PagedSyncArgs sync,
-                       uint32_t total, int S, int P, uint32_t out_tile, int allow_tma, int cache_hint, int variant)
+                       uint32_t total, int S, int P, int batch, int static_schedule, uint32_t out_tile, int allow_tma, int cache_hint,
+                       int variant)
 {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int W = blockDim.x >> 5;
-  const uint32_t tile = gen.a.tile;
+  const int R = blockDim.x >> 6;
   const int ring_ndst = gen.a.replicate ? gen.a.ndst : 1;
-  SmemView v = carve(smem, W, S, tile, out_tile, ring_ndst);
-  init_bars(v.bars, S);
-  const StreamSync ss = make_sync(sync, gen.a, W);
-  const uint32_t first = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
-  const uint32_t stride = gridDim.x * W;
-  RingParams rp{S, P, tile, out_tile, allow_tma != 0, cache_hint, CAST == KVBM_CAST_NONE ? variant : 0};
-  warp_ring<CAST>(gen, first, stride, total, v.in, v.out, v.bars, v.desc, ring_ndst, rp, ss);
+  const StreamSync ss = make_sync(sync, gen.a, total, R);
+  RingParams rp{S, P, batch, gen.a.tile, out_tile, allow_tma != 0, static_schedule != 0, cache_hint, CAST == KVBM_CAST_NONE ? variant : 0};
+  run_rings<CAST>(smem, gen, total, ring_ndst, rp, ss);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -363,6 +395,67 @@ kvbm_permute_kernel(void* const* universal_ptrs, void* const* block_ptrs, uint64
   }
 }
 
+// Fast path of K2 / K3 for head rows that are a power-of-two number of 16-byte vectors (hd*elem = 64 B ... 4 KiB: every
+// real KV geometry).  One CTA per (block, layer, outer) chunk -- the hardware CTA scheduler balances the SMs -- and one
+// warp per head: for a fixed head the universal side is ONE contiguous run of nt rows and the chunk side is nt rows at a
+// constant stride (NHD) or contiguous as well (HND), so a lane's addresses advance by shifts and adds: no division per
+// vector (the reference peels 5 div/mod per ELEMENT, tensor_kernels.cu:150-187) and 8 independent 16 B loads per lane
+// are in flight before the first store.
+template <bool TO_UNIVERSAL>
+__global__ void __launch_bounds__(256)
+kvbm_permute_rows_kernel(void* const* __restrict__ universal_ptrs, void* const* __restrict__ block_ptrs, uint32_t nh, uint32_t nl,
+                         uint32_t no, uint32_t nt, uint32_t log2_v /* 16 B vectors per head row */, uint32_t elem, int layout)
+{
+  const uint32_t chunk_id = blockIdx.x;  // (b * nl + nl_i) * no + no_i
+  const uint32_t b = chunk_id / (nl * no);
+  const uint32_t rem = chunk_id - b * (nl * no);
+  const uint32_t nl_i = rem / no, no_i = rem - nl_i * no;
+  uint8_t* chunk = static_cast<uint8_t*>(block_ptrs[chunk_id]);
+  uint8_t* uni = static_cast<uint8_t*>(universal_ptrs[b]);
+  const uint32_t V = 1u << log2_v;
+  const uint32_t row = V << 4;            // bytes per head row
+  const uint32_t run = nt << log2_v;      // 16 B vectors of one head on the universal side
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(chunk) | reinterpret_cast<uintptr_t>(uni)) & 15) == 0;
+  for (uint32_t nh_i = warp; nh_i < nh; nh_i += nwarps) {
+    uint8_t* u = uni + (static_cast<size_t>((nh_i * nl + nl_i) * no + no_i) * nt << log2_v << 4);
+    // chunk-side offset of vector v = (nt_i, c): NHD (nt_i*nh + nh_i)*row + 16c ; HND (nh_i*nt + nt_i)*row + 16c
+    const size_t c_base = layout == KVBM_BLOCK_LAYOUT_NHD ? static_cast<size_t>(nh_i) * row : static_cast<size_t>(nh_i) * nt * row;
+    const size_t c_stride = layout == KVBM_BLOCK_LAYOUT_NHD ? static_cast<size_t>(nh) * row : row;
+    auto chunk_off = [&](uint32_t v) { return c_base + static_cast<size_t>(v >> log2_v) * c_stride + ((v & (V - 1)) << 4); };
+    if (aligned) {
+      constexpr int U = 8;
+      uint32_t v = lane;
+      for (; v + (U - 1) * 32 < run; v += U * 32) {
+        uint4 x[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+          x[k] = ptx::ld_stream_v4(TO_UNIVERSAL ? chunk + chunk_off(v + k * 32) : u + (static_cast<size_t>(v + k * 32) << 4));
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+          ptx::st_stream_v4(TO_UNIVERSAL ? u + (static_cast<size_t>(v + k * 32) << 4) : chunk + chunk_off(v + k * 32), x[k]);
+      }
+      for (; v < run; v += 32) {
+        const uint4 x = ptx::ld_stream_v4(TO_UNIVERSAL ? chunk + chunk_off(v) : u + (static_cast<size_t>(v) << 4));
+        ptx::st_stream_v4(TO_UNIVERSAL ? u + (static_cast<size_t>(v) << 4) : chunk + chunk_off(v), x);
+      }
+    } else {
+      // buffers only promise element alignment: same walk, one element at a time
+      const uint32_t per_vec = 16 / elem;
+      for (uint32_t e = lane; e < run * per_vec; e += 32) {
+        const uint32_t v = e / per_vec, within = (e - v * per_vec) * elem;
+        uint8_t* cp = chunk + chunk_off(v) + within;
+        uint8_t* up = u + (static_cast<size_t>(v) << 4) + within;
+        uint8_t* d = TO_UNIVERSAL ? up : cp;
+        const uint8_t* sp = TO_UNIVERSAL ? cp : up;
+        if (elem == 2) *reinterpret_cast<uint16_t*>(d) = *reinterpret_cast<const uint16_t*>(sp);
+        else if (elem == 4) *reinterpret_cast<uint32_t*>(d) = *reinterpret_cast<const uint32_t*>(sp);
+        else *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(sp);
+      }
+    }
+  }
+}
+
 static size_t dtype_size(int dtype)
 {
   switch (dtype) {
@@ -396,6 +489,20 @@ static cudaError_t launch_permute(void* const* universal_ptrs, void* const* bloc
   // pointers, so only widen past the element size when the row allows it and keep 2/4/8-byte
   // vectors naturally aligned with the element type.
   const size_t row = hd * elem;
+  DeviceInfo di;
+  cudaError_t e = device_info(&di);
+  if (e != cudaSuccess) return e;
+  if (row >= 16 && row <= 4096 && (row & (row - 1)) == 0 && num_blocks * nl * no < (1ull << 31) && nh * nl * no * nt * row < (1ull << 40)) {
+    uint32_t log2_v = 0;
+    while ((16u << log2_v) < row) ++log2_v;
+    const unsigned grid = static_cast<unsigned>(num_blocks * nl * no);
+    const int threads = static_cast<int>(std::min<size_t>(8, std::max<size_t>(1, nh))) * 32;
+    kvbm_permute_rows_kernel<TO_UNIVERSAL><<<grid, threads, 0, stream>>>(universal_ptrs, block_ptrs, static_cast<uint32_t>(nh),
+                                                                          static_cast<uint32_t>(nl), static_cast<uint32_t>(no),
+                                                                          static_cast<uint32_t>(nt), log2_v, static_cast<uint32_t>(elem), layout);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+  }
   int vec = static_cast<int>(elem);
   if (row % 16 == 0)
     vec = 16;
@@ -406,9 +513,6 @@ static cudaError_t launch_permute(void* const* universal_ptrs, void* const* bloc
   const uint32_t hdv = static_cast<uint32_t>(row / vec);
   const uint32_t units_per_block = static_cast<uint32_t>(total_per_block * elem / vec);
   const uint64_t total_units = static_cast<uint64_t>(units_per_block) * num_blocks;
-  DeviceInfo di;
-  cudaError_t e = device_info(&di);
-  if (e != cudaSuccess) return e;
   const uint64_t want = (total_units + 255) / 256;
   const int grid = static_cast<int>(std::min<uint64_t>(want, static_cast<uint64_t>(di.sm_count) * 16));
   auto go = [&](auto kern) {
@@ -454,6 +558,8 @@ static cudaError_t preload_kernels()
   KVBM_PRELOAD(kvbm_paged_copy_kernel<KVBM_CAST_BF16_TO_FP8E4M3>)
   KVBM_PRELOAD(kvbm_set_flags_kernel)
   KVBM_PRELOAD(kvbm_wait_flag_kernel)
+  KVBM_PRELOAD((kvbm_permute_rows_kernel<true>))
+  KVBM_PRELOAD((kvbm_permute_rows_kernel<false>))
   KVBM_PRELOAD((kvbm_permute_kernel<16, true>))
   KVBM_PRELOAD((kvbm_permute_kernel<8, true>))
   KVBM_PRELOAD((kvbm_permute_kernel<4, true>))
@@ -513,18 +619,22 @@ kvbm_kernels_launch_vectorized_copy(void** src_ptrs, void** dst_ptrs, size_t cop
   cudaError_t e = device_info(&di);
   if (e != cudaSuccess) return e;
 
-  const uint32_t unit = copy_size_bytes > (1u << 20) ? (1u << 20) : static_cast<uint32_t>(copy_size_bytes);
-  RingCfg rc = make_ring(di, unit, 0, 0, 0, 0);
-  const uint64_t tiles_per_pair = (copy_size_bytes + rc.tile - 1) / rc.tile;
-  const uint64_t total = tiles_per_pair * static_cast<uint64_t>(num_pairs);
-  if (tiles_per_pair >= (1ull << 31) || total >= (1ull << 32)) return cudaErrorInvalidValue;
-
-  PairGen gen{src_ptrs, dst_ptrs, copy_size_bytes, static_cast<uint32_t>(tiles_per_pair), rc.tile};
-  const uint64_t ctas_needed = (total + rc.warps - 1) / rc.warps;
-  const int grid = static_cast<int>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(default_ctas(di))));
-  if ((e = set_smem(kvbm_pair_copy_kernel, rc.smem)) != cudaSuccess) return e;
-  kvbm_pair_copy_kernel<<<grid, rc.warps * 32, rc.smem, stream>>>(gen, static_cast<uint32_t>(total), rc.stages,
-                                                                 rc.pending, rc.tile, 1);
+  const uint64_t pairs = static_cast<uint64_t>(num_pairs);
+  uint64_t ctas;
+  uint32_t chunks_per_pair = 1;
+  if (copy_size_bytes <= kPairSmall) {
+    ctas = (pairs + 7) / 8;  // 8 warps per CTA, one pair each
+  } else {
+    const uint64_t cpp = (copy_size_bytes + kPairChunk - 1) / kPairChunk;
+    if (cpp >= (1ull << 32)) return cudaErrorInvalidValue;
+    chunks_per_pair = static_cast<uint32_t>(cpp);
+    ctas = pairs * cpp;
+  }
+  const uint64_t gx = std::min<uint64_t>(ctas, 1ull << 30);
+  const uint64_t gy = (ctas + gx - 1) / gx;
+  if (gy > 65535) return cudaErrorInvalidValue;
+  kvbm_pair_copy_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(gy)), 256, 0, stream>>>(src_ptrs, dst_ptrs, copy_size_bytes,
+                                                                                                    chunks_per_pair, pairs);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();  // :570
 }
@@ -664,9 +774,7 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   sync.completion_flag = o.completion_flag;
   sync.completion_value = o.completion_value;
   sync.layer_ready = o.layer_ready_flags;
-  sync.workspace = o.sync_workspace;
   sync.epoch = o.epoch;
-  sync.num_layers_total = static_cast<int>(src->num_layers);
   sync.gate_timeout_ns = static_cast<uint64_t>(o.gate_timeout_ms > 0 ? o.gate_timeout_ms : 10000) * 1000000ull;
   if (o.layer_ready_flags && !o.sync_workspace) return cudaErrorInvalidValue;  // the abort word lives in the workspace
   bool needs_ws = o.completion_flag != nullptr;
@@ -677,8 +785,7 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   DeviceInfo di;
   cudaError_t e = device_info(&di);
   if (e != cudaSuccess) return e;
-  RingCfg rc = make_ring(di, src->region_bytes, o.warps_per_cta, o.stages, o.tile_bytes, cast_mode, o.stores_in_flight,
-                         gen.a.replicate ? data_dsts : 1);
+  RingCfg rc = make_ring(di, src->region_bytes, o.warps_per_cta, o.stages, o.tile_bytes, cast_mode, o.stores_in_flight);
 
   gen.a.n_blocks = static_cast<uint32_t>(num_blocks);
   gen.a.layer_begin = static_cast<uint32_t>(layer_begin);
@@ -690,24 +797,37 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
   gen.a.dst_den = den;
   const uint64_t fan = gen.a.replicate ? 1 : static_cast<uint64_t>(data_dsts);
   const uint64_t total = static_cast<uint64_t>(gen.a.n_layers) * gen.a.n_blocks * gen.a.outer * fan * gen.a.tiles_per_region;
-  if (total >= (1ull << 32)) return cudaErrorInvalidValue;
+  if (total >= (1ull << 31)) return cudaErrorInvalidValue;
 
-  const uint64_t ctas_needed = (total + rc.warps - 1) / rc.warps;
-  // Default: one CTA per TPC (half the SMs).  Measured on B200 (profiles/r01_sweep_n1_fine.json): 74 CTAs x 4 warps
-  // move 5.96 TB/s r+w on a same-GPU copy vs 5.70 with 148, and 32 CTAs already saturate NVLink -- and the other
-  // half of the chip stays free for whatever the engine is running.
+  const uint64_t rings_needed = (total + rc.batch - 1) / rc.batch;
+  const uint64_t ctas_needed = (rings_needed + rc.rings - 1) / rc.rings;
+  // Default: one CTA per TPC (half the SMs).  Measured on B200 (profiles/r02_copylab_n1_b.jsonl): 74 CTAs x 2 rings move
+  // 512 MiB HBM->HBM in 0.1704 ms, the same as 132-148 CTAs x 1 ring, and 16 CTAs already saturate an NVLink peer --
+  // and the other half of the chip stays free for whatever the engine is running.
   int cap = o.max_ctas > 0 ? o.max_ctas : (cast_mode == KVBM_CAST_NONE ? default_ctas(di) : di.sm_count);  // the cast is ALU work: use every SM
   const int grid = static_cast<int>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(cap)));
   const int allow_tma = o.force_simt ? 0 : 1;
   const uint32_t total32 = static_cast<uint32_t>(total);
 
+  // control words: the caller's workspace ([num_layers] layer counters, then 3 control words) or a pool slot
+  int dev = 0, pool_slot = -1;
+  if (o.sync_workspace) {
+    sync.layer_counters = o.sync_workspace;
+    sync.ctl = o.sync_workspace + src->num_layers;
+  } else if (!o.static_schedule && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+    sync.ctl = sched_acquire(dev, stream, &pool_slot);
+  }
+
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t err = set_smem(kern, rc.smem);
-    if (err != cudaSuccess) return err;
-    kern<<<grid, rc.warps * 32, rc.smem, stream>>>(gen, sync, total32, rc.stages, rc.pending, rc.out_tile, allow_tma,
-                                                   o.cache_hint, mc ? (o.multicast == 2 ? 0 : 4) : o.variant);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return cudaGetLastError();
+    if (err == cudaSuccess) {
+      kern<<<grid, rc.rings * 64, rc.smem, stream>>>(gen, sync, total32, rc.stages, rc.pending, rc.batch, o.static_schedule,
+                                                     rc.out_tile, allow_tma, o.cache_hint, mc ? (o.multicast == 2 ? 0 : 4) : o.variant);
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      err = cudaGetLastError();
+    }
+    sched_release(dev, pool_slot, stream);
+    return err;
   };
   switch (cast_mode) {
     case KVBM_CAST_NONE: return launch(kvbm_paged_copy_kernel<KVBM_CAST_NONE>);

@@ -101,7 +101,13 @@ class PagedCopyOpts(C.Structure):
         ("variant", C.c_int),
         ("gate_timeout_ms", C.c_int),
         ("multicast", C.c_int),
+        ("static_schedule", C.c_int),
     ]
+
+
+def sync_workspace_words(num_layers: int) -> int:
+    """KVBM_SYNC_WORKSPACE_WORDS: u32 words of PagedCopyOpts.sync_workspace (per-layer counters + control words)."""
+    return int(num_layers) + 4
 
 
 _configured = False

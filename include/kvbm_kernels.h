@@ -83,6 +83,8 @@ bool kvbm_kernels_is_stub_build(void);
 /* ============================ Part 2: v2 extensions ============================ */
 
 #define KVBM_MAX_DESTINATIONS 8
+/* u32 words of kvbm_paged_copy_opts.sync_workspace for a source pool of `num_layers` layers */
+#define KVBM_SYNC_WORKSPACE_WORDS(num_layers) ((num_layers) + 4)
 
 /* Geometry of one KV pool as the kernel sees it.  It is the device form of
  * Layout::memory_region (lib/kvbm-physical/src/layout/mod.rs:73-78):
@@ -119,9 +121,12 @@ enum {
 typedef struct kvbm_paged_copy_opts {
   uint32_t epoch;                 /* value written to done flags / compared with ready flags (>=) */
   const uint32_t* layer_ready_flags; /* nullable; [num_layers]; layer l is read only after flag >= epoch */
-  uint32_t* sync_workspace;       /* device u32[num_layers + 2], zeroed (left zeroed); required iff any flag or gating is used */
+  uint32_t* sync_workspace;       /* device u32[KVBM_SYNC_WORKSPACE_WORDS(num_layers)], zeroed (left zeroed by every launch):
+                                     per-layer landed-item counters, then the launch's control words (rings finished, abort,
+                                     tile-scheduler tickets).  Required iff any flag or gating is used; without it the
+                                     library lends the launch a slot of a small per-device pool for the tile scheduler. */
   int max_ctas;                   /* 0 = default (one CTA per TPC = #SM/2, the measured optimum); smaller values leave more SMs to the engine */
-  int warps_per_cta;              /* 0 = default */
+  int warps_per_cta;              /* 0 = default (4).  Two warps -- a producer and a consumer -- form one ring. */
   int stages;                     /* 0 = default */
   int tile_bytes;                 /* 0 = default */
   int force_simt;                 /* 1 = never use the TMA path (diagnostics) */
@@ -142,6 +147,8 @@ typedef struct kvbm_paged_copy_opts {
                                      device bound to the object; dsts[1..] contribute only their done / layer_done flags.  This is
                                      the replacement of the grouped ncclBcast (kvbm-engine collectives/nccl.rs:421-462): egress of
                                      the source GPU is 1x the payload instead of Nx.  Requires cast_mode NONE, 16-byte strides. */
+  int static_schedule;            /* diagnostics: 1 = split the tiles round-robin over the rings instead of the dynamic
+                                     (ticket) tile scheduler */
 } kvbm_paged_copy_opts;
 
 /* Gather `num_blocks` non-contiguous blocks x layers [layer_begin, layer_end) x outer from `src`,

@@ -1,3 +1,4 @@
+#define _GNU_SOURCE
 /*
  * kvbm_oracle.c -- CPU restatement of the reference KV-block transfer path (see kvbm_oracle.h).
  * TEST INFRASTRUCTURE ONLY: never linked into, loaded by, or called from the product path.
@@ -6,6 +7,7 @@
 
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -228,11 +230,18 @@ typedef struct {
   int has_range;
   size_t lb, le;
   int rc;
+  int cpu; /* >= 0: pin this worker to that CPU (bench hygiene: no migration between NUMA nodes mid-copy) */
 } mt_job;
 
 static void* mt_worker(void* p)
 {
   mt_job* j = (mt_job*)p;
+  if (j->cpu >= 0) {
+    cpu_set_t one;
+    CPU_ZERO(&one);
+    CPU_SET(j->cpu, &one);
+    (void)pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+  }
   j->rc = oracle_execute_memcpy_transfer(j->src, j->dst, j->src_ids + j->begin,
                                          j->dst_ids + j->begin, j->end - j->begin, j->has_range,
                                          j->lb, j->le);
@@ -248,9 +257,15 @@ int oracle_execute_memcpy_transfer_mt(const oracle_layout* src, const oracle_lay
   if ((size_t)nthreads > n) nthreads = (int)n;
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
   mt_job* jobs = (mt_job*)malloc(sizeof(mt_job) * nthreads);
+  /* worker t runs on the t-th CPU this process is allowed to use */
+  cpu_set_t allowed;
+  int cpus[CPU_SETSIZE], ncpu = 0;
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0)
+    for (int c = 0; c < CPU_SETSIZE; ++c)
+      if (CPU_ISSET(c, &allowed)) cpus[ncpu++] = c;
   for (int t = 0; t < nthreads; ++t) {
     mt_job j = {src, dst, src_ids, dst_ids, n * t / nthreads, n * (t + 1) / nthreads,
-                has_range, lb, le, 0};
+                has_range, lb, le, 0, ncpu > 0 ? cpus[t % ncpu] : -1};
     jobs[t] = j;
     pthread_create(&th[t], NULL, mt_worker, &jobs[t]);
   }

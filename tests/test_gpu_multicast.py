@@ -125,7 +125,7 @@ def test_kernel_abi_multicast_with_per_receiver_flags_and_layer_range(group, mod
     s_t = torch.tensor(sid, dtype=torch.int32, device="cuda:0")
     d_t = torch.tensor(did, dtype=torch.int32, device="cuda:0")
     flags = [torch.zeros(1 + NL, dtype=torch.int32, device=f"cuda:{d}") for d in range(ndev)]
-    ws = torch.zeros(NL + 2, dtype=torch.int32, device="cuda:0")
+    ws = torch.zeros(NL + 4, dtype=torch.int32, device="cuda:0")
     dsts = [K.PagedDst(d_desc, s_t.data_ptr(), d_t.data_ptr(), f.data_ptr(), f[1:].data_ptr()) for f in flags]
     opts = K.PagedCopyOpts(epoch=3, sync_workspace=ws.data_ptr(), multicast=mode)
     K.check(K.paged_copy(s_desc, dsts, n, 1, 3, 0, opts, int(torch.cuda.current_stream().cuda_stream)), "paged_copy")

@@ -205,7 +205,7 @@ def test_completion_and_layer_flags():
     src_p, d0_p, d1_p = DevicePool(src_h), DevicePool(d0_h), DevicePool(d1_h)
     flags = torch.zeros(2, dtype=torch.int32, device="cuda")
     layer_flags = torch.zeros(2, nl, dtype=torch.int32, device="cuda")
-    ws = torch.zeros(nl + 2, dtype=torch.int32, device="cuda")
+    ws = torch.zeros(nl + 4, dtype=torch.int32, device="cuda")
     ready = torch.zeros(nl, dtype=torch.int32, device="cuda")
     s_ids = ids_dev(sid)
     a, b = ids_dev(did0), ids_dev(did1)
@@ -223,7 +223,7 @@ def test_completion_and_layer_flags():
         torch.cuda.synchronize()
         assert flags.tolist() == [epoch, epoch]
         assert layer_flags.tolist() == [[epoch] * nl, [epoch] * nl]
-        assert ws.tolist() == [0] * (nl + 2)
+        assert ws.tolist() == [0] * (nl + 4)
     check_against_oracle(src_h, d0_h, d0_p, sid, did0)
     check_against_oracle(src_h, d1_h, d1_p, sid, did1)
 
@@ -387,7 +387,7 @@ def test_gate_timeout_aborts_instead_of_hanging():
     src_p, dst_p = DevicePool(src_h), DevicePool(dst_h)
     ready = torch.zeros(nl, dtype=torch.int32, device="cuda")
     done = torch.zeros(1, dtype=torch.int32, device="cuda")
-    ws = torch.zeros(nl + 2, dtype=torch.int32, device="cuda")
+    ws = torch.zeros(nl + 4, dtype=torch.int32, device="cuda")
     host_word = torch.zeros(16, dtype=torch.int32).pin_memory()
     s, d = ids_dev(range(n)), ids_dev(range(n, 2 * n))
     K.check(K.set_flags(ready.data_ptr(), 0, 1, 9, stream_ptr()))          # only layer 0 is ever released
@@ -398,7 +398,7 @@ def test_gate_timeout_aborts_instead_of_hanging():
                         stream_ptr(side)) == 0
     side.synchronize()                                                      # returns: the kernel did not hang
     assert (int(host_word[0]) & 0xFFFFFFFF) == 0xFFFFFFFF and done.tolist() == [0]
-    assert ws.tolist() == [0] * (nl + 2)                                     # workspace left clean for the next launch
+    assert ws.tolist() == [0] * (nl + 4)                                     # workspace left clean for the next launch
     # layer 0 (released) was copied, later layers were not
     dst_p.download()
     assert dst_h.block_checksums(range(n, 2 * n), range(0, 1)) == {n + i: src_h.block_checksum(i, range(0, 1)) for i in range(n)}
