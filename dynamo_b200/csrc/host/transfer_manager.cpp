@@ -232,6 +232,9 @@ struct kvbm_transfer_manager {
   std::unordered_map<std::string, void*> ipc_cache;
   // (agent name, worker id) of every SerializedLayout imported so far (manager/mod.rs:572-584 refuses a second load)
   std::set<std::pair<std::string, uint64_t>> loaded_remotes;
+  // TransferCapabilities (transfer/strategy.rs:245-278).  allow_gpu_rdma = peers may be written directly over NVLink
+  // (the default here); 0 forces the reference's TwoHop plan Device -> Pinned -> Device through a bounce buffer.
+  kvbm_transfer_capabilities caps{0, 1};
 
   Layout* find(kvbm_layout_handle h)
   {
@@ -480,72 +483,12 @@ static int check_compat(const Layout& S, const Layout& D, int cast)
   return KVBM_OK;
 }
 
-static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, const kvbm_layout_handle* dst_h,
-                   const size_t* const* src_ids, const size_t* const* dst_ids, size_t n, bool replicate,
-                   const kvbm_transfer_options* opts_in, kvbm_notification* out)
+// One block-table kernel launch (execute_cuda_transfer, executor/cuda.rs:39-156) on `stream`, optionally ordered after
+// `wait_ev`.  The manager mutex is held by the caller.
+static int launch_cuda(kvbm_transfer_manager* m, Layout* S, Layout* const* D, int nd, const size_t* const* src_ids,
+                       const size_t* const* dst_ids, size_t n, bool replicate, size_t lb, size_t le,
+                       const kvbm_transfer_options& o, cudaStream_t stream, cudaEvent_t wait_ev, Slot** slot_out, uint64_t* seq_out)
 {
-  kvbm_transfer_options o{};
-  if (opts_in) o = *opts_in;
-  if (out) *out = 0;
-  if (nd < 1 || nd > KVBM_MAX_DESTINATIONS) return fail(KVBM_ERR, "number of destinations must be in 1..=8");
-  std::lock_guard<std::mutex> lk(m->mu);
-  Layout* S = m->find(src_h);
-  if (!S) return fail(KVBM_ERR_HANDLE, "invalid source handle");
-  if (S->unmapped) return fail(KVBM_ERR_UNSUPPORTED, "source layout is a descriptor of another process's host memory: not addressable from this process");
-  std::vector<Layout*> D(nd);
-  for (int d = 0; d < nd; ++d) {
-    D[d] = m->find(dst_h[d]);
-    if (!D[d]) return fail(KVBM_ERR_HANDLE, "invalid destination handle");
-    if (D[d]->unmapped) return fail(KVBM_ERR_UNSUPPORTED, "destination layout is a descriptor of another process's host memory: not addressable from this process");
-    int rc = check_compat(*S, *D[d], o.cast_mode);
-    if (rc) return rc;
-    if (n && (!src_ids || !dst_ids || !src_ids[d] || !dst_ids[d])) return fail(KVBM_ERR, "null block id list");
-    rc = validate_block_transfer(src_ids[d], n, dst_ids[d], n, S->cfg.num_blocks, D[d]->cfg.num_blocks, src_h == dst_h[d]);
-    if (rc) return rc;
-  }
-  size_t lb = 0, le = S->cfg.num_layers;
-  if (o.has_layer_range) {
-    lb = o.layer_begin;
-    le = o.layer_end;
-    if (lb > le || le > S->cfg.num_layers)
-      return fail(KVBM_ERR_RANGE, "Layer range " + std::to_string(lb) + ".." + std::to_string(le) + " exceeds num_layers " + std::to_string(S->cfg.num_layers));
-  }
-  if (n == 0 || lb == le) return KVBM_OK;
-
-  // select_strategy (strategy.rs:78-108): every layout handled here is local or peer-mapped
-  kvbm_transfer_plan plan{};
-  for (int d = 0; d < nd; ++d) {
-    kvbm_transfer_plan p{};
-    int rc = select_direct_strategy(S->storage, D[d]->storage, nullptr, &p);
-    if (rc) return rc;
-    if (d && (p.first != plan.first || p.two_hop != plan.two_hop)) return fail(KVBM_ERR_UNSUPPORTED, "destinations need different strategies");
-    plan = p;
-  }
-  if (plan.two_hop) return fail(KVBM_ERR_UNSUPPORTED, "two-hop (disk) plans are outside this library");
-
-  if (plan.first == KVBM_STRATEGY_MEMCPY) {
-    if (o.cast_mode != KVBM_CAST_NONE) return fail(KVBM_ERR_UNSUPPORTED, "the fused cast exists only on the CUDA strategies");
-    for (int d = 0; d < nd; ++d) {
-      int rc = host_memcpy_transfer(*S, *D[d], src_ids[d], dst_ids[d], n, o.has_layer_range != 0, lb, le);
-      if (rc) return rc;
-      m->bytes_moved += n * (le - lb) * S->cfg.outer_dim * D[d]->region;
-    }
-    return KVBM_OK;  // synchronous: TransferCompleteNotification::completed() (memcpy.rs:91-92)
-  }
-  if (plan.first != KVBM_STRATEGY_CUDA_ASYNC_H2D && plan.first != KVBM_STRATEGY_CUDA_ASYNC_D2H && plan.first != KVBM_STRATEGY_CUDA_ASYNC_D2D)
-    return fail(KVBM_ERR_UNSUPPORTED, "NIXL strategies are outside this library (the NVLink peer path replaces them)");
-  if (m->device < 0) return fail(KVBM_ERR_CUDA, "this TransferManager was created without a CUDA device; CUDA strategies have no CPU fallback");
-
-  DeviceGuard g(m->device);
-  // stream: caller's, or round-robin from the pool (cuda.rs:82-90: D2H pool for D2H, H2D pool otherwise)
-  cudaStream_t stream;
-  if (o.use_caller_stream)
-    stream = o.cuda_stream;
-  else if (plan.first == KVBM_STRATEGY_CUDA_ASYNC_D2H)
-    stream = m->d2h[m->rr_d2h++ % kStreams];
-  else
-    stream = m->h2d[m->rr_h2d++ % kStreams];
-
   // block tables: narrow to int32 into pinned staging, async upload on the transfer's stream (no host sync;
   // the reference blocks on pointers_transfered_event.synchronize(), cuda.rs:324)
   const size_t lists = replicate ? static_cast<size_t>(nd) + 1 : 2 * static_cast<size_t>(nd);
@@ -553,6 +496,7 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
   uint64_t seq;
   int rc = acquire_slot(m, lists * n, S->cfg.num_layers + 4, &sl, &seq);
   if (rc) return rc;
+  if (wait_ev) CU(cudaStreamWaitEvent(stream, wait_ev, 0));
   auto narrow = [&](const size_t* ids, int32_t* dstp) { for (size_t i = 0; i < n; ++i) dstp[i] = static_cast<int32_t>(ids[i]); };
   std::vector<const int32_t*> dev_src(nd), dev_dst(nd);
   size_t k = 0;
@@ -589,6 +533,7 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
   ko.sync_workspace = sl->dev_ws;
   ko.max_ctas = o.max_ctas;
   ko.gate_timeout_ms = o.gate_timeout_ms;
+  ko.gate_mode = o.gate_mode;
   ko.multicast = o.multicast;
   ko.completion_flag = sl->host_flag;
   ko.completion_value = static_cast<uint32_t>(seq);
@@ -597,6 +542,160 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
   CU(cudaEventRecord(sl->ev, stream));
   sl->in_flight = true;
   for (int d = 0; d < nd; ++d) m->bytes_moved += n * (le - lb) * S->cfg.outer_dim * D[d]->region;
+  *slot_out = sl;
+  *seq_out = seq;
+  return KVBM_OK;
+}
+
+static bool cuda_strategy(int s) { return s == KVBM_STRATEGY_CUDA_ASYNC_H2D || s == KVBM_STRATEGY_CUDA_ASYNC_D2H || s == KVBM_STRATEGY_CUDA_ASYNC_D2D; }
+
+// execute_two_hop_transfer (executor/mod.rs:477-571) with handle_buffered_transfer's two bounce groups (:357-416): the
+// bounce blocks are split in two halves; chunk i goes src -> half (i & 1) -> dst.  The reference runs two tokio tasks
+// that each await their hops; here both hops are stream work ordered by events, so chunk i+1's first hop overlaps chunk
+// i's second hop and the host never blocks.  One bounce block = strictly sequential, like the reference (:526-548).
+static int execute_two_hop(kvbm_transfer_manager* m, Layout* S, Layout* D, Layout* B, const size_t* src_ids, const size_t* dst_ids,
+                           size_t n, const size_t* bounce_ids, size_t nb, size_t lb, size_t le, const kvbm_transfer_plan& plan,
+                           const kvbm_transfer_options& o, kvbm_notification* out)
+{
+  auto pick = [&](int strategy) { return strategy == KVBM_STRATEGY_CUDA_ASYNC_D2H ? m->d2h[m->rr_d2h++ % kStreams] : m->h2d[m->rr_h2d++ % kStreams]; };
+  cudaStream_t s1 = pick(plan.first), s2 = pick(plan.second);
+  nb = std::min(nb, n);
+  const size_t half = nb >= 2 ? nb / 2 : nb;
+  const size_t group_begin[2] = {0, half};
+  const size_t group_len[2] = {half, nb >= 2 ? nb - half : 0};
+  const int groups = nb >= 2 ? 2 : 1;
+  cudaEvent_t hop2_done[2] = {nullptr, nullptr};
+  kvbm_transfer_options o1 = o, o2 = o;
+  o1.done_flag = nullptr;        // completion signals belong to the hop that lands the bytes at the destination
+  o1.layer_done_flags = nullptr;
+  o2.layer_ready_flags = nullptr;  // ... and gating to the hop that reads the source
+  uint64_t last = 0;
+  size_t pos = 0;
+  for (int c = 0; pos < n; ++c) {
+    const int g = c % groups;
+    const size_t cnt = std::min(group_len[g], n - pos);
+    const size_t* bids = bounce_ids + group_begin[g];
+    const size_t* sp = src_ids + pos;
+    const size_t* dp = dst_ids + pos;
+    Slot *a, *b;
+    uint64_t sa, sb;
+    Layout* Bp = B;
+    int rc = launch_cuda(m, S, &Bp, 1, &sp, &bids, cnt, true, lb, le, o1, s1, hop2_done[g], &a, &sa);
+    if (rc) return rc;
+    Layout* Dp = D;
+    kvbm_transfer_options o2c = o2;
+    if (pos + cnt < n) o2c.done_flag = nullptr;  // only the last chunk announces the whole transfer
+    rc = launch_cuda(m, B, &Dp, 1, &bids, &dp, cnt, true, lb, le, o2c, s2, a->ev, &b, &sb);
+    if (rc) return rc;
+    hop2_done[g] = b->ev;
+    last = sb;
+    pos += cnt;
+  }
+  if (out) *out = last;
+  return KVBM_OK;
+}
+
+static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, const kvbm_layout_handle* dst_h,
+                   const size_t* const* src_ids, const size_t* const* dst_ids, size_t n, bool replicate,
+                   const kvbm_transfer_options* opts_in, kvbm_notification* out)
+{
+  kvbm_transfer_options o{};
+  if (opts_in) o = *opts_in;
+  if (out) *out = 0;
+  if (nd < 1 || nd > KVBM_MAX_DESTINATIONS) return fail(KVBM_ERR, "number of destinations must be in 1..=8");
+  std::lock_guard<std::mutex> lk(m->mu);
+  Layout* S = m->find(src_h);
+  if (!S) return fail(KVBM_ERR_HANDLE, "invalid source handle");
+  if (S->unmapped) return fail(KVBM_ERR_UNSUPPORTED, "source layout is a descriptor of another process's host memory: not addressable from this process");
+  // transfer/mod.rs:128-147: the KV block layout overrides exist in the options, but any pair that would need a
+  // transformation is rejected (select_transform_kernel is dead code in the reference, executor/mod.rs:46-100)
+  if (o.src_kv_layout != o.dst_kv_layout && o.src_kv_layout != 0 && o.dst_kv_layout != 0)
+    return fail(KVBM_ERR_UNSUPPORTED, "Layout transformation not supported: source and destination KV block layouts differ");
+  std::vector<Layout*> D(nd);
+  for (int d = 0; d < nd; ++d) {
+    D[d] = m->find(dst_h[d]);
+    if (!D[d]) return fail(KVBM_ERR_HANDLE, "invalid destination handle");
+    if (D[d]->unmapped) return fail(KVBM_ERR_UNSUPPORTED, "destination layout is a descriptor of another process's host memory: not addressable from this process");
+    int rc = check_compat(*S, *D[d], o.cast_mode);
+    if (rc) return rc;
+    if (n && (!src_ids || !dst_ids || !src_ids[d] || !dst_ids[d])) return fail(KVBM_ERR, "null block id list");
+    rc = validate_block_transfer(src_ids[d], n, dst_ids[d], n, S->cfg.num_blocks, D[d]->cfg.num_blocks, src_h == dst_h[d]);
+    if (rc) return rc;
+  }
+  size_t lb = 0, le = S->cfg.num_layers;
+  if (o.has_layer_range) {
+    lb = o.layer_begin;
+    le = o.layer_end;
+    if (lb > le || le > S->cfg.num_layers)
+      return fail(KVBM_ERR_RANGE, "Layer range " + std::to_string(lb) + ".." + std::to_string(le) + " exceeds num_layers " + std::to_string(S->cfg.num_layers));
+  }
+  if (n == 0 || lb == le) return KVBM_OK;
+
+  // select_strategy (strategy.rs:78-108): every layout handled here is local or peer-mapped
+  kvbm_transfer_plan plan{};
+  for (int d = 0; d < nd; ++d) {
+    kvbm_transfer_plan p{};
+    int rc = select_direct_strategy(S->storage, D[d]->storage, &m->caps, &p);
+    if (rc) return rc;
+    // strategy.rs:222-233,245-278: a device pool of ANOTHER GPU is "remote"; without GPU RDMA it is reached through
+    // pinned host memory: TwoHop { CudaAsyncD2H, Pinned, CudaAsyncH2D }
+    if (!p.two_hop && p.first == KVBM_STRATEGY_CUDA_ASYNC_D2D && !m->caps.allow_gpu_rdma &&
+        (S->device_id != D[d]->device_id || S->remote != D[d]->remote))
+      p = kvbm_transfer_plan{1, KVBM_STRATEGY_CUDA_ASYNC_D2H, KVBM_STORAGE_PINNED, KVBM_STRATEGY_CUDA_ASYNC_H2D};
+    if (d && (p.first != plan.first || p.two_hop != plan.two_hop)) return fail(KVBM_ERR_UNSUPPORTED, "destinations need different strategies");
+    plan = p;
+  }
+  if (plan.two_hop) {
+    if (!cuda_strategy(plan.first) || !cuda_strategy(plan.second))
+      return fail(KVBM_ERR_UNSUPPORTED, "two-hop plans with a NIXL (disk / remote agent) leg are outside this library");
+    if (m->device < 0) return fail(KVBM_ERR_CUDA, "this TransferManager was created without a CUDA device; CUDA strategies have no CPU fallback");
+    if (nd != 1) return fail(KVBM_ERR_UNSUPPORTED, "two-hop transfers take one destination");
+    if (o.use_caller_stream) return fail(KVBM_ERR_UNSUPPORTED, "Two-hop transfers don't support caller-provided streams");  // executor/mod.rs:441
+    if (o.cast_mode != KVBM_CAST_NONE) return fail(KVBM_ERR_UNSUPPORTED, "the fused cast is not available on two-hop transfers");
+    if (!o.bounce_layout || !o.bounce_block_ids || o.num_bounce_blocks == 0)
+      return fail(KVBM_ERR, "Two-hop transfers require a bounce buffer.");  // executor/mod.rs:514-519
+    Layout* B = m->find(o.bounce_layout);
+    if (!B) return fail(KVBM_ERR_HANDLE, "invalid bounce buffer handle");
+    if (B->storage != plan.bounce_location) return fail(KVBM_ERR, "Bounce buffer layout does not match bounce location.");  // :521-527
+    int rc = check_compat(*S, *B, KVBM_CAST_NONE);
+    if (rc) return rc;
+    if ((rc = check_compat(*B, *D[0], KVBM_CAST_NONE))) return rc;
+    std::unordered_set<size_t> seen;
+    for (size_t i = 0; i < o.num_bounce_blocks; ++i) {
+      if (o.bounce_block_ids[i] >= B->cfg.num_blocks) return fail(KVBM_ERR_RANGE, "bounce block id out of range");
+      if (!seen.insert(o.bounce_block_ids[i]).second) return fail(KVBM_ERR_DUPLICATE_DST, "duplicate bounce block id");
+    }
+    DeviceGuard g(m->device);
+    return execute_two_hop(m, S, D[0], B, src_ids[0], dst_ids[0], n, o.bounce_block_ids, o.num_bounce_blocks, lb, le, plan, o, out);
+  }
+
+  if (plan.first == KVBM_STRATEGY_MEMCPY) {
+    if (o.cast_mode != KVBM_CAST_NONE) return fail(KVBM_ERR_UNSUPPORTED, "the fused cast exists only on the CUDA strategies");
+    if (o.use_caller_stream) return fail(KVBM_ERR_UNSUPPORTED, "cuda_stream option is not supported for Memcpy strategy");  // executor/mod.rs:272-276
+    for (int d = 0; d < nd; ++d) {
+      int rc = host_memcpy_transfer(*S, *D[d], src_ids[d], dst_ids[d], n, o.has_layer_range != 0, lb, le);
+      if (rc) return rc;
+      m->bytes_moved += n * (le - lb) * S->cfg.outer_dim * D[d]->region;
+    }
+    return KVBM_OK;  // synchronous: TransferCompleteNotification::completed() (memcpy.rs:91-92)
+  }
+  if (!cuda_strategy(plan.first))
+    return fail(KVBM_ERR_UNSUPPORTED, "NIXL strategies are outside this library (the NVLink peer path replaces them)");
+  if (m->device < 0) return fail(KVBM_ERR_CUDA, "this TransferManager was created without a CUDA device; CUDA strategies have no CPU fallback");
+
+  DeviceGuard g(m->device);
+  // stream: caller's, or round-robin from the pool (cuda.rs:82-90: D2H pool for D2H, H2D pool otherwise)
+  cudaStream_t stream;
+  if (o.use_caller_stream)
+    stream = o.cuda_stream;
+  else if (plan.first == KVBM_STRATEGY_CUDA_ASYNC_D2H)
+    stream = m->d2h[m->rr_d2h++ % kStreams];
+  else
+    stream = m->h2d[m->rr_h2d++ % kStreams];
+  Slot* sl;
+  uint64_t seq;
+  int rc = launch_cuda(m, S, D.data(), nd, src_ids, dst_ids, n, replicate, lb, le, o, stream, nullptr, &sl, &seq);
+  if (rc) return rc;
   // caller-provided stream: caller manages sync, completed() is returned (cuda.rs:139-141)
   if (out) *out = o.use_caller_stream ? 0 : seq;
   return KVBM_OK;
@@ -916,6 +1015,14 @@ extern "C" int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void
   L.remote = !same_process;
   L.unmapped = unmapped;
   return finish_register(m, std::move(L), static_cast<int>(hd.storage), hd.device_id, out);
+}
+
+extern "C" int kvbm_manager_set_capabilities(kvbm_transfer_manager* m, const kvbm_transfer_capabilities* caps)
+{
+  if (!m || !caps) return fail(KVBM_ERR, "null argument");
+  std::lock_guard<std::mutex> lk(m->mu);
+  m->caps = *caps;
+  return KVBM_OK;
 }
 
 extern "C" int kvbm_manager_execute_transfer(kvbm_transfer_manager* m, kvbm_layout_handle src, const size_t* src_ids, kvbm_layout_handle dst,

@@ -721,10 +721,10 @@ kvbm_kernels_is_stub_build(void)
 // =================================================================================================
 // C ABI -- Part 2 (v2 extensions)
 // =================================================================================================
-extern "C" cudaError_t
-kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* dsts, int num_dsts, int num_blocks,
-                           int layer_begin, int layer_end, int cast_mode, const kvbm_paged_copy_opts* opts,
-                           cudaStream_t stream)
+static cudaError_t
+paged_copy_impl(const kvbm_paged_layout* src, const kvbm_paged_dst* dsts, int num_dsts, int num_blocks,
+                int layer_begin, int layer_end, int cast_mode, const kvbm_paged_copy_opts* opts,
+                cudaStream_t stream)
 {
   if (num_blocks == 0 || num_dsts == 0 || layer_end == layer_begin) return cudaSuccess;
   if (!src || !dsts) return cudaErrorInvalidValue;
@@ -834,6 +834,67 @@ kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* d
     case KVBM_CAST_FP8E4M3_TO_BF16: return launch(kvbm_paged_copy_kernel<KVBM_CAST_FP8E4M3_TO_BF16>);
     default: return launch(kvbm_paged_copy_kernel<KVBM_CAST_BF16_TO_FP8E4M3>);
   }
+}
+
+// CUDA loads modules lazily by default, and the first launch of a not-yet-loaded kernel (of ANY module in the process)
+// can wait for the device to drain -- which never happens while a gated transfer spins on ready flags that the stalled
+// launch was supposed to release.  This library preloads its own kernels, but it cannot load the engine's.  So a
+// spinning gate is only used when the process runs with eager loading (or the caller insists); otherwise the gate
+// moves to the stream front-end: one cuStreamWaitValue32 + one single-layer launch per layer -- nothing resident spins.
+static bool eager_module_loading()
+{
+  static const int mode = [] {
+    typedef int (*fn_t)(int*);
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult r;
+    int m = 0;
+    if (cudaGetDriverEntryPoint("cuModuleGetLoadingMode", &f, cudaEnableDefault, &r) == cudaSuccess && f &&
+        reinterpret_cast<fn_t>(f)(&m) == 0)
+      return m;
+    (void)cudaGetLastError();
+    return 0;
+  }();
+  return mode == 1;  // CU_MODULE_EAGER_LOADING
+}
+
+extern "C" int
+kvbm_kernels_gate_would_spin(void)
+{
+  return eager_module_loading() ? 1 : 0;
+}
+
+extern "C" cudaError_t
+kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_paged_dst* dsts, int num_dsts, int num_blocks,
+                           int layer_begin, int layer_end, int cast_mode, const kvbm_paged_copy_opts* opts,
+                           cudaStream_t stream)
+{
+  const bool gated = opts && opts->layer_ready_flags != nullptr;
+  if (!gated || num_blocks == 0 || num_dsts == 0 || layer_end <= layer_begin || !dsts || num_dsts < 0 || num_dsts > KVBM_MAX_DESTINATIONS)
+    return paged_copy_impl(src, dsts, num_dsts, num_blocks, layer_begin, layer_end, cast_mode, opts, stream);
+  const int mode = opts->gate_mode;
+  if (mode < KVBM_GATE_AUTO || mode > KVBM_GATE_STREAM_WAIT) return cudaErrorInvalidValue;
+  if (mode == KVBM_GATE_SPIN || (mode == KVBM_GATE_AUTO && eager_module_loading()))
+    return paged_copy_impl(src, dsts, num_dsts, num_blocks, layer_begin, layer_end, cast_mode, opts, stream);
+  DeviceInfo di;
+  cudaError_t e = device_info(&di);
+  if (e != cudaSuccess) return e;
+  if (!stream_memops()) return mode == KVBM_GATE_AUTO ? paged_copy_impl(src, dsts, num_dsts, num_blocks, layer_begin, layer_end, cast_mode, opts, stream)
+                                                       : cudaErrorNotSupported;
+  kvbm_paged_copy_opts o = *opts;
+  o.layer_ready_flags = nullptr;
+  kvbm_paged_dst dd[KVBM_MAX_DESTINATIONS];
+  for (int l = layer_begin; l < layer_end; ++l) {
+    const bool last = l + 1 == layer_end;
+    // CU_STREAM_WAIT_VALUE_GEQ: the stream front-end polls the word, no SM is occupied
+    if (g_wait32(stream, reinterpret_cast<unsigned long long>(opts->layer_ready_flags + l), opts->epoch, 0) != 0) return cudaErrorUnknown;
+    for (int d = 0; d < num_dsts; ++d) {
+      dd[d] = dsts[d];
+      if (!last) dd[d].done_flag = nullptr;
+    }
+    o.completion_flag = last ? opts->completion_flag : nullptr;
+    if ((e = paged_copy_impl(src, dd, num_dsts, num_blocks, l, l + 1, cast_mode, &o, stream)) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 extern "C" cudaError_t

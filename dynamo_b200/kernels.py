@@ -101,6 +101,7 @@ class PagedCopyOpts(C.Structure):
         ("variant", C.c_int),
         ("gate_timeout_ms", C.c_int),
         ("multicast", C.c_int),
+        ("gate_mode", C.c_int),
         ("static_schedule", C.c_int),
     ]
 
@@ -147,8 +148,15 @@ EXPORTED_SYMBOLS = [
     "kvbm_kernels_launch_universal_from_block", "kvbm_kernels_launch_block_from_universal",
     "kvbm_kernels_has_memcpy_batch_async", "kvbm_kernels_is_stub_build",
     "kvbm_kernels_paged_copy_v2", "kvbm_kernels_set_flags", "kvbm_kernels_wait_flag", "kvbm_kernels_stream_wait_event",
-    "kvbm_kernels_launch_count", "kvbm_kernels_build_info",
+    "kvbm_kernels_launch_count", "kvbm_kernels_build_info", "kvbm_kernels_gate_would_spin",
 ]
+
+GATE_AUTO, GATE_SPIN, GATE_STREAM_WAIT = 0, 1, 2
+
+
+def gate_would_spin() -> bool:
+    """True when gated transfers spin in ONE launch (eager CUDA module loading); False when they gate on the stream."""
+    return bool(lib().kvbm_kernels_gate_would_spin())
 
 
 def is_memcpy_batch_available() -> bool:

@@ -97,6 +97,12 @@ class _COptions(C.Structure):
         ("gate_timeout_ms", C.c_int),
         ("multicast", C.c_int),
         ("done_flag", C.c_void_p),
+        ("bounce_layout", C.c_uint64),
+        ("bounce_block_ids", C.c_void_p),
+        ("num_bounce_blocks", C.c_size_t),
+        ("src_kv_layout", C.c_int),
+        ("dst_kv_layout", C.c_int),
+        ("gate_mode", C.c_int),
     ]
 
 
@@ -141,6 +147,10 @@ class TransferOptions:
     gate_timeout_ms: int = 0
     multicast: int = 0                    # destination layout lives in a MulticastGroup.map() range (NVLS)
     done_flag: int = 0                    # word on the destination GPU that receives `epoch` on completion (cf. nixl_write_notification)
+    bounce_buffer: Optional[tuple] = None # (layout handle, block ids): BounceBuffer of options.rs:45-51 for two-hop transfers
+    src_kv_layout: int = 0                # KvBlockLayout overrides (options.rs:63-80); a pair needing a transform is rejected
+    dst_kv_layout: int = 0
+    gate_mode: int = 0                    # kernels.GATE_AUTO / GATE_SPIN / GATE_STREAM_WAIT
 
     @staticmethod
     def from_layer_range(layer_range: Optional[range]) -> "TransferOptions":
@@ -148,10 +158,16 @@ class TransferOptions:
 
     def _c(self) -> _COptions:
         lr = self.layer_range
+        bl, bids, nb = 0, None, 0
+        if self.bounce_buffer is not None:
+            bl, ids = self.bounce_buffer
+            self._bounce_keepalive = (C.c_size_t * max(1, len(ids)))(*[int(x) for x in ids])
+            bids, nb = C.cast(self._bounce_keepalive, C.c_void_p), len(ids)
         return _COptions(int(lr is not None), lr.start if lr is not None else 0, lr.stop if lr is not None else 0,
                          self.cuda_stream or 0, int(self.cuda_stream is not None), int(self.cast_mode), self.max_ctas,
                          self.layer_ready_flags, self.layer_done_flags, self.epoch, self.gate_timeout_ms,
-                         int(self.multicast), self.done_flag)
+                         int(self.multicast), self.done_flag, int(bl), bids, nb, int(self.src_kv_layout),
+                         int(self.dst_kv_layout), int(self.gate_mode))
 
 
 @dataclass
@@ -171,7 +187,7 @@ EXPORTED_SYMBOLS = [
     "kvbm_layout_memory_region", "kvbm_layout_is_fully_contiguous", "kvbm_manager_enable_peer_access",
     "kvbm_manager_export_metadata", "kvbm_manager_import_metadata", "kvbm_manager_execute_transfer",
     "kvbm_manager_execute_fanout", "kvbm_notification_is_complete", "kvbm_notification_wait",
-    "kvbm_manager_bytes_moved", "kvbm_manager_h2d_bytes",
+    "kvbm_manager_bytes_moved", "kvbm_manager_h2d_bytes", "kvbm_manager_set_capabilities",
     "kvbm_manager_export_serialized_layout", "kvbm_manager_import_serialized_layout", "kvbm_layout_descriptor_json",
     "kvbm_manager_import_descriptor_json",
     "kvbm_mc_supported", "kvbm_mc_group_create", "kvbm_mc_group_export_fd", "kvbm_mc_group_import_fd",
@@ -214,6 +230,7 @@ def lib() -> C.CDLL:
         # the id lists are `const size_t*`; declared void* so a raw address (numpy buffer) passes without a ctypes cast
         L.kvbm_manager_execute_transfer.argtypes = [vp, u64, vp, u64, vp, sz, P(_COptions), P(u64)]
         L.kvbm_manager_execute_fanout.argtypes = [vp, u64, i, P(u64), P(P(sz)), P(P(sz)), sz, i, P(_COptions), P(u64)]
+        L.kvbm_manager_set_capabilities.argtypes = [vp, P(_CCaps)]
         L.kvbm_notification_is_complete.argtypes = [vp, u64]
         L.kvbm_notification_wait.argtypes = [vp, u64, C.c_int64]
         L.kvbm_manager_bytes_moved.argtypes = [vp]
@@ -455,6 +472,12 @@ class TransferManager:
         ids on every rank -- here one replicate launch over peer mappings instead of grouped ncclBcast."""
         return self.execute_fanout(src, dsts, [src_block_ids] * len(dsts), [dst_block_ids] * len(dsts), replicate=True,
                                    options=TransferOptions(layer_range=layer_range))
+
+    def set_capabilities(self, allow_gds: bool = False, allow_gpu_rdma: bool = True) -> None:
+        """TransferCapabilities (strategy.rs:245-278); allow_gpu_rdma=False turns cross-GPU transfers into the reference's
+        TwoHop plan through `TransferOptions.bounce_buffer`."""
+        caps = _CCaps(int(allow_gds), int(allow_gpu_rdma))
+        _check(lib().kvbm_manager_set_capabilities(self._h, C.byref(caps)))
 
     def bytes_moved(self) -> int:
         return lib().kvbm_manager_bytes_moved(self._h)

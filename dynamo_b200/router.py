@@ -208,3 +208,68 @@ def prefix_hit_block_table(tree: RadixTree, worker: Tuple[int, int], request_blo
     scores = tree.find_matches(request_block_hashes, False).scores
     matched = min(scores.get(worker, 0), len(src_block_ids))
     return list(src_block_ids[matched:]), list(dst_block_ids[matched:]), matched
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# KV event publisher: the reference's C ABI (lib/bindings/c/src/lib.rs:112-116,328-391) through ctypes
+# ------------------------------------------------------------------------------------------------------------------
+_EVENT_CB = C.CFUNCTYPE(None, C.c_char_p, C.c_size_t, C.c_void_p)
+_ev_cfg = False
+
+
+def _ev_lib() -> C.CDLL:
+    global _ev_cfg
+    L = lib()
+    if not _ev_cfg:
+        u64, u32, sz, vp = C.c_uint64, C.c_uint32, C.c_size_t, C.c_void_p
+        P = C.POINTER
+        L.dynamo_llm_init.argtypes = [C.c_char_p, C.c_char_p, u32]
+        L.dynamo_llm_init.restype = u32
+        L.dynamo_llm_shutdown.restype = u32
+        L.dynamo_llm_load_publisher_create.restype = u32
+        L.dynamo_kv_event_publish_stored.argtypes = [u64, P(u32), P(sz), P(u64), sz, P(u64), C.c_char_p]
+        L.dynamo_kv_event_publish_stored.restype = u32
+        L.dynamo_kv_event_publish_removed.argtypes = [u64, P(u64), sz]
+        L.dynamo_kv_event_publish_removed.restype = u32
+        L.dynamo_kv_event_set_worker_id.argtypes = [u64]
+        L.dynamo_kv_event_attach_tree.argtypes = [vp]
+        L.dynamo_kv_event_subscribe.argtypes = [_EVENT_CB, vp]
+        L.dynamo_kv_event_published_count.restype = u64
+        _ev_cfg = True
+    return L
+
+
+class KvEventPublisher:
+    """`dynamo_llm_init` + `dynamo_kv_event_publish_stored/removed` as an engine's C++ executor thread calls them.
+    One per process (the reference keeps the publisher in a process-wide OnceCell).  Events reach the attached RadixTree
+    (in-process indexer) and `on_event(json_bytes)`; in Dynamo they ride the runtime's "kv-events" subject."""
+
+    def __init__(self, namespace: str, component: Optional[str], kv_block_size: int, worker_id: int = 0,
+                 tree: Optional[RadixTree] = None, on_event=None):
+        L = _ev_lib()
+        if L.dynamo_llm_init(namespace.encode(), component.encode() if component else None, kv_block_size) != 0:
+            raise RuntimeError("dynamo_llm_init failed")
+        L.dynamo_kv_event_set_worker_id(worker_id)
+        self._tree = tree
+        L.dynamo_kv_event_attach_tree(tree._h if tree is not None else None)
+        self._cb = _EVENT_CB(lambda p, n, _u: on_event(C.string_at(p, n))) if on_event is not None else _EVENT_CB(0)
+        L.dynamo_kv_event_subscribe(self._cb, None)
+        self.kv_block_size = kv_block_size
+
+    def publish_stored(self, event_id: int, token_ids: Sequence[int], num_block_tokens: Sequence[int], block_ids: Sequence[int],
+                       parent_hash: Optional[int] = None, lora_name: Optional[str] = None) -> bool:
+        toks = (C.c_uint32 * max(1, len(token_ids)))(*[int(t) for t in token_ids])
+        nbt = (C.c_size_t * max(1, len(num_block_tokens)))(*[int(x) for x in num_block_tokens])
+        ph = C.byref(C.c_uint64(parent_hash & 0xFFFFFFFFFFFFFFFF)) if parent_hash is not None else None
+        return _ev_lib().dynamo_kv_event_publish_stored(event_id, toks, nbt, _u64s(block_ids), len(block_ids), ph,
+                                                        lora_name.encode() if lora_name else None) == 0
+
+    def publish_removed(self, event_id: int, block_ids: Sequence[int]) -> bool:
+        return _ev_lib().dynamo_kv_event_publish_removed(event_id, _u64s(block_ids), len(block_ids)) == 0
+
+    @staticmethod
+    def published_count() -> int:
+        return int(_ev_lib().dynamo_kv_event_published_count())
+
+    def shutdown(self) -> None:
+        _ev_lib().dynamo_llm_shutdown()

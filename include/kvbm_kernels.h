@@ -112,6 +112,8 @@ typedef struct kvbm_paged_dst {
   uint32_t* layer_done_flags;    /* nullable; [num_layers]; entry l set to `epoch` when layer l landed */
 } kvbm_paged_dst;
 
+enum { KVBM_GATE_AUTO = 0, KVBM_GATE_SPIN = 1, KVBM_GATE_STREAM_WAIT = 2 };
+
 enum {
   KVBM_CAST_NONE = 0,
   KVBM_CAST_FP8E4M3_TO_BF16 = 1, /* exact; NaN codes -> 0x7fc0 */
@@ -147,6 +149,12 @@ typedef struct kvbm_paged_copy_opts {
                                      device bound to the object; dsts[1..] contribute only their done / layer_done flags.  This is
                                      the replacement of the grouped ncclBcast (kvbm-engine collectives/nccl.rs:421-462): egress of
                                      the source GPU is 1x the payload instead of Nx.  Requires cast_mode NONE, 16-byte strides. */
+  int gate_mode;                  /* how layer_ready_flags are waited for: KVBM_GATE_AUTO (0) = warps of the ONE launch spin on
+                                     the flags when the process loads CUDA modules eagerly (CUDA_MODULE_LOADING=EAGER), else
+                                     the wait moves to the stream (cuStreamWaitValue32 + a single-layer launch per layer) so
+                                     that nothing resident spins while some other kernel of the process is still being loaded
+                                     lazily -- see kvbm_kernels_gate_would_spin(); KVBM_GATE_SPIN (1) / KVBM_GATE_STREAM_WAIT
+                                     (2) force either behaviour.  gate_timeout_ms applies to the spinning form only. */
   int static_schedule;            /* diagnostics: 1 = split the tiles round-robin over the rings instead of the dynamic
                                      (ticket) tile scheduler */
 } kvbm_paged_copy_opts;
@@ -160,6 +168,10 @@ cudaError_t kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_
                                        int num_dsts, int num_blocks, int layer_begin,
                                        int layer_end, int cast_mode,
                                        const kvbm_paged_copy_opts* opts, cudaStream_t stream);
+
+/* 1 when KVBM_GATE_AUTO would let the transfer's warps spin on the ready flags (eager module loading detected through
+ * cuModuleGetLoadingMode), 0 when it would gate on the stream instead. */
+int kvbm_kernels_gate_would_spin(void);
 
 /* Small helpers so hosts without a CUDA binding (ctypes, cgo, JNI) can drive the flags. */
 cudaError_t kvbm_kernels_set_flags(uint32_t* flags, int first, int count, uint32_t value,

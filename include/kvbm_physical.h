@@ -107,6 +107,13 @@ typedef struct kvbm_transfer_options {
   uint32_t* done_flag;               /* nullable: word in the DESTINATION GPU's memory that receives `epoch` once every byte of
                                         the transfer has landed -- the role of TransferOptions::nixl_write_notification
                                         (options.rs:36-43: "delivered to the remote node after the RDMA write completes") */
+  /* BounceBuffer (options.rs:45-51): a registered layout + the blocks of it a two-hop transfer may stage through */
+  uint64_t bounce_layout;            /* kvbm_layout_handle; 0 = none */
+  const size_t* bounce_block_ids;
+  size_t num_bounce_blocks;
+  int src_kv_layout, dst_kv_layout;  /* KvBlockLayout overrides (options.rs:63-80): 0 = the layout's own; a pair that would
+                                        need a transformation is rejected exactly as transfer/mod.rs:128-147 does */
+  int gate_mode;                     /* see kvbm_paged_copy_opts.gate_mode */
 } kvbm_transfer_options;
 
 typedef struct kvbm_transfer_manager kvbm_transfer_manager;
@@ -171,6 +178,13 @@ int kvbm_manager_import_serialized_layout(kvbm_transfer_manager* m, const void* 
                                           size_t cap, size_t* n_out);
 int kvbm_layout_descriptor_json(kvbm_transfer_manager* m, kvbm_layout_handle h, char* buf, size_t cap, size_t* len);
 int kvbm_manager_import_descriptor_json(kvbm_transfer_manager* m, const char* json, size_t len, kvbm_layout_handle* out);
+
+/* TransferCapabilities (transfer/strategy.rs:245-278).  Default {allow_gds 0, allow_gpu_rdma 1}.  With allow_gpu_rdma = 0 a
+ * Device -> Device transfer between different GPUs follows the reference's TwoHop plan (strategy.rs:222-233):
+ * CudaAsyncD2H into the bounce buffer named in the options (Pinned), then CudaAsyncH2D into the destination; the bounce blocks
+ * are split into two groups and the hops of consecutive chunks overlap (executor/mod.rs:357-416,477-571).  Without a bounce
+ * buffer such a transfer fails with "Two-hop transfers require a bounce buffer." as in the reference. */
+int kvbm_manager_set_capabilities(kvbm_transfer_manager* m, const kvbm_transfer_capabilities* caps);
 
 /* execute_transfer (manager/mod.rs:227-303).  ids are host arrays, consumed before return. */
 int kvbm_manager_execute_transfer(kvbm_transfer_manager* m, kvbm_layout_handle src, const size_t* src_ids,

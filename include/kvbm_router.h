@@ -72,6 +72,30 @@ size_t kvr_tree_find_matches(kvr_radix_tree* t, const uint64_t* sequence, size_t
                              uint32_t* dp_ranks, uint32_t* scores, uint64_t* tree_sizes, size_t cap, uint64_t* frequencies,
                              size_t freq_cap, size_t* n_freq);
 
+/* ---- KV-cache event publisher: the reference's C ABI (lib/bindings/c/src/lib.rs:74-78,112-116,177-194,328-391) ----
+ * dynamo_llm_init creates the process-wide publisher (component NULL/"" -> "backend"; a second init keeps the first);
+ * publish_stored hashes each block's tokens (compute_block_hash_for_seq, optional LoRA name) and publishes ONE Stored event
+ * with the blocks whose num_block_tokens equal kv_block_size -- the first partial block ends the list, exactly as
+ * kv_event_create_stored_from_parts does; parent_hash NULL = None.  Publishing before init returns ERR (the reference
+ * unwraps).  Events are RouterEvent{worker_id, storage_tier: device, event: KvCacheEvent{.., dp_rank: 0}}
+ * (lib/kv-router/src/protocols.rs:473-520,695-735).  Dynamo sends them over its runtime's "kv-events" subject; this library
+ * owns no runtime, so the host registers the sinks: an in-process RadixTree (the events are applied as the indexer would)
+ * and/or a callback that receives each event as the JSON serde_json writes for RouterEvent. */
+enum { DYNAMO_LLM_OK = 0, DYNAMO_LLM_ERR = 1 };
+uint32_t dynamo_llm_init(const char* namespace_c_str, const char* component_c_str, uint32_t kv_block_size);
+uint32_t dynamo_llm_shutdown(void);
+uint32_t dynamo_llm_load_publisher_create(void);
+uint32_t dynamo_kv_event_publish_stored(uint64_t event_id, const uint32_t* token_ids, const size_t* num_block_tokens,
+                                        const uint64_t* block_ids, size_t num_blocks, const uint64_t* parent_hash,
+                                        const char* lora_name);
+uint32_t dynamo_kv_event_publish_removed(uint64_t event_id, const uint64_t* block_ids, size_t num_blocks);
+/* sinks / identity (extensions: in Dynamo the runtime provides them) */
+typedef void (*dynamo_kv_event_callback)(const char* router_event_json, size_t len, void* user);
+uint32_t dynamo_kv_event_set_worker_id(uint64_t worker_id);
+uint32_t dynamo_kv_event_attach_tree(kvr_radix_tree* tree);   /* NULL detaches */
+uint32_t dynamo_kv_event_subscribe(dynamo_kv_event_callback cb, void* user);
+uint64_t dynamo_kv_event_published_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -424,3 +424,91 @@ def test_c_program_drives_the_host_abi(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "host ABI ok" in r.stdout, r.stdout + r.stderr
+
+
+# ------------------------------------------------------------------ round-2 additions
+def test_router_library_exports_every_declared_symbol():
+    import re
+    from dynamo_b200 import router as R
+    syms = _exported(R.ROUTER_SO)
+    txt = open(os.path.join(ROOT, "include", "kvbm_router.h")).read()
+    declared = set(re.findall(r"\b((?:kvr|dynamo)_[a-z0-9_]+)\s*\(", txt)) - {"dynamo_kv_event_callback"}
+    assert {"dynamo_llm_init", "dynamo_kv_event_publish_stored", "dynamo_kv_event_publish_removed", "kvr_tree_find_matches"} <= declared
+    assert declared <= syms, declared - syms
+
+
+def _blob_with_identity(blob: bytes, identity: int) -> bytes:
+    """BlobHeader (transfer_manager.cpp): magic[8] version fully_contiguous block_dim storage device_id n_allocs (6 x u32)
+    worker_id pid (2 x u64) -> the process identity sits at byte offset 40."""
+    import struct
+    return blob[:40] + struct.pack("<Q", identity) + blob[48:]
+
+
+def test_remote_host_layout_without_mapping_is_descriptor_only(mgr):
+    """a System/Pinned layout exported by ANOTHER process has no IPC handle; its addresses mean nothing here.
+    It is importable as a descriptor (geometry + memory_region arithmetic) but every transfer touching it is refused."""
+    cfg = std_cfg(4)
+    buf = np.zeros(cfg.required_bytes(), dtype=np.uint8)
+    local = mgr.register_fully_contiguous(cfg, buf.ctypes.data, buf.size, StorageKind.System)
+    other = np.zeros(cfg.required_bytes(), dtype=np.uint8)
+    h_other = mgr.register_fully_contiguous(cfg, other.ctypes.data, other.size, StorageKind.System)
+    blob = mgr.export_metadata(h_other)
+    same = mgr.import_metadata(blob)                                   # same process: usable as before
+    mgr.execute_transfer(local, [0], same, [1])
+    import struct
+    me = struct.unpack("<Q", blob[40:48])[0]
+    assert me >> 32, "the process identity must carry a nonce above the pid (pid alone collides across PID namespaces)"
+    foreign = mgr.import_metadata(_blob_with_identity(blob, me ^ (0x5a5a << 32)))   # same pid, different process nonce
+    assert mgr.memory_region(foreign, 1, 0, 0)[1] == cfg.region_size()
+    for a, b in ((local, foreign), (foreign, local)):
+        with pytest.raises(KvbmError) as e:
+            mgr.execute_transfer(a, [0], b, [1])
+        assert e.value.code == ErrorCode.UNSUPPORTED and "not addressable" in e.value.msg
+
+
+def test_two_hop_plan_needs_a_bounce_buffer_and_kv_layout_overrides_are_rejected(mgr):
+    """executor/mod.rs:514-527 error texts; transfer/mod.rs:128-147 rejects pairs that would need a transformation."""
+    from dynamo_b200.physical import TransferOptions
+    cfg = std_cfg(4)
+    a = np.zeros(cfg.required_bytes(), dtype=np.uint8)
+    b = np.zeros(cfg.required_bytes(), dtype=np.uint8)
+    ha = mgr.register_fully_contiguous(cfg, a.ctypes.data, a.size, StorageKind.System)
+    hb = mgr.register_fully_contiguous(cfg, b.ctypes.data, b.size, StorageKind.System)
+    with pytest.raises(KvbmError) as e:
+        mgr.execute_transfer(ha, [0], hb, [1], TransferOptions(src_kv_layout=1, dst_kv_layout=2))
+    assert e.value.code == ErrorCode.UNSUPPORTED and "Layout transformation not supported" in e.value.msg
+    mgr.execute_transfer(ha, [0], hb, [1], TransferOptions(src_kv_layout=2, dst_kv_layout=2))   # same layout: plain copy
+    # Device<->System stay "not supported", exactly like strategy.rs:150-160 (there is no implicit staging)
+    dev_like = mgr.register_fully_contiguous(cfg, a.ctypes.data, a.size, StorageKind.Device)
+    with pytest.raises(KvbmError) as e:
+        mgr.execute_transfer(dev_like, [0], hb, [1])
+    assert e.value.code == ErrorCode.UNSUPPORTED and "Device to System" in e.value.msg
+    with pytest.raises(KvbmError) as e:
+        mgr.execute_transfer(hb, [0], dev_like, [1])
+    assert e.value.code == ErrorCode.UNSUPPORTED and "System to Device" in e.value.msg
+    # capabilities: with GPU RDMA disallowed a cross-GPU D2D becomes TwoHop{D2H, Pinned, H2D}; it needs a CUDA manager and a
+    # bounce buffer -- on this host-only manager the plan is selected and then fails loudly for the right reason
+    mgr.set_capabilities(allow_gpu_rdma=False)
+    try:
+        d0 = mgr.register_fully_contiguous(cfg, a.ctypes.data, a.size, StorageKind.Device, 0)
+        d1 = mgr.register_fully_contiguous(cfg, b.ctypes.data, b.size, StorageKind.Device, 1)
+        with pytest.raises(KvbmError) as e:
+            mgr.execute_transfer(d0, [0], d1, [1])
+        assert e.value.code == ErrorCode.CUDA and "no CPU fallback" in e.value.msg
+    finally:
+        mgr.set_capabilities(allow_gpu_rdma=True)
+
+
+def test_layout_ids_are_reused_and_never_overwrite_a_live_layout(mgr):
+    """next_layout_id is a u16; registering past 65535 must not clobber a live layout."""
+    cfg = std_cfg(2)
+    buf = np.zeros(cfg.required_bytes(), dtype=np.uint8)
+    keep = mgr.register_fully_contiguous(cfg, buf.ctypes.data, buf.size, StorageKind.System)
+    seen = set()
+    for _ in range(66000):                                              # wraps the 16-bit id space once
+        h = mgr.register_fully_contiguous(cfg, buf.ctypes.data, buf.size, StorageKind.System)
+        assert h != keep and h & 0xFFFF != 0
+        seen.add(h & 0xFFFF)
+        mgr.unregister(h)
+    assert len(seen) > 60000
+    assert mgr.memory_region(keep, 1, 0, 0)[1] == cfg.region_size()    # the early layout is still the same layout

@@ -237,3 +237,75 @@ def test_prefix_hit_block_table_feeds_the_transfer_path():
     assert matched == 12 and s == src_ids[12:] and d == dst_ids[12:]
     s, d, matched = R.prefix_hit_block_table(t, (6, 0), local, src_ids, dst_ids)
     assert matched == 0 and len(s) == 20
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# KV event publisher C ABI (lib/bindings/c/src/lib.rs:112-116,228-391)
+# ------------------------------------------------------------------------------------------------------------------
+def test_compute_block_hash_golden_constant():
+    """protocols.rs:937-951 (test_router_event_new): compute_block_hash(b"test data") == 13226331709069118873."""
+    assert R.compute_hash(b"test data") == 13226331709069118873
+    assert xxhash.xxh3_64_intdigest(b"test data", seed=1337) == 13226331709069118873
+
+
+def test_event_publish_before_init_is_an_error_and_shutdown_without_init_too():
+    L = R._ev_lib()
+    L.dynamo_llm_shutdown()                                         # whatever an earlier test left behind
+    assert L.dynamo_llm_shutdown() == 1                             # "Runtime not initialized" (lib.rs:177-190)
+    ids = (R.C.c_uint64 * 1)(7)
+    assert L.dynamo_kv_event_publish_removed(1, ids, 1) == 1        # the reference unwraps KV_PUB: no publisher, no publish
+    assert L.dynamo_llm_load_publisher_create() == 0                # lib.rs:192-194
+    assert L.dynamo_llm_init(None, b"backend", 4) == 1              # namespace must be a C string (lib.rs:149-155)
+
+
+def test_event_publish_stored_and_removed_feed_the_radix_tree_and_emit_router_event_json():
+    KB = 4
+    events = []
+    tree = R.RadixTree()
+    R._ev_lib().dynamo_llm_shutdown()
+    pub = R.KvEventPublisher("ns", None, KB, worker_id=42, tree=tree, on_event=events.append)
+    try:
+        tokens = list(range(100, 100 + 3 * KB))
+        want_hashes = R.compute_block_hash_for_seq(tokens, KB)
+        assert want_hashes == [xxhash.xxh3_64_intdigest(struct.pack("<4I", *tokens[i:i + KB]), seed=1337) for i in range(0, 12, KB)]
+        assert pub.publish_stored(1, tokens, [KB, KB, KB], [1000, 1001, 1002])
+        ev = json.loads(events[-1])
+        assert ev == {"worker_id": 42, "storage_tier": "device",
+                      "event": {"event_id": 1, "dp_rank": 0,
+                                "data": {"stored": {"parent_hash": None,
+                                                    "blocks": [{"block_hash": 1000 + i, "tokens_hash": want_hashes[i], "mm_extra_info": None}
+                                                               for i in range(3)]}}}}
+        assert tree.find_matches(want_hashes).scores == {(42, 0): 3} and tree.lookup_size(42) == 3
+        # the JSON is what RadixTree.apply_event (the serde shape of RouterEvent) accepts: a second indexer converges
+        twin = R.RadixTree()
+        twin.apply_event(events[-1])
+        assert twin.find_matches(want_hashes).scores == {(42, 0): 3}
+        # continuation under a parent + a partial block: the first block whose token count != kv_block_size ends the event
+        more = list(range(500, 500 + 2 * KB + 2))
+        assert pub.publish_stored(2, more, [KB, KB, 2], [1003, 1004, 1005], parent_hash=1002)
+        ev2 = json.loads(events[-1])["event"]["data"]["stored"]
+        assert ev2["parent_hash"] == 1002 and [b["block_hash"] for b in ev2["blocks"]] == [1003, 1004]
+        full = want_hashes + R.compute_block_hash_for_seq(more, KB)
+        assert tree.find_matches(full).scores == {(42, 0): 5}
+        # a partial block FIRST publishes an empty Stored event (kv_event_create_stored_from_parts breaks before pushing)
+        assert pub.publish_stored(3, [1, 2], [2], [2000])
+        assert json.loads(events[-1])["event"]["data"]["stored"]["blocks"] == []
+        # LoRA adapters hash to different blocks (protocols.rs:74-110)
+        assert pub.publish_stored(4, tokens[:KB], [KB], [3000], lora_name="adapter-a")
+        th = json.loads(events[-1])["event"]["data"]["stored"]["blocks"][0]["tokens_hash"]
+        assert th == R.compute_block_hash_for_seq(tokens[:KB], KB, lora_name="adapter-a")[0] != want_hashes[0]
+        # removed
+        assert pub.publish_removed(5, [1004])
+        assert json.loads(events[-1])["event"]["data"] == {"removed": {"block_hashes": [1004]}}
+        assert tree.find_matches(full).scores == {(42, 0): 4}
+        # an event the indexer rejects surfaces as ERR (parent unknown -> ParentBlockNotFound)
+        assert not pub.publish_stored(6, tokens[:KB], [KB], [4000], parent_hash=999999)
+        assert not pub.publish_removed(7, [555])
+        # a second init keeps the first publisher (OnceCell semantics): block size stays 4
+        assert R._ev_lib().dynamo_llm_init(b"other", b"x", 64) == 0
+        assert pub.publish_stored(8, list(range(4)), [4], [5000])
+        assert len(json.loads(events[-1])["event"]["data"]["stored"]["blocks"]) == 1
+        assert R.KvEventPublisher.published_count() >= 8
+    finally:
+        pub.shutdown()
+        tree.close()
