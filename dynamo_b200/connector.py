@@ -203,6 +203,7 @@ class KvConnectorWorker:
         self._pending: List[Tuple[BlockTransferRequest, Optional[TransferOptions]]] = []   # waiting for their requirement
         self._inflight: List[Tuple[TransferCompleteNotification, Optional[LeaderTransferRequest]]] = []
         self._enqueued: Dict[Tuple[str, str], int] = {}      # (request_id, uuid) -> epoch at worker-side enqueue
+        self._unprocessed: Dict[str, Set[str]] = {}           # request_id -> uuids completed before their slot existed
         self._early: Set[Tuple[str, str]] = set()             # offloads launched (gated) before the last layer was saved
         self.failures: List[Tuple[Optional[str], Optional[str], str]] = []   # transfers that aborted: (request_id, uuid, error)
         self._ready_flags = None
@@ -274,7 +275,7 @@ class KvConnectorWorker:
         for s in md.new_slots:
             if s["request_id"] in self.slots:
                 raise AssertionError("slot already exists")
-            self.slots[s["request_id"]] = _Slot(int(s["expected_immediate_ops"]))     # create_slot_with_immediate_ops
+            self._new_slot(s["request_id"], int(s["expected_immediate_ops"]))        # create_slot_with_immediate_ops
         onboarding, offloading = [], []
         for op in md.operations:
             (onboarding if op.transfer_type == LOAD else offloading).append(op)
@@ -321,10 +322,12 @@ class KvConnectorWorker:
         for r in done_off:
             self.maybe_finished_offloading.discard(r)
             self.slots.pop(r, None)
+            self._unprocessed.pop(r, None)
         done_on = {r for r in self.maybe_finished_onboarding if self.slots[r].is_complete()}
         for r in done_on:
             self.maybe_finished_onboarding.discard(r)
             self.slots.pop(r, None)
+            self._unprocessed.pop(r, None)
         return done_off, done_on
 
     # -- transfers issued by the leader -------------------------------------------------------------------
@@ -361,6 +364,14 @@ class KvConnectorWorker:
             self.mgr = None
 
     # -- internals ------------------------------------------------------------------------------------------
+    def _new_slot(self, request_id: str, expected_immediate_ops: int) -> None:
+        slot = _Slot(expected_immediate_ops)
+        buffered = self._unprocessed.get(request_id)
+        if buffered:                      # add_slot (scheduler.rs:403-437): results that beat the slot are applied to it
+            assert len(buffered) <= max(expected_immediate_ops, len(buffered)), "buffered results exceed expected immediate ops"
+            slot.completed |= buffered
+        self.slots[request_id] = slot
+
     def _enqueue(self, op: WorkerTransferRequest) -> None:
         if op.request_id not in self.slots:
             raise AssertionError("slot does not exist")                              # scheduler.rs:220-228
@@ -444,6 +455,10 @@ class KvConnectorWorker:
             if done:
                 if cr is not None and cr.request_id in self.slots:
                     self.slots[cr.request_id].completed.add(cr.uuid)
+                elif cr is not None:
+                    # an Immediate transfer can finish before the metadata that creates its slot is bound: keep the result
+                    # until the slot appears (Scheduler.unprocessed_immediate_results, scheduler.rs:403-437,510-537)
+                    self._unprocessed.setdefault(cr.request_id, set()).add(cr.uuid)
             else:
                 rest.append((note, cr))
         self._inflight = rest
@@ -507,7 +522,7 @@ class TrtllmKvConnectorWorker(KvConnectorWorker):
         for sl in md.new_slots:
             if sl["request_id"] in self.slots:
                 raise AssertionError("slot already exists")
-            self.slots[sl["request_id"]] = _Slot(int(sl["expected_immediate_ops"]))
+            self._new_slot(sl["request_id"], int(sl["expected_immediate_ops"]))
         self.onboarding_operations = [op for op in md.operations if op.transfer_type == LOAD]
         self.offloading_operations = [op for op in md.operations if op.transfer_type == STORE]
         self._epoch += 1
