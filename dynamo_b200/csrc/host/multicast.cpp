@@ -29,6 +29,7 @@ struct Driver {
   CUresult (*MulticastCreate)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*);
   CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice);
   CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long);
+  CUresult (*MulticastBindAddr)(CUmemGenericAllocationHandle, size_t, CUdeviceptr, size_t, unsigned long long);
   CUresult (*MulticastUnbind)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t);
   CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags);
   CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
@@ -67,7 +68,7 @@ Driver& driver()
   static Driver d = [] {
     Driver x{};
     x.ok = resolve("cuMulticastCreate", &x.MulticastCreate, &x.why) && resolve("cuMulticastAddDevice", &x.MulticastAddDevice, &x.why) &&
-           resolve("cuMulticastBindMem", &x.MulticastBindMem, &x.why) && resolve("cuMulticastUnbind", &x.MulticastUnbind, &x.why) &&
+           resolve("cuMulticastBindMem", &x.MulticastBindMem, &x.why) && resolve("cuMulticastBindAddr", &x.MulticastBindAddr, &x.why) && resolve("cuMulticastUnbind", &x.MulticastUnbind, &x.why) &&
            resolve("cuMulticastGetGranularity", &x.MulticastGetGranularity, &x.why) && resolve("cuMemCreate", &x.MemCreate, &x.why) &&
            resolve("cuMemRelease", &x.MemRelease, &x.why) && resolve("cuMemAddressReserve", &x.MemAddressReserve, &x.why) &&
            resolve("cuMemAddressFree", &x.MemAddressFree, &x.why) && resolve("cuMemMap", &x.MemMap, &x.why) &&
@@ -111,6 +112,7 @@ struct Member {
   CUmemGenericAllocationHandle mem = 0;
   CUdeviceptr va = 0;
   bool bound = false;
+  bool owned = true;   // false: the engine's own allocation bound with cuMulticastBindAddr -- never unmapped / released here
 };
 struct Mapping {
   int device = -1;
@@ -316,6 +318,27 @@ extern "C" int kvbm_mc_group_bind_local(kvbm_mc_group* g, int device, void** uni
   return KVBM_OK;
 }
 
+// Bind memory the ENGINE already owns (a KV pool it allocated itself) instead of allocating a pool here: the range must be
+// backed by the driver's virtual-memory-management API (cuMemCreate + cuMemMap -- e.g. PyTorch's expandable segments) and
+// aligned to the multicast granularity.  The first kvbm_mc_group_size() bytes of `ptr` become this device's share.
+extern "C" int kvbm_mc_group_bind_addr(kvbm_mc_group* g, int device, void* ptr, size_t bytes)
+{
+  int rc = check_ready(g);
+  if (rc) return rc;
+  if (!ptr || bytes < g->size) return set_last_error(KVBM_ERR, "bind_addr: the range must cover kvbm_mc_group_size() bytes");
+  if ((rc = touch_device(device))) return rc;
+  CUresult r = driver().MulticastBindAddr(g->mc, 0, reinterpret_cast<CUdeviceptr>(ptr), g->size, 0);
+  if (r != CUDA_SUCCESS)
+    return fail_cu(r, "cuMulticastBindAddr (is the range cuMemCreate-backed and granularity-aligned?)");
+  Member mb;
+  mb.device = device;
+  mb.va = reinterpret_cast<CUdeviceptr>(ptr);
+  mb.bound = true;
+  mb.owned = false;
+  g->members.push_back(mb);
+  return KVBM_OK;
+}
+
 extern "C" int kvbm_mc_group_map(kvbm_mc_group* g, int device, void** multicast_ptr)
 {
   int rc = check_ready(g);
@@ -368,6 +391,7 @@ extern "C" void kvbm_mc_group_destroy(kvbm_mc_group* g)
       CUdevice dev;
       if (mb.bound && d.DeviceGet(&dev, mb.device) == CUDA_SUCCESS) d.MulticastUnbind(g->mc, dev, 0, g->size);
       step("unbind");
+      if (!mb.owned) continue;
       d.MemUnmap(mb.va, g->size);
       d.MemAddressFree(mb.va, g->size);
       step("unmap pool");

@@ -191,7 +191,7 @@ EXPORTED_SYMBOLS = [
     "kvbm_manager_export_serialized_layout", "kvbm_manager_import_serialized_layout", "kvbm_layout_descriptor_json",
     "kvbm_manager_import_descriptor_json",
     "kvbm_mc_supported", "kvbm_mc_group_create", "kvbm_mc_group_export_fd", "kvbm_mc_group_import_fd",
-    "kvbm_mc_group_size", "kvbm_mc_group_add_device", "kvbm_mc_group_bind_local", "kvbm_mc_group_map",
+    "kvbm_mc_group_size", "kvbm_mc_group_add_device", "kvbm_mc_group_bind_local", "kvbm_mc_group_bind_addr", "kvbm_mc_group_map",
     "kvbm_mc_group_destroy",
 ]
 
@@ -249,6 +249,7 @@ def lib() -> C.CDLL:
         L.kvbm_mc_group_size.restype = sz
         L.kvbm_mc_group_add_device.argtypes = [vp, i]
         L.kvbm_mc_group_bind_local.argtypes = [vp, i, P(vp)]
+        L.kvbm_mc_group_bind_addr.argtypes = [vp, i, vp, sz]
         L.kvbm_mc_group_map.argtypes = [vp, i, P(vp)]
         L.kvbm_mc_group_destroy.argtypes = [vp]
         L.kvbm_mc_group_destroy.restype = None
@@ -533,6 +534,10 @@ class MulticastGroup:
         p = C.c_void_p()
         _check(lib().kvbm_mc_group_bind_local(self._h, device, C.byref(p)))
         return p.value
+
+    def bind_addr(self, device: int, ptr: int, nbytes: int) -> None:
+        """Bind memory the engine already owns (cuMemCreate-backed, granularity-aligned) instead of a pool allocated here."""
+        _check(lib().kvbm_mc_group_bind_addr(self._h, device, ptr, nbytes))
 
     def map(self, device: int) -> int:
         """Map the multicast object for the sending device; returns the multicast address of offset 0."""

@@ -220,6 +220,9 @@ size_t kvbm_mc_group_size(const kvbm_mc_group* g);
 int kvbm_mc_group_add_device(kvbm_mc_group* g, int device);
 /* allocate this device's pool (cuMemCreate), map it for the device and bind it at offset 0 of the object */
 int kvbm_mc_group_bind_local(kvbm_mc_group* g, int device, void** unicast_ptr);
+/* bind the first kvbm_mc_group_size() bytes of memory the ENGINE owns (cuMulticastBindAddr): the range must be backed by the
+ * driver's VMM API (cuMemCreate / cuMemMap, e.g. PyTorch expandable segments) and aligned to the multicast granularity */
+int kvbm_mc_group_bind_addr(kvbm_mc_group* g, int device, void* ptr, size_t bytes);
 /* map the multicast object for `device` (the sender); stores to the returned range reach every bound pool */
 int kvbm_mc_group_map(kvbm_mc_group* g, int device, void** multicast_ptr);
 void kvbm_mc_group_destroy(kvbm_mc_group* g);

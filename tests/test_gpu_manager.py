@@ -240,3 +240,53 @@ def test_done_flag_option_delivers_the_epoch_to_destination_memory(mgr):
     O.execute_memcpy_transfer(src.twin, ref, [0, 1, 2], [5, 6, 7])
     for got, want in zip(dst.bytes(), ref.buffers):
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("bounce_blocks", [1, 2, 5, 64], ids=lambda b: f"bounce{b}")
+def test_two_hop_through_a_pinned_bounce_buffer(mgr, bounce_blocks):
+    """TwoHop{CudaAsyncD2H, Pinned, CudaAsyncH2D} (strategy.rs:222-233) executed like executor/mod.rs:357-416,477-571: the
+    bounce blocks are split into two groups, chunks alternate between them, one bounce block = one block at a time.  The two
+    device pools are registered as living on different GPUs (device ids 0 / 1) so that disallowing GPU RDMA selects the plan;
+    the bytes are checked against the oracle and the bounce pool must hold nothing but staged copies of source blocks."""
+    nb, n = 40, 23
+    src, dst = Pool(mgr, "LWs", nb, StorageKind.Device, nl=3), Pool(mgr, "FC", nb, StorageKind.Device, nl=3)
+    far = mgr.register_fully_contiguous(dst.cfg, dst.mem[0].data_ptr(), dst.mem[0].numel(), StorageKind.Device, 1)
+    bounce = Pool(mgr, "FC", max(bounce_blocks, 2), StorageKind.Pinned, nl=3)
+    rng = np.random.default_rng(bounce_blocks)
+    for b in src.twin.buffers:
+        b[:] = rng.integers(0, 256, b.size, dtype=np.uint8)
+    src.upload()
+    sid, did = rng.permutation(nb)[:n], rng.permutation(nb)[:n]
+    bids = list(rng.permutation(max(bounce_blocks, 2))[:bounce_blocks])
+    mgr.set_capabilities(allow_gpu_rdma=False)
+    try:
+        with pytest.raises(KvbmError) as e:                                   # executor/mod.rs:514-519
+            mgr.execute_transfer(src.h, list(sid), far, list(did))
+        assert "Two-hop transfers require a bounce buffer." in e.value.msg
+        dev_bounce = Pool(mgr, "FC", 4, StorageKind.Device, nl=3)
+        with pytest.raises(KvbmError) as e:                                   # :521-527
+            mgr.execute_transfer(src.h, list(sid), far, list(did), TransferOptions(bounce_buffer=(dev_bounce.h, [0, 1])))
+        assert "Bounce buffer layout does not match bounce location." in e.value.msg
+        with pytest.raises(KvbmError):
+            mgr.execute_transfer(src.h, list(sid), far, list(did), TransferOptions(bounce_buffer=(bounce.h, [0, 0])))   # duplicate ids
+        before = K.launch_count()
+        note = mgr.execute_transfer(src.h, list(sid), far, list(did), TransferOptions(bounce_buffer=(bounce.h, bids)))
+        note.wait(30.0)
+        nbq = min(bounce_blocks, n)
+        lens = [nbq // 2, nbq - nbq // 2] if nbq >= 2 else [nbq]
+        pos = chunks = 0
+        while pos < n:
+            pos += min(lens[chunks % len(lens)], n - pos)
+            chunks += 1
+        assert K.launch_count() - before == 2 * chunks                          # two launches (hops) per chunk
+        # same device id on both sides stays a direct D2D even without GPU RDMA
+        mgr.execute_transfer(src.h, list(sid[:3]), dst.h, [int(x) for x in np.setdiff1d(np.arange(nb), did)[:3]]).wait(30.0)
+    finally:
+        mgr.set_capabilities(allow_gpu_rdma=True)
+    dst.download()
+    want = src.twin.block_checksums(sid)
+    for s, d in zip(sid, did):
+        assert dst.twin.block_checksum(int(d)) == want[int(s)]
+    bounce.download()
+    staged = {bounce.twin.block_checksum(int(b)) for b in bids}
+    assert staged <= set(want.values())

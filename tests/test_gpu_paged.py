@@ -102,7 +102,8 @@ def test_random_block_tables_vllm_layout(geom, force_simt):
     check_against_oracle(src_h, dst_h, dst_p, sid, did)
 
 
-@pytest.mark.parametrize("warps,stages,tile", [(1, 2, 4096), (2, 5, 8192), (4, 3, 16384), (8, 2, 2048), (3, 16, 512)])
+@pytest.mark.parametrize("warps,stages,tile", [(1, 2, 4096), (2, 5, 8192), (4, 3, 16384), (8, 2, 2048), (3, 16, 512), (2, 1, 4096),
+                                                (16, 3, 1024)])
 def test_ring_geometries(warps, stages, tile):
     nb, n = 32, 16
     mk = lambda: make_layout(O.LW, nb, nl=3, no=2, page=16, inner=512, dt=2, block_dim=O.BLOCK_IS_SECOND_DIM)
@@ -403,3 +404,65 @@ def test_gate_timeout_aborts_instead_of_hanging():
     dst_p.download()
     assert dst_h.block_checksums(range(n, 2 * n), range(0, 1)) == {n + i: src_h.block_checksum(i, range(0, 1)) for i in range(n)}
     assert not dst_h.region_bytes(n, 2, 0).any()
+
+
+@pytest.mark.parametrize("static_schedule", [0, 1], ids=["tickets", "static"])
+def test_tile_scheduler_modes_and_pool_slots_without_workspace(static_schedule):
+    """The dynamic tile scheduler needs zeroed control words.  Launches that bring no workspace borrow a slot of the library's
+    per-device pool (64 slots, reused once the launch behind them has finished); 150 back-to-back launches cycle it twice
+    and every one must still copy exactly.  static_schedule=1 is the round-robin split (diagnostics)."""
+    nb, n = 48, 40
+    mk = lambda: make_layout(O.LW, nb, nl=4, no=2, page=16, inner=512, dt=2, block_dim=O.BLOCK_IS_SECOND_DIM)
+    src_h, dst_h = mk(), mk()
+    randomize(src_h, 77)
+    src_p, dst_p = DevicePool(src_h), DevicePool(dst_h)
+    rng = np.random.default_rng(3)
+    sp = stream_ptr()
+    last = None
+    for it in range(150 if not static_schedule else 3):
+        sid, did = rng.permutation(nb)[:n], rng.permutation(nb)[:n]
+        s, d = ids_dev(sid), ids_dev(did)
+        opts = K.PagedCopyOpts(static_schedule=static_schedule, max_ctas=5 + it % 7)
+        assert K.paged_copy(src_p.desc, [K.PagedDst(dst_p.desc, s.data_ptr(), d.data_ptr(), 0, 0)], n, 0, 4, 0, opts, sp) == 0
+        last = (sid, did)
+        if it % 50 == 49 or static_schedule:
+            torch.cuda.synchronize()
+            dst_p.download()
+            assert dst_h.block_checksums(did) == {int(b): src_h.block_checksum(int(a)) for a, b in zip(sid, did)}
+    torch.cuda.synchronize()
+    dst_p.download()
+    sid, did = last
+    assert dst_h.block_checksums(did) == {int(b): src_h.block_checksum(int(a)) for a, b in zip(sid, did)}
+
+
+def test_gate_on_the_stream_when_nothing_may_spin():
+    """gate_mode = STREAM_WAIT (what AUTO picks under lazy module loading): the ready flags are waited for by the stream
+    front-end (cuStreamWaitValue32) and each layer is its own launch -- same bytes, same flags, no resident spinner."""
+    nb, n, nl = 32, 16, 5
+    mk = lambda: make_layout(O.LW, nb, nl=nl, no=2, page=16, inner=256, dt=2, block_dim=O.BLOCK_IS_SECOND_DIM)
+    src_h, dst_h = mk(), mk()
+    randomize(src_h, 5)
+    sid, did = np.arange(n), np.arange(n)[::-1].copy() + 9
+    src_p, dst_p = DevicePool(src_h), DevicePool(dst_h)
+    done = torch.zeros(1, dtype=torch.int32, device="cuda")
+    layer_done = torch.zeros(nl, dtype=torch.int32, device="cuda")
+    ws = torch.zeros(K.sync_workspace_words(nl), dtype=torch.int32, device="cuda")
+    ready = torch.zeros(nl, dtype=torch.int32, device="cuda")
+    host_word = torch.zeros(16, dtype=torch.int32).pin_memory()
+    s, d = ids_dev(sid), ids_dev(did)
+    side = torch.cuda.Stream()
+    assert K.gate_would_spin() is True          # tests run with CUDA_MODULE_LOADING=EAGER (conftest)
+    before = K.launch_count()
+    opts = K.PagedCopyOpts(epoch=4, layer_ready_flags=ready.data_ptr(), sync_workspace=ws.data_ptr(), gate_mode=K.GATE_STREAM_WAIT,
+                           completion_flag=host_word.data_ptr(), completion_value=77)
+    assert K.paged_copy(src_p.desc, [K.PagedDst(dst_p.desc, s.data_ptr(), d.data_ptr(), done.data_ptr(), layer_done.data_ptr())],
+                        n, 0, nl, 0, opts, stream_ptr(side)) == 0
+    assert K.launch_count() - before == nl       # one single-layer launch per layer
+    for l in range(nl):
+        assert int(host_word[0]) == 0 and done.tolist() == [0]               # nothing announced before the last layer
+        assert K.set_flags(ready.data_ptr(), l, 1, 4, stream_ptr()) == 0
+    side.synchronize()
+    torch.cuda.synchronize()
+    assert done.tolist() == [4] and layer_done.tolist() == [4] * nl and int(host_word[0]) == 77
+    assert ws.tolist() == [0] * K.sync_workspace_words(nl)
+    check_against_oracle(src_h, dst_h, dst_p, sid, did)
