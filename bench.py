@@ -838,12 +838,12 @@ def gpu_baselines(torch, K, mgr, h_src, h_dst, sid, did, dev, world, iters=5):
     def per_chunk(mode):
         K.check(raw(s_arr, d_arr, REGION, npairs, int(mode), sp))
         stream.synchronize()
-    res["memcpy_per_chunk"] = dict(timed(lambda: per_chunk(MemcpyBatchMode.FALLBACK_ONLY)),
+    res["memcpy_per_chunk"] = dict(timed(lambda: per_chunk(MemcpyBatchMode.FallbackOnly)),
                                    what="one cudaMemcpyAsync per (block, layer, K/V) chunk = the v1 D2D path "
                                         "(block/transfer/cuda.rs:299-391) and UCX cuda_ipc behaviour")
     if K.is_memcpy_batch_available():
         try:
-            res["memcpy_batch"] = dict(timed(lambda: per_chunk(MemcpyBatchMode.BATCH_WITHOUT_FALLBACK)),
+            res["memcpy_batch"] = dict(timed(lambda: per_chunk(MemcpyBatchMode.BatchWithoutFallback)),
                                        what="cudaMemcpyBatchAsync over the same chunk list (K4, tensor_kernels.cu:389-473)")
         except Exception as e:   # the driver may refuse peer batches
             res["memcpy_batch"] = {"unavailable": str(e)[:120]}
@@ -859,7 +859,7 @@ def gpu_baselines(torch, K, mgr, h_src, h_dst, sid, did, dev, world, iters=5):
             dsts = (C.c_void_p * nl_used)(*[int(dbase[i]) for i in range(nl_used)])   # whole layers of the mapped decode pool
 
         def whole():
-            K.check(raw(srcs, dsts, per_layer, nl_used, int(MemcpyBatchMode.FALLBACK_ONLY), sp))
+            K.check(raw(srcs, dsts, per_layer, nl_used, int(MemcpyBatchMode.FallbackOnly), sp))
             stream.synchronize()
         res["memcpy_whole"] = dict(timed(whole, moved=nl_used * per_layer),
                                    what=f"{nl_used} contiguous {per_layer >> 20} MiB cudaMemcpyAsync, rank 0 -> " +

@@ -24,7 +24,7 @@
 #include <string>
 #include <vector>
 
-#include "../dynamo_b200/csrc/kernels/ptx.cuh"
+#include "../dynamo_b200/csrc/kernels/copy_engine.cuh"
 #include "../include/kvbm_kernels.h"
 
 using namespace kvbm;
@@ -235,6 +235,35 @@ __global__ void __launch_bounds__(256, 1) ws_copy_kernel(const __grid_constant__
       t[2] = ptx::globaltimer_ns();
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ws_engine: the PRODUCT engine (copy_engine.cuh run_rings) on the lab's job, to compare with the lab ring above
+// ------------------------------------------------------------------------------------------------------------
+struct JobGen {
+  Job j;
+  __device__ __forceinline__ void get(uint32_t item, Piece& p) const
+  {
+    uint64_t s, d;
+    uint32_t bytes;
+    item_addr(j, item, s, d, bytes);
+    p.src = reinterpret_cast<const uint8_t*>(s);
+    p.dst[0] = reinterpret_cast<uint8_t*>(d);
+    p.bytes = bytes;
+    p.ndst = 1;
+    p.layer = 0;
+  }
+};
+
+__global__ void __launch_bounds__(512, 1) ws_engine_kernel(const __grid_constant__ JobGen gen, uint32_t* ctl, int S, int P, int B)
+{
+  extern __shared__ __align__(128) uint8_t smem[];
+  StreamSync ss{};
+  ss.ctl = ctl;
+  ss.total_rings = gridDim.x * (blockDim.x >> 6);
+  ss.layer_end = 1;
+  RingParams rp{S, P, B, gen.j.tile, 0, true, false, 0, 0};
+  run_rings<0, true>(smem, gen, gen.j.total, 1, rp, ss);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -673,6 +702,89 @@ int main(int argc, char** argv)
       CK(cudaStreamSynchronize(st));
       const unsigned long long bad = verify();
       report("ref_k1", "", time_it(launch, st, iters), bad);
+    }
+  }
+
+  if (only == "engine") {
+    CK(cudaFuncSetAttribute(ws_engine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(ws_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    struct C {
+      int grid, R, S, P, B, tile;
+    };
+    const C cs[] = {{132, 1, 6, 1, 8, 16384}, {74, 2, 6, 2, 8, 16384}, {148, 1, 6, 2, 8, 32768}, {148, 2, 3, 1, 8, 16384}, {16, 2, 6, 2, 4, 16384}, {16, 4, 3, 1, 4, 16384}};
+    for (const C& c : cs) {
+      Job j = job;
+      j.tile = c.tile;
+      j.tiles_per_region = (region + c.tile - 1) / c.tile;
+      j.total = regions * j.tiles_per_region;
+      JobGen g{j};
+      char cfg[200];
+      snprintf(cfg, sizeof cfg, "\"grid\":%d,\"R\":%d,\"S\":%d,\"P\":%d,\"B\":%d,\"tile\":%d,", c.grid, c.R, c.S, c.P, c.B, c.tile);
+      {
+        const size_t smem = cta_smem_bytes(c.R, c.S, c.tile, 0);
+        clear_dst();
+        auto launch = [&]() { ws_engine_kernel<<<c.grid, 64 * c.R, smem, st>>>(g, d_counter, c.S, c.P, c.B); };
+        launch();
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        const unsigned long long bad = verify();
+        report("ws_engine", cfg, time_it(launch, st, iters), bad);
+      }
+      {
+        const size_t smem = c.R * 1024 + static_cast<size_t>(c.R) * c.S * c.tile;
+        WsParams wp{c.S, c.P, c.B, 2, 0, 4, d_counter + 8, nullptr};
+        clear_dst();
+        auto launch = [&]() { ws_copy_kernel<<<c.grid, 64 * c.R, smem, st>>>(j, wp); };
+        launch();
+        CK(cudaStreamSynchronize(st));
+        const unsigned long long bad = verify();
+        report("ws_lab", cfg, time_it(launch, st, iters), bad);
+      }
+    }
+  }
+
+  // ---------------- the product library under different options (what does the launcher add?) ----------------
+  if (only == "libsweep") {
+    void* h = dlopen((root + "/../dynamo_b200/libkvbm_kernels.so").c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!h) fprintf(stderr, "lib: %s\n", dlerror());
+    if (h) {
+      typedef cudaError_t (*paged_fn)(const kvbm_paged_layout*, const kvbm_paged_dst*, int, int, int, int, int, const kvbm_paged_copy_opts*, cudaStream_t);
+      paged_fn paged = reinterpret_cast<paged_fn>(dlsym(h, "kvbm_kernels_paged_copy_v2"));
+      kvbm_paged_layout L{d_sb, region, static_cast<uint64_t>(region) * pool, region, static_cast<uint32_t>(layers), outer, static_cast<uint32_t>(pool)};
+      kvbm_paged_dst D{};
+      D.layout = L;
+      D.layout.layer_base = d_db;
+      D.src_block_ids = d_sid;
+      D.dst_block_ids = d_did;
+      uint32_t* ws;
+      CK(cudaMalloc(&ws, 4 * (layers + 4)));
+      CK(cudaMemset(ws, 0, 4 * (layers + 4)));
+      struct V {
+        const char* name;
+        int ws, stat, warps, ctas, stages, tile, pend;
+      };
+      const V vs[] = {{"default_pool", 0, 0, 0, 0, 0, 0, 0},      {"default_ws", 1, 0, 0, 0, 0, 0, 0},       {"static", 0, 1, 0, 0, 0, 0, 0},
+                      {"r1_148", 1, 0, 2, 148, 0, 0, 0},           {"r1_132_p1", 1, 0, 2, 132, 6, 16384, 1},  {"r2_74_p1", 1, 0, 4, 74, 6, 16384, 1},
+                      {"r1_148_t32", 1, 0, 2, 148, 6, 32768, 2},   {"r2_148", 1, 0, 4, 148, 3, 16384, 1},     {"r4_74", 1, 0, 8, 74, 3, 16384, 1}};
+      for (const V& v : vs) {
+        kvbm_paged_copy_opts o{};
+        o.sync_workspace = v.ws ? ws : nullptr;
+        o.static_schedule = v.stat;
+        o.warps_per_cta = v.warps;
+        o.max_ctas = v.ctas;
+        o.stages = v.stages;
+        o.tile_bytes = v.tile;
+        o.stores_in_flight = v.pend;
+        clear_dst();
+        auto launch = [&]() { CK(paged(&L, &D, 1, blocks, 0, layers, 0, &o, st)); };
+        launch();
+        CK(cudaStreamSynchronize(st));
+        const unsigned long long bad = verify();
+        Timing t = time_it(launch, st, iters);
+        char cfg[160];
+        snprintf(cfg, sizeof cfg, "\"variant\":\"%s\",", v.name);
+        report("libsweep", cfg, t, bad);
+      }
     }
   }
 

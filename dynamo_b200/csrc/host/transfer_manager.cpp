@@ -524,8 +524,8 @@ static int launch_cuda(kvbm_transfer_manager* m, Layout* S, Layout* const* D, in
     dd[d].layout = descriptor(*D[d]);
     dd[d].src_block_ids = dev_src[d];
     dd[d].dst_block_ids = dev_dst[d];
-    dd[d].done_flag = (d == 0) ? o.done_flag : nullptr;
-    dd[d].layer_done_flags = (d == 0) ? o.layer_done_flags : nullptr;
+    dd[d].done_flag = o.per_dst_done_flags ? o.per_dst_done_flags[d] : ((d == 0) ? o.done_flag : nullptr);
+    dd[d].layer_done_flags = o.per_dst_layer_done_flags ? o.per_dst_layer_done_flags[d] : ((d == 0) ? o.layer_done_flags : nullptr);
   }
   kvbm_paged_copy_opts ko{};
   ko.epoch = o.epoch;
@@ -568,6 +568,8 @@ static int execute_two_hop(kvbm_transfer_manager* m, Layout* S, Layout* D, Layou
   kvbm_transfer_options o1 = o, o2 = o;
   o1.done_flag = nullptr;        // completion signals belong to the hop that lands the bytes at the destination
   o1.layer_done_flags = nullptr;
+  o1.per_dst_done_flags = nullptr;
+  o1.per_dst_layer_done_flags = nullptr;
   o2.layer_ready_flags = nullptr;  // ... and gating to the hop that reads the source
   uint64_t last = 0;
   size_t pos = 0;

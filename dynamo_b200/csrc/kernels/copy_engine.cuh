@@ -261,19 +261,29 @@ __device__ __forceinline__ void warp_cast_simt(uint8_t* dst, const uint8_t* src,
 // on the ramp), later tickets come from ss.ctl[2] and shrink towards the end of the transfer (guided self-scheduling)
 // so that all rings run dry together.  Without control words the schedule is a static round-robin of batches.
 // ------------------------------------------------------------------------------------------
-template <int CAST, class Gen>
+// FAST = the plain hot path, known at compile time: one destination, TMA load + TMA store, no cache hints, no gating and
+// no per-layer flags.  A ring is ONE instruction stream per direction, so every instruction of the per-item chain costs
+// its full latency (~10 ns); folding the run-time generality away is worth 10 % on the HBM-bound copy
+// (profiles/r02_copylab_libsweep.jsonl vs r02_copylab_engine.jsonl).
+template <int CAST, bool FAST, class Gen>
 __device__ __forceinline__ void ring_producer(const Gen& gen, uint32_t total, uint32_t my_ring, uint32_t nrings,
-                                              const RingSmem& sm, int ndst, const RingParams& rp, const StreamSync& ss)
+                                              const RingSmem& sm, int ndst_rt, const RingParams& rp, const StreamSync& ss)
 {
   const int lane = threadIdx.x & 31;
+  const int ndst = FAST ? 1 : ndst_rt;
+  const int variant = FAST ? 0 : rp.variant;
+  const int cache_hint = FAST ? 0 : rp.cache_hint;
+  const bool allow_tma = FAST ? true : rp.allow_tma;
+  const bool gate = FAST ? false : ss.gate;
   const int S = rp.S;
   const uint32_t B = static_cast<uint32_t>(rp.batch);
-  const uint64_t policy = rp.cache_hint ? ptx::policy_evict_first() : 0;
+  const uint64_t policy = cache_hint ? ptx::policy_evict_first() : 0;
   const bool dynamic = ss.ctl != nullptr && !rp.static_schedule;
-  int ready_layer = ss.gate ? ss.layer_begin - 1 : 0x7fffffff;
-  uint32_t q = 0;          // items this ring has issued
+  int ready_layer = gate ? ss.layer_begin - 1 : 0x7fffffff;
   uint32_t k = 0;          // tickets taken
   uint32_t last_start = 0;
+  int slot = 0;            // slot of the next item; `wait_parity` = parity the producer waits for on empty[slot]
+  uint32_t wait_parity = 1;
   bool aborted = false;
 
   while (!aborted) {
@@ -303,22 +313,22 @@ __device__ __forceinline__ void ring_producer(const Gen& gen, uint32_t total, ui
     p.bytes = 0;
     p.ndst = ndst;
     p.layer = 0;
-    bool ok = false;
+    uint32_t meta = 0;  // bytes | kSlotTma
     if (static_cast<uint32_t>(lane) < cnt) {
       gen.get(item0 + lane, p);
-      ok = rp.allow_tma && piece_tma_ok(p);
+      bool ok = allow_tma && piece_tma_ok(p);
       if (CAST != 0) ok = ok && (p.bytes & 31) == 0;  // both sides whole 16 B vectors
+      meta = p.bytes | (ok ? kSlotTma : 0u);
     }
-    for (uint32_t i = 0; i < cnt; ++i, ++q) {
+    for (uint32_t i = 0; i < cnt; ++i) {
       const uint64_t src_i = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(p.src), i);
-      const uint32_t bytes_i = __shfl_sync(0xffffffffu, p.bytes, i);
-      const int layer_i = __shfl_sync(0xffffffffu, p.layer, i);
-      const bool ok_i = __shfl_sync(0xffffffffu, static_cast<int>(ok), i) != 0;
+      const uint32_t meta_i = __shfl_sync(0xffffffffu, meta, i);
+      const int layer_i = FAST ? 0 : __shfl_sync(0xffffffffu, p.layer, i);
       uint64_t dst_i[kMaxDst];
 #pragma unroll
       for (int d = 0; d < kMaxDst; ++d)
         if (d < ndst) dst_i[d] = __shfl_sync(0xffffffffu, reinterpret_cast<uint64_t>(p.dst[d]), i);
-      if (layer_i > ready_layer) {
+      if (!FAST && layer_i > ready_layer) {
         if (!wait_layer_ready(ss, layer_i, lane)) {  // gate timeout: abandon the rest (the abort is recorded)
           aborted = true;
           break;
@@ -326,19 +336,19 @@ __device__ __forceinline__ void ring_producer(const Gen& gen, uint32_t total, ui
         ready_layer = layer_i;
       }
       if (lane == 0) {
-        const int slot = q % S;
-        ptx::mbar_wait(sm.empty0 + 8 * slot, ((q / S) & 1) ^ 1);
+        ptx::mbar_wait(sm.empty0 + 8 * slot, wait_parity);
         SlotCtl& c = sm.ctl[slot];
         c.src = src_i;
 #pragma unroll
         for (int d = 0; d < kMaxDst; ++d)
           if (d < ndst) c.dst[d] = dst_i[d];
         c.layer = static_cast<uint32_t>(layer_i);
-        const bool load = ok_i && rp.variant != 3;
-        c.bytes = bytes_i | (ok_i ? kSlotTma : 0u);
+        c.bytes = meta_i;
+        const uint32_t bytes_i = meta_i & ~kSlotTma;
+        const bool load = (meta_i & kSlotTma) != 0 && variant != 3;
         if (load) {
           ptx::mbar_arrive_expect_tx(sm.full0 + 8 * slot, bytes_i);
-          if (rp.cache_hint & 1)
+          if (cache_hint & 1)
             ptx::bulk_g2s_hint(sm.in0 + slot * rp.tile_in, reinterpret_cast<const void*>(src_i), bytes_i, sm.full0 + 8 * slot, policy);
           else
             ptx::bulk_g2s(sm.in0 + slot * rp.tile_in, reinterpret_cast<const void*>(src_i), bytes_i, sm.full0 + 8 * slot);
@@ -346,13 +356,16 @@ __device__ __forceinline__ void ring_producer(const Gen& gen, uint32_t total, ui
           ptx::mbar_arrive(sm.full0 + 8 * slot);
         }
       }
+      if (++slot == S) {
+        slot = 0;
+        wait_parity ^= 1u;
+      }
     }
     __syncwarp();
   }
   // end of this ring's stream
   if (lane == 0) {
-    const int slot = q % S;
-    ptx::mbar_wait(sm.empty0 + 8 * slot, ((q / S) & 1) ^ 1);
+    ptx::mbar_wait(sm.empty0 + 8 * slot, wait_parity);
     sm.ctl[slot].layer = kSlotEnd;
     sm.ctl[slot].bytes = 0;
     ptx::mbar_arrive(sm.full0 + 8 * slot);
@@ -365,14 +378,18 @@ __device__ __forceinline__ void ring_producer(const Gen& gen, uint32_t total, ui
 // layer, it drains its stores and adds what it finished to the layer's counter -- so a receiver that releases
 // layer l+1 only after seeing layer l done can never dead-lock against a producer blocked on l+1's gate.
 // ------------------------------------------------------------------------------------------
-template <int CAST>
-__device__ __forceinline__ void ring_consumer(const RingSmem& sm, int ndst, const RingParams& rp, const StreamSync& ss)
+template <int CAST, bool FAST>
+__device__ __forceinline__ void ring_consumer(const RingSmem& sm, int ndst_rt, const RingParams& rp, const StreamSync& ss)
 {
   const int lane = threadIdx.x & 31;
+  const int ndst = FAST ? 1 : ndst_rt;
+  const int variant = FAST ? 0 : rp.variant;
+  const int cache_hint = FAST ? 0 : rp.cache_hint;
+  const bool want_layers = FAST ? false : ss.want_layers;
   const int S = rp.S;
   const int P = rp.P;
-  const uint64_t policy = rp.cache_hint ? ptx::policy_evict_first() : 0;
-  const bool deferred_release = CAST == 0 && rp.variant == 0;  // TMA stores read the input slot asynchronously
+  const uint64_t policy = cache_hint ? ptx::policy_evict_first() : 0;
+  const bool deferred_release = CAST == 0 && variant == 0;  // TMA stores read the input slot asynchronously
   uint32_t deferred = 0;  // bit (q & 31): item q's slot is handed back once its bulk store has read it
   int cur_layer = -1;
   uint32_t unpublished = 0;
@@ -404,10 +421,11 @@ __device__ __forceinline__ void ring_consumer(const RingSmem& sm, int ndst, cons
   };
 
   uint32_t q = 0;
+  int slot = 0;          // slot of item q
+  uint32_t parity = 0;   // parity the consumer waits for on full[slot]
+  int rel_slot = 0;      // slot of item q - P (the next deferred release)
   for (;; ++q) {
-    const int slot = q % S;
-    const uint32_t parity = (q / S) & 1;
-    if (ss.want_layers && unpublished != 0) {
+    if (want_layers && unpublished != 0) {
       uint32_t ready = 0;
       if (lane == 0) ready = ptx::mbar_try_wait(sm.full0 + 8 * slot, parity) ? 1u : 0u;
       ready = __shfl_sync(0xffffffffu, ready, 0);
@@ -422,7 +440,7 @@ __device__ __forceinline__ void ring_consumer(const RingSmem& sm, int ndst, cons
     const bool tma = (meta_bytes & kSlotTma) != 0;
     const int layer = static_cast<int>(meta_layer);
     const uint32_t in = sm.in0 + slot * rp.tile_in;
-    if (ss.want_layers && unpublished != 0 && layer != cur_layer) publish(q);
+    if (want_layers && unpublished != 0 && layer != cur_layer) publish(q);
     cur_layer = layer;
 
     if (!tma) {
@@ -430,7 +448,7 @@ __device__ __forceinline__ void ring_consumer(const RingSmem& sm, int ndst, cons
       const uint8_t* src = reinterpret_cast<const uint8_t*>(c.src);
       for (int d = 0; d < ndst; ++d) {
         uint8_t* dst = reinterpret_cast<uint8_t*>(c.dst[d]);
-        if (CAST == 0 && rp.variant == 4)
+        if (CAST == 0 && variant == 4)
           warp_copy_simt_mc(dst, src, bytes, lane);
         else if (CAST == 0)
           warp_copy_simt(dst, src, bytes, lane);
@@ -442,12 +460,12 @@ __device__ __forceinline__ void ring_consumer(const RingSmem& sm, int ndst, cons
         ptx::mbar_arrive(sm.empty0 + 8 * slot);
         ptx::bulk_commit();  // always one group per item (possibly empty) so the wait_group counts hold
       }
-    } else if (CAST == 0 && rp.variant == 0) {
+    } else if (CAST == 0 && variant == 0) {
       if (lane == 0) {
 #pragma unroll
         for (int d = 0; d < kMaxDst; ++d)
           if (d < ndst) {
-            if (rp.cache_hint & 2)
+            if (cache_hint & 2)
               ptx::bulk_s2g_hint(reinterpret_cast<void*>(c.dst[d]), in, bytes, policy);
             else
               ptx::bulk_s2g(reinterpret_cast<void*>(c.dst[d]), in, bytes);
@@ -456,11 +474,11 @@ __device__ __forceinline__ void ring_consumer(const RingSmem& sm, int ndst, cons
         deferred |= 1u << (q & 31);
       }
     } else if (CAST == 0) {  // variants 1, 2, 3, 4: the slot is released synchronously
-      if (rp.variant == 1) {
+      if (variant == 1) {
         for (int d = 0; d < ndst; ++d) warp_store_from_smem(reinterpret_cast<uint8_t*>(c.dst[d]), in, bytes, lane);
-      } else if (rp.variant == 4) {
+      } else if (variant == 4) {
         warp_store_from_smem_mc(reinterpret_cast<uint8_t*>(c.dst[0]), in, bytes, lane);
-      } else if (rp.variant == 3) {  // stores only: whatever is in the slot
+      } else if (variant == 3) {  // stores only: whatever is in the slot
         if (lane == 0) {
 #pragma unroll
           for (int d = 0; d < kMaxDst; ++d)
@@ -472,7 +490,7 @@ __device__ __forceinline__ void ring_consumer(const RingSmem& sm, int ndst, cons
       __syncwarp();
       if (lane == 0) {
         ptx::mbar_arrive(sm.empty0 + 8 * slot);
-        if (rp.variant != 3) ptx::bulk_commit();
+        if (variant != 3) ptx::bulk_commit();
       }
     } else {
       const uint32_t dst_bytes = CAST == 1 ? bytes * 2 : bytes / 2;
@@ -490,23 +508,35 @@ __device__ __forceinline__ void ring_consumer(const RingSmem& sm, int ndst, cons
         ptx::bulk_commit();
       }
     }
-    if (deferred_release && lane == 0) {
-      // stores q-P+1..q may still be reading their slots; everything older has left shared memory
-      ptx::bulk_wait_read_n(P);
-      if (q >= static_cast<uint32_t>(P)) {
-        const uint32_t j = q - P;
-        if (deferred & (1u << (j & 31))) {
-          ptx::mbar_arrive(sm.empty0 + 8 * (j % S));
-          deferred &= ~(1u << (j & 31));
+    if (deferred_release) {
+      if (lane == 0) {
+        // stores q-P+1..q may still be reading their slots; everything older has left shared memory
+        if (P == 1)
+          ptx::bulk_wait_read<1>();
+        else if (P == 2)
+          ptx::bulk_wait_read<2>();
+        else
+          ptx::bulk_wait_read_n(P);
+        if (q >= static_cast<uint32_t>(P)) {
+          const uint32_t bit = 1u << ((q - P) & 31);
+          if (deferred & bit) {
+            ptx::mbar_arrive(sm.empty0 + 8 * rel_slot);
+            deferred &= ~bit;
+          }
         }
       }
+      if (q >= static_cast<uint32_t>(P) && ++rel_slot == S) rel_slot = 0;
     }
     ++unpublished;
+    if (++slot == S) {
+      slot = 0;
+      parity ^= 1u;
+    }
   }
 
   drain();
   if (lane == 0) {
-    if (ss.want_layers && unpublished != 0) arrive_layer(ss, cur_layer, unpublished);
+    if (want_layers && unpublished != 0) arrive_layer(ss, cur_layer, unpublished);
     arrive_transfer(ss);
   }
 }
@@ -582,7 +612,7 @@ __host__ __device__ constexpr uint32_t cta_smem_bytes(int R, int S, uint32_t til
   return static_cast<uint32_t>(R) * (ring_ctl_bytes() + static_cast<uint32_t>(S) * tile_in + 2u * tile_out);
 }
 
-template <int CAST, class Gen>
+template <int CAST, bool FAST, class Gen>
 __device__ __forceinline__ void run_rings(uint8_t* smem, const Gen& gen, uint32_t total, int ndst, const RingParams& rp,
                                           const StreamSync& ss)
 {
@@ -609,9 +639,9 @@ __device__ __forceinline__ void run_rings(uint8_t* smem, const Gen& gen, uint32_
   const uint32_t nrings = gridDim.x * R;
   const uint32_t my_ring = blockIdx.x * R + ring;
   if (producer)
-    ring_producer<CAST>(gen, total, my_ring, nrings, sm, ndst, rp, ss);
+    ring_producer<CAST, FAST>(gen, total, my_ring, nrings, sm, ndst, rp, ss);
   else
-    ring_consumer<CAST>(sm, ndst, rp, ss);
+    ring_consumer<CAST, FAST>(sm, ndst, rp, ss);
 }
 
 }  // namespace kvbm

@@ -52,7 +52,7 @@ static cudaError_t device_info(DeviceInfo* out)
   return cudaSuccess;
 }
 
-static int default_ctas(const DeviceInfo& di) { return (di.sm_count + 1) / 2; }
+static int default_ctas(const DeviceInfo& di) { return di.sm_count; }
 
 // Ring geometry of one launch.
 struct RingCfg {
@@ -65,11 +65,14 @@ struct RingCfg {
   uint32_t out_tile;  // cast only
 };
 
-// defaults measured on B200 (benchmarks/copylab.cu -> profiles/r02_copylab_*.jsonl): 74 CTAs x 2 rings x 6 slots x
-// 16 KiB with guided tickets of <= 8 items copy 512 MiB HBM->HBM in 0.1704 ms (cudaMemcpy 0.1731, reference K1 0.1783)
-constexpr int kDefaultRings = 2;
+// Defaults measured on B200 (benchmarks/copylab.cu -> profiles/r02_copylab_*.jsonl).  One SM moves at most ~50 GB/s per
+// direction through the TMA however many rings it runs, so the HBM-bound copy wants (nearly) every SM: 132-148 CTAs copy
+// 512 MiB HBM->HBM in 0.170 ms (cudaMemcpy 0.173, reference K1 0.177-0.178); 74 CTAs sit at the per-SM limit and are
+// sensitive to every instruction of the per-item chain.  A whole 32 KiB region per bulk op halves that chain's share;
+// smaller regions get more rings per CTA instead (~192 KiB of slots per CTA either way).  16 CTAs saturate an NVLink
+// peer: callers that overlap the transfer with compute pass max_ctas.
 constexpr int kDefaultStages = 6;
-constexpr uint32_t kDefaultTile = 16384;
+constexpr uint32_t kDefaultTile = 32768;
 constexpr int kDefaultBatch = 8;
 
 static uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
@@ -78,21 +81,22 @@ static uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 static RingCfg make_ring(const DeviceInfo& di, uint32_t unit_bytes, int warps, int stages, int tile, int cast, int pending = 0)
 {
   RingCfg c{};
-  c.rings = warps > 0 ? std::max(1, std::min(warps, 16) / 2) : kDefaultRings;
   c.batch = kDefaultBatch;
   // default tile: the whole unit when it is small, else kDefaultTile pieces
   uint32_t t = tile > 0 ? static_cast<uint32_t>(tile) : std::min<uint32_t>(std::max<uint32_t>(unit_bytes, 16), kDefaultTile);
   t = round_up(t, 32);
+  // rings per CTA: as many as keep ~32 KiB x S of slots busy (1 for 32 KiB tiles, 2 for 16 KiB, 4 for <= 8 KiB)
+  c.rings = warps > 0 ? std::max(1, std::min(warps, 16) / 2) : static_cast<int>(std::max<uint32_t>(1, std::min<uint32_t>(4, kDefaultTile / t)));
   const uint32_t budget = static_cast<uint32_t>(di.max_smem_optin) - 1024;
   for (;;) {
     const uint32_t out = cast == 1 ? 2 * t : (cast == 2 ? t / 2 : 0);
     // default depth: ~96 KiB of slots per ring (small tiles get more slots), at least 3, at most 12
-    int s = stages > 0 ? stages : std::max(3, std::min<int>(12, static_cast<int>(kDefaultStages * kDefaultTile / t)));
+    int s = stages > 0 ? stages : kDefaultStages;
     s = std::max(2, std::min(s, kMaxStages));  // one slot cannot overlap a load with a store
     while (s > 2 && cta_smem_bytes(c.rings, s, t, out) > budget) --s;
     if (cta_smem_bytes(c.rings, s, t, out) <= budget) {
       c.stages = s;
-      c.pending = pending > 0 ? std::min(pending, s - 1) : std::max(1, s / 3);
+      c.pending = pending > 0 ? std::min(pending, s - 1) : std::max(1, s / 3);  // 2 of 6
       c.tile = t;
       c.out_tile = out;
       c.smem = cta_smem_bytes(c.rings, s, t, out);
@@ -333,7 +337,7 @@ __device__ __forceinline__ StreamSync make_sync(const PagedSyncArgs& s, const Pa
   return ss;
 }
 
-template <int CAST>
+template <int CAST, bool FAST>
 __global__ void __launch_bounds__(512, 1)
 kvbm_paged_copy_kernel(const __grid_constant__ PagedGen gen, const __grid_constant__ PagedSyncArgs sync,
                        uint32_t total, int S, int P, int batch, int static_schedule, uint32_t out_tile, int allow_tma, int cache_hint,
@@ -344,7 +348,7 @@ kvbm_paged_copy_kernel(const __grid_constant__ PagedGen gen, const __grid_consta
   const int ring_ndst = gen.a.replicate ? gen.a.ndst : 1;
   const StreamSync ss = make_sync(sync, gen.a, total, R);
   RingParams rp{S, P, batch, gen.a.tile, out_tile, allow_tma != 0, static_schedule != 0, cache_hint, CAST == KVBM_CAST_NONE ? variant : 0};
-  run_rings<CAST>(smem, gen, total, ring_ndst, rp, ss);
+  run_rings<CAST, FAST>(smem, gen, total, ring_ndst, rp, ss);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -553,9 +557,12 @@ static cudaError_t preload_kernels()
 #define KVBM_PRELOAD(k) \
   if ((e = cudaFuncGetAttributes(&attr, k)) != cudaSuccess) return e;
   KVBM_PRELOAD(kvbm_pair_copy_kernel)
-  KVBM_PRELOAD(kvbm_paged_copy_kernel<KVBM_CAST_NONE>)
-  KVBM_PRELOAD(kvbm_paged_copy_kernel<KVBM_CAST_FP8E4M3_TO_BF16>)
-  KVBM_PRELOAD(kvbm_paged_copy_kernel<KVBM_CAST_BF16_TO_FP8E4M3>)
+  KVBM_PRELOAD((kvbm_paged_copy_kernel<KVBM_CAST_NONE, false>))
+  KVBM_PRELOAD((kvbm_paged_copy_kernel<KVBM_CAST_FP8E4M3_TO_BF16, false>))
+  KVBM_PRELOAD((kvbm_paged_copy_kernel<KVBM_CAST_BF16_TO_FP8E4M3, false>))
+  KVBM_PRELOAD((kvbm_paged_copy_kernel<KVBM_CAST_NONE, true>))
+  KVBM_PRELOAD((kvbm_paged_copy_kernel<KVBM_CAST_FP8E4M3_TO_BF16, true>))
+  KVBM_PRELOAD((kvbm_paged_copy_kernel<KVBM_CAST_BF16_TO_FP8E4M3, true>))
   KVBM_PRELOAD(kvbm_set_flags_kernel)
   KVBM_PRELOAD(kvbm_wait_flag_kernel)
   KVBM_PRELOAD((kvbm_permute_rows_kernel<true>))
@@ -801,10 +808,8 @@ paged_copy_impl(const kvbm_paged_layout* src, const kvbm_paged_dst* dsts, int nu
 
   const uint64_t rings_needed = (total + rc.batch - 1) / rc.batch;
   const uint64_t ctas_needed = (rings_needed + rc.rings - 1) / rc.rings;
-  // Default: one CTA per TPC (half the SMs).  Measured on B200 (profiles/r02_copylab_n1_b.jsonl): 74 CTAs x 2 rings move
-  // 512 MiB HBM->HBM in 0.1704 ms, the same as 132-148 CTAs x 1 ring, and 16 CTAs already saturate an NVLink peer --
-  // and the other half of the chip stays free for whatever the engine is running.
-  int cap = o.max_ctas > 0 ? o.max_ctas : (cast_mode == KVBM_CAST_NONE ? default_ctas(di) : di.sm_count);  // the cast is ALU work: use every SM
+  // Default: one CTA per SM (see the note at kDefaultTile); max_ctas leaves SMs to whatever the engine is running.
+  int cap = o.max_ctas > 0 ? o.max_ctas : default_ctas(di);
   const int grid = static_cast<int>(std::min<uint64_t>(ctas_needed, static_cast<uint64_t>(cap)));
   const int allow_tma = o.force_simt ? 0 : 1;
   const uint32_t total32 = static_cast<uint32_t>(total);
@@ -829,10 +834,18 @@ paged_copy_impl(const kvbm_paged_layout* src, const kvbm_paged_dst* dsts, int nu
     sched_release(dev, pool_slot, stream);
     return err;
   };
+  // the plain hot path gets the kernel with the generality folded away at compile time (copy_engine.cuh, FAST)
+  bool any_layer_flags = false;
+  for (int d = 0; d < num_dsts; ++d) any_layer_flags = any_layer_flags || dsts[d].layer_done_flags != nullptr;
+  const bool fast = !mc && o.variant == 0 && o.cache_hint == 0 && allow_tma && !o.layer_ready_flags && !any_layer_flags &&
+                    (gen.a.replicate ? data_dsts : 1) == 1;
   switch (cast_mode) {
-    case KVBM_CAST_NONE: return launch(kvbm_paged_copy_kernel<KVBM_CAST_NONE>);
-    case KVBM_CAST_FP8E4M3_TO_BF16: return launch(kvbm_paged_copy_kernel<KVBM_CAST_FP8E4M3_TO_BF16>);
-    default: return launch(kvbm_paged_copy_kernel<KVBM_CAST_BF16_TO_FP8E4M3>);
+    case KVBM_CAST_NONE:
+      return fast ? launch(kvbm_paged_copy_kernel<KVBM_CAST_NONE, true>) : launch(kvbm_paged_copy_kernel<KVBM_CAST_NONE, false>);
+    case KVBM_CAST_FP8E4M3_TO_BF16:
+      return fast ? launch(kvbm_paged_copy_kernel<KVBM_CAST_FP8E4M3_TO_BF16, true>) : launch(kvbm_paged_copy_kernel<KVBM_CAST_FP8E4M3_TO_BF16, false>);
+    default:
+      return fast ? launch(kvbm_paged_copy_kernel<KVBM_CAST_BF16_TO_FP8E4M3, true>) : launch(kvbm_paged_copy_kernel<KVBM_CAST_BF16_TO_FP8E4M3, false>);
   }
 }
 

@@ -103,6 +103,8 @@ class _COptions(C.Structure):
         ("src_kv_layout", C.c_int),
         ("dst_kv_layout", C.c_int),
         ("gate_mode", C.c_int),
+        ("per_dst_done_flags", C.c_void_p),
+        ("per_dst_layer_done_flags", C.c_void_p),
     ]
 
 
@@ -151,6 +153,8 @@ class TransferOptions:
     src_kv_layout: int = 0                # KvBlockLayout overrides (options.rs:63-80); a pair needing a transform is rejected
     dst_kv_layout: int = 0
     gate_mode: int = 0                    # kernels.GATE_AUTO / GATE_SPIN / GATE_STREAM_WAIT
+    per_dst_done_flags: Optional[Sequence[int]] = None        # fan-out: one done-flag address per destination (0 = none)
+    per_dst_layer_done_flags: Optional[Sequence[int]] = None  # fan-out: one layer-done array address per destination
 
     @staticmethod
     def from_layer_range(layer_range: Optional[range]) -> "TransferOptions":

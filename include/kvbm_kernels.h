@@ -127,7 +127,8 @@ typedef struct kvbm_paged_copy_opts {
                                      per-layer landed-item counters, then the launch's control words (rings finished, abort,
                                      tile-scheduler tickets).  Required iff any flag or gating is used; without it the
                                      library lends the launch a slot of a small per-device pool for the tile scheduler. */
-  int max_ctas;                   /* 0 = default (one CTA per TPC = #SM/2, the measured optimum); smaller values leave more SMs to the engine */
+  int max_ctas;                   /* 0 = default (one CTA per SM: an SM moves at most ~50 GB/s per direction, the HBM-bound copy wants
+                                     them all); smaller values leave SMs to the engine -- 16 CTAs saturate an NVLink peer */
   int warps_per_cta;              /* 0 = default (4).  Two warps -- a producer and a consumer -- form one ring. */
   int stages;                     /* 0 = default */
   int tile_bytes;                 /* 0 = default */

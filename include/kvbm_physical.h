@@ -114,6 +114,11 @@ typedef struct kvbm_transfer_options {
   int src_kv_layout, dst_kv_layout;  /* KvBlockLayout overrides (options.rs:63-80): 0 = the layout's own; a pair that would
                                         need a transformation is rejected exactly as transfer/mod.rs:128-147 does */
   int gate_mode;                     /* see kvbm_paged_copy_opts.gate_mode */
+  /* fan-out only: per-destination signals (arrays of num_dsts pointers, entries may be NULL).  When set they replace
+   * done_flag / layer_done_flags, which only reach destination 0.  With `multicast` they name the flags of every receiver of
+   * the one multicast write -- what a staged broadcast needs (disagg.StagedBroadcast). */
+  uint32_t* const* per_dst_done_flags;
+  uint32_t* const* per_dst_layer_done_flags;
 } kvbm_transfer_options;
 
 typedef struct kvbm_transfer_manager kvbm_transfer_manager;
