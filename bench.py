@@ -861,9 +861,22 @@ def gpu_baselines(torch, K, mgr, h_src, h_dst, sid, did, dev, world, iters=5):
         def whole():
             K.check(raw(srcs, dsts, per_layer, nl_used, int(MemcpyBatchMode.FallbackOnly), sp))
             stream.synchronize()
-        res["memcpy_whole"] = dict(timed(whole, moved=nl_used * per_layer),
+        whole()
+        evs = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            K.check(raw(srcs, dsts, per_layer, nl_used, int(MemcpyBatchMode.FallbackOnly), sp))
+            e1.record(stream)
+            e1.synchronize()
+            evs.append(e0.elapsed_time(e1))
+        dev_ms = statistics.median(evs)
+        res["memcpy_whole"] = dict(timed(whole, moved=nl_used * per_layer), device_ms=round(dev_ms, 4),
+                                   wall_gbs=None,
                                    what=f"{nl_used} contiguous {per_layer >> 20} MiB cudaMemcpyAsync, rank 0 -> " +
-                                        ("its own HBM" if world == 1 else "rank 1's pool layers over NVLink") + " (DMA engines): the measured copy ceiling of this box")
+                                        ("its own HBM" if world == 1 else "rank 1's pool layers over NVLink") + " (DMA engines): the measured copy ceiling of this box; gbs = CUDA events on the stream, wall_gbs includes the host's launches")
+        res["memcpy_whole"]["wall_gbs"] = res["memcpy_whole"]["gbs"]
+        res["memcpy_whole"]["gbs"] = round(nl_used * per_layer / (dev_ms * 1e-3) / 1e9, 2)
         del big_a
     except Exception as e:
         res["memcpy_whole"] = {"unavailable": str(e)[:120]}

@@ -135,3 +135,40 @@ def share_fd(rank: int, world: int, fd: Optional[int], name: str, timeout_s: flo
         if not fds:
             raise RuntimeError("no descriptor received")
         return fds[0]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Staged NVLS broadcast: identical KV blocks to N decode workers that each allocate their OWN destination blocks
+# ----------------------------------------------------------------------------------------------------------------------
+def staged_send(mgr: TransferManager, src_handle: int, src_block_ids: Sequence[int], staging_mc_handle: int,
+                receiver_ready_flags: Sequence[int], epoch: int, stream: int,
+                receiver_free_flags: Optional[Sequence[int]] = None) -> TransferCompleteNotification:
+    """Root half of `CollectiveOps::broadcast` (lib/kvbm-engine/src/collectives/mod.rs:99-106, nccl.rs:421-462) for
+    receivers with distinct block tables.  The multicast mode needs the same offsets in every bound pool, which a real
+    decode worker's own allocations never give; so the payload is multicast ONCE into a small staging pool every receiver
+    bound to the group (blocks 0..n-1), and each receiver scatters it locally (`staged_receive`).
+
+    `staging_mc_handle`   layout registered over the group's multicast mapping (`MulticastGroup.map`)
+    `receiver_ready_flags[r]`  address (peer-mapped into this process) of receiver r's per-layer flag array: the kernel
+                          sets entry l to `epoch` when layer l has landed in EVERY staging pool
+    `receiver_free_flags[r]`   address on THIS GPU that receiver r's local scatter sets to the epoch it has consumed:
+                          the next send waits for them on the device before it overwrites the staging pool"""
+    from . import kernels as K
+    n = len(src_block_ids)
+    nr = len(receiver_ready_flags)
+    if receiver_free_flags is not None and epoch > 1:
+        for p in receiver_free_flags:
+            K.check(K.wait_flag(int(p), epoch - 1, stream), "wait_flag(free)")
+    stage_ids = list(range(n))
+    opts = TransferOptions(multicast=1, epoch=epoch, cuda_stream=stream, per_dst_layer_done_flags=[int(p) for p in receiver_ready_flags])
+    return mgr.execute_fanout(src_handle, [staging_mc_handle] * nr, [src_block_ids] * nr, [stage_ids] * nr, True, opts)
+
+
+def staged_receive(mgr: TransferManager, staging_local_handle: int, dst_handle: int, dst_block_ids: Sequence[int],
+                   ready_flags: int, epoch: int, free_flag: int = 0, max_ctas: int = 0) -> TransferCompleteNotification:
+    """Receiver half: ONE gated launch on the receiver's own GPU copies staging block i -> dst_block_ids[i], layer by
+    layer as the root's flags arrive (HBM -> HBM, hidden behind the multicast), then reports `epoch` to `free_flag`
+    (an address in the root's memory, peer-mapped here)."""
+    stage_ids = list(range(len(dst_block_ids)))
+    opts = TransferOptions(layer_ready_flags=int(ready_flags), epoch=epoch, done_flag=int(free_flag), max_ctas=max_ctas)
+    return mgr.execute_transfer(staging_local_handle, stage_ids, dst_handle, dst_block_ids, opts)

@@ -171,7 +171,15 @@ class TransferOptions:
                          self.cuda_stream or 0, int(self.cuda_stream is not None), int(self.cast_mode), self.max_ctas,
                          self.layer_ready_flags, self.layer_done_flags, self.epoch, self.gate_timeout_ms,
                          int(self.multicast), self.done_flag, int(bl), bids, nb, int(self.src_kv_layout),
-                         int(self.dst_kv_layout), int(self.gate_mode))
+                         int(self.dst_kv_layout), int(self.gate_mode), self._ptr_array("_pd", self.per_dst_done_flags),
+                         self._ptr_array("_pl", self.per_dst_layer_done_flags))
+
+    def _ptr_array(self, keep: str, ptrs):
+        if ptrs is None:
+            return None
+        arr = (C.c_void_p * max(1, len(ptrs)))(*[int(p) or None for p in ptrs])
+        setattr(self, keep, arr)          # keep the array alive as long as the options object
+        return C.cast(arr, C.c_void_p)
 
 
 @dataclass

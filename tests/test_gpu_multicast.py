@@ -9,6 +9,7 @@ from dynamo_b200 import kernels as K
 from dynamo_b200.physical import (BlockDimension, KvbmError, LayoutConfig, MulticastGroup, StorageKind, TransferManager,
                                   TransferOptions, multicast_supported)
 from oracle import oracle as O
+from tests.gpu_util import stream_ptr
 
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu, pytest.mark.timeout(200)]
 
@@ -136,3 +137,73 @@ def test_kernel_abi_multicast_with_per_receiver_flags_and_layer_range(group, mod
         assert flags[d].tolist() == [3, 0, 3, 3, 0], f"flags on cuda:{d}"
         assert np.array_equal(p.cpu().numpy(), want), f"pool on cuda:{d} differs from the oracle (multicast={mode})"
     mgr.close()
+
+
+def test_staged_broadcast_serves_receivers_with_their_own_block_tables(group):
+    """The multicast write needs identical offsets in every bound pool; real decode workers allocate their own blocks.
+    Staged form (disagg.staged_send / staged_receive): multicast once into blocks 0..n-1 of the group-bound pools, every
+    receiver scatters locally into ITS table, gated layer by layer on the flags the root's kernel sets in its memory; the
+    root reuses the staging pool only after every receiver reported the previous epoch.  Byte-exact vs the oracle."""
+    from dynamo_b200.disagg import staged_receive, staged_send
+    g, pools, mc = group
+    nd = len(pools)
+    _reset(pools)
+    src = _src_pool(4242)
+    root = TransferManager(device=0, worker_id=70)
+    receivers = list(range(1, nd))
+    for d in receivers:
+        root.enable_peer_access(d)
+    h_src = root.register_layer_separate(_cfg(), [b.data_ptr() for b in src], [b.numel() for b in src], BlockDimension.BlockIsSecondDim,
+                                         StorageKind.Device, 0)
+    h_mc = root.register_layer_separate(_cfg(), [mc + l * PER_LAYER for l in range(NL)], [PER_LAYER] * NL,
+                                        BlockDimension.BlockIsSecondDim, StorageKind.Device, 0)
+    free = torch.zeros(nd, dtype=torch.int32, device="cuda:0")
+    side = torch.cuda.Stream(device="cuda:0")
+    mgrs, h_stage, h_dst, dsts, ready = {}, {}, {}, {}, {}
+    for d in receivers:
+        with torch.cuda.device(d):
+            m = TransferManager(device=d, worker_id=70 + d)
+            m.enable_peer_access(0)
+            mgrs[d] = m
+            h_stage[d] = m.register_layer_separate(_cfg(), [pools[d].data_ptr() + l * PER_LAYER for l in range(NL)], [PER_LAYER] * NL,
+                                                   BlockDimension.BlockIsSecondDim, StorageKind.Device, d)
+            dsts[d] = [torch.zeros(PER_LAYER, dtype=torch.uint8, device=f"cuda:{d}") for _ in range(NL)]
+            h_dst[d] = m.register_layer_separate(_cfg(), [b.data_ptr() for b in dsts[d]], [PER_LAYER] * NL,
+                                                 BlockDimension.BlockIsSecondDim, StorageKind.Device, d)
+            ready[d] = torch.zeros(NL, dtype=torch.int32, device=f"cuda:{d}")
+    for d in range(nd):
+        torch.cuda.synchronize(d)
+    n = 20
+    want = {d: _twin() for d in receivers}
+    for epoch in (1, 2, 3):
+        rng = np.random.default_rng(100 + epoch)
+        sid = rng.permutation(NB)[:n]
+        dids = {d: rng.permutation(NB)[:n] for d in receivers}            # every receiver scatters into its OWN blocks
+        notes = []
+        for d in receivers:                                                 # receivers first: they wait (on their GPU) for the flags
+            with torch.cuda.device(d):
+                notes.append(staged_receive(mgrs[d], h_stage[d], h_dst[d], list(dids[d]), ready[d].data_ptr(), epoch,
+                                            free_flag=free[d:].data_ptr(), max_ctas=8))
+        staged_send(root, h_src, list(sid), h_mc, [ready[d].data_ptr() for d in receivers], epoch, stream_ptr(side),
+                    receiver_free_flags=[free[d:].data_ptr() for d in receivers])
+        try:
+            for nt in notes:
+                nt.wait(60.0)
+        except KvbmError as e:      # say what the flags looked like: which half of the hand-shake did not happen?
+            import time
+            time.sleep(0.2)
+            state = {d: ready[d].tolist() for d in receivers}
+            raise AssertionError(f"epoch {epoch}: {e}; ready flags {state}; free {free.tolist()}; root stream idle: {side.query()}")
+        side.synchronize()
+        for d in receivers:
+            O.execute_memcpy_transfer(_twin(src), want[d], sid, dids[d])
+            got = np.concatenate([b.cpu().numpy() for b in dsts[d]])
+            assert np.array_equal(got, np.concatenate(want[d].buffers)), f"receiver {d} epoch {epoch}"
+            assert ready[d].tolist() == [epoch] * NL
+        assert free[1:].tolist() == [epoch] * len(receivers)
+    for d in range(nd):
+        torch.cuda.synchronize(d)
+    for m in mgrs.values():
+        m.close()
+    root.close()
+    _reset(pools)

@@ -304,11 +304,16 @@ def test_full_size_config3_fp8_roundtrip_is_identity():
         nan = (av & 0x7F) == 0x7F
         assert torch.equal(cv[~nan], av[~nan])
         assert bool(((cv[nan] & 0x7F) == 0x7F).all())
-    # and one region against the torch-generated table
-    table = torch.from_numpy(np.load(os.path.join(GOLD, "fp8_e4m3_to_bf16_torch.npy")).astype(np.int32)).cuda()
-    src_codes = a_bufs[5].view(2, nbp, 16384)[1, int(sid[9])].long()
-    got = b_bufs[5].view(2, nbp, 32768)[1, int(did[9])].view(torch.int16).int() & 0xFFFF
-    assert torch.equal(got, table[src_codes])
+    # and EVERY moved region (256 blocks x 32 layers x K/V) against the torch-generated golden table, on the device
+    table = torch.from_numpy(np.load(os.path.join(GOLD, "fp8_e4m3_to_bf16_torch.npy")).astype(np.uint16).view(np.int16).copy()).cuda()
+    drows = did.long()
+    for l in range(nl):
+        codes = a_bufs[l].view(2, nbp, 16384)[:, rows].long()                 # [2, n, 16384] fp8 codes
+        got = b_bufs[l].view(2, nbp, 32768)[:, drows].view(torch.int16)       # [2, n, 16384] bf16 bit patterns
+        assert torch.equal(got, table[codes]), f"layer {l} differs from the golden fp8->bf16 table"
+    untouched = torch.ones(nbp, dtype=torch.bool, device="cuda")
+    untouched[drows] = False
+    assert not b_bufs[9].view(2, nbp, 32768)[:, untouched].any()
 
 
 def test_full_size_config4_layer_stream_equals_one_shot():
