@@ -848,38 +848,41 @@ def gpu_baselines(torch, K, mgr, h_src, h_dst, sid, did, dev, world, iters=5):
         except Exception as e:   # the driver may refuse peer batches
             res["memcpy_batch"] = {"unavailable": str(e)[:120]}
     try:
-        per_layer = OUTER * POOL_BLOCKS * REGION
-        nl_used = max(1, min(NL, payload // per_layer))
-        big_a = torch.empty(nl_used * per_layer, dtype=torch.uint8, device=dev)
-        srcs = (C.c_void_p * nl_used)(*[big_a.data_ptr() + i * per_layer for i in range(nl_used)])
-        if world == 1:
-            big_b = torch.empty(nl_used * per_layer, dtype=torch.uint8, device=dev)
-            dsts = (C.c_void_p * nl_used)(*[big_b.data_ptr() + i * per_layer for i in range(nl_used)])
+        # the contiguous DMA ceiling: ONE cudaMemcpyAsync of the request's byte count, rank 0's GPU -> the next GPU (a buffer this
+        # process allocates there itself; peer access enabled so that the copy goes over NVLink), CUDA events on the stream
+        big_a = torch.empty(payload, dtype=torch.uint8, device=dev)
+        if world == 1 or torch.cuda.device_count() < 2:
+            big_b = torch.empty(payload, dtype=torch.uint8, device=dev)
+            where = "its own HBM"
         else:
-            dsts = (C.c_void_p * nl_used)(*[int(dbase[i]) for i in range(nl_used)])   # whole layers of the mapped decode pool
+            peer = (torch.cuda.current_device() + 1) % torch.cuda.device_count()
+            mgr.enable_peer_access(peer)
+            big_b = torch.empty(payload, dtype=torch.uint8, device=f"cuda:{peer}")
+            torch.cuda.synchronize(peer)
+            where = f"GPU {peer} over NVLink"
+        srcs = (C.c_void_p * 1)(big_a.data_ptr())
+        dsts = (C.c_void_p * 1)(big_b.data_ptr())
 
         def whole():
-            K.check(raw(srcs, dsts, per_layer, nl_used, int(MemcpyBatchMode.FallbackOnly), sp))
+            K.check(raw(srcs, dsts, payload, 1, int(MemcpyBatchMode.FallbackOnly), sp))
             stream.synchronize()
         whole()
         evs = []
-        for _ in range(iters):
+        for _ in range(iters + 3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            K.check(raw(srcs, dsts, per_layer, nl_used, int(MemcpyBatchMode.FallbackOnly), sp))
+            K.check(raw(srcs, dsts, payload, 1, int(MemcpyBatchMode.FallbackOnly), sp))
             e1.record(stream)
             e1.synchronize()
             evs.append(e0.elapsed_time(e1))
         dev_ms = statistics.median(evs)
-        res["memcpy_whole"] = dict(timed(whole, moved=nl_used * per_layer), device_ms=round(dev_ms, 4),
-                                   wall_gbs=None,
-                                   what=f"{nl_used} contiguous {per_layer >> 20} MiB cudaMemcpyAsync, rank 0 -> " +
-                                        ("its own HBM" if world == 1 else "rank 1's pool layers over NVLink") + " (DMA engines): the measured copy ceiling of this box; gbs = CUDA events on the stream, wall_gbs includes the host's launches")
-        res["memcpy_whole"]["wall_gbs"] = res["memcpy_whole"]["gbs"]
-        res["memcpy_whole"]["gbs"] = round(nl_used * per_layer / (dev_ms * 1e-3) / 1e9, 2)
-        del big_a
+        r = timed(whole)
+        res["memcpy_whole"] = {"ms": r["ms"], "device_ms": round(dev_ms, 4), "gbs": round(payload / (dev_ms * 1e-3) / 1e9, 2), "wall_gbs": r["gbs"],
+                               "what": f"one contiguous {payload >> 20} MiB cudaMemcpyAsync, rank 0 -> {where} (DMA engines): the measured copy "
+                                       "ceiling of this box; gbs = CUDA events on the stream, wall_gbs includes the host's launch + sync"}
+        del big_a, big_b
     except Exception as e:
-        res["memcpy_whole"] = {"unavailable": str(e)[:120]}
+        res["memcpy_whole"] = {"unavailable": str(e)[:160]}
     # two-hop plan GPU -> pinned -> GPU (strategy.rs:222-233, executor/mod.rs:357-416): what the reference does when direct
     # GPU RDMA is not allowed
     try:
