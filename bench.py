@@ -16,8 +16,9 @@ A "step" is one gather -> NVLink -> scatter of that request's KV.
              rank 0 launches ONE kernel that stores to all decode pools (measured: SM-issued peer stores cap at 706 GB/s
              per destination, peer loads reach 775; profiles/r02_copylab_{push,pull}.jsonl).
 
-  value      GB/s of destination bytes, kernel launched through the C ABI with block tables already in HBM; the step time
-             is the MEDIAN of the per-step CUDA-event times (max over ranks); the mean over the same K steps is kept too
+  value      GB/s of destination bytes, kernel launched through the C ABI with block tables already in HBM; K launches back
+             to back, each bracketed by its own pair of CUDA events: the step time is the MEDIAN of the K per-launch device
+             times (max over ranks); total / K of the same K steps is kept too (`ms_per_step_mean`)
   e2e        same metric through the host API (TransferManager.execute_transfer / execute_fanout): block tables arrive as
              HOST lists every step, are uploaded inside the timed region, and the step ends when the host observes the
              completion word the kernel writes back.  (KV pages are device-resident by definition of the path.)
@@ -482,25 +483,26 @@ def run_ours(args):
         return launch
 
     def timed_leg(launch, steps, epoch0):
-        """K steps with one CUDA event between consecutive launches.  Returns (median step ms, mean step ms), both max over
-        ranks.  Ranks that only receive (push mode) wait ON THE DEVICE for the last step's done flag."""
+        """K steps back to back, every launch bracketed by its own pair of CUDA events on the launching stream.  Returns
+        (median of the K per-launch device times, total / K), both max over ranks.  Ranks that only receive (push mode) wait
+        ON THE DEVICE for the last step's done flag, so the total covers the landing of the last byte."""
         barrier()
-        marks = [ev() for _ in range(steps + 1)]
+        starts, ends = [ev() for _ in range(steps)], [ev() for _ in range(steps)]
+        first, last = ev(), ev()
+        first.record(stream)
         if launch is not None:
-            for i in range(steps):
-                marks[i].record(stream)
+            for i in range(steps):          # back to back, no host sync: each launch bracketed by its own pair of events
+                starts[i].record(stream)
                 launch(epoch0 + i + 1)
-            marks[steps].record(stream)
-        else:
-            marks[0].record(stream)
-            if world > 1 and is_dst and not pull:
-                K.check(K.wait_flag(flag_buf.data_ptr(), epoch0 + steps, sp))   # device-side: all K steps landed here
-            marks[steps].record(stream)
+                ends[i].record(stream)
+        elif world > 1 and is_dst and not pull:
+            K.check(K.wait_flag(flag_buf.data_ptr(), epoch0 + steps, sp))   # device-side: all K steps landed here
+        last.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
         barrier()
-        total = marks[0].elapsed_time(marks[steps])
-        med = statistics.median(marks[i].elapsed_time(marks[i + 1]) for i in range(steps)) if launch is not None else 0.0
+        total = first.elapsed_time(last)
+        med = statistics.median(starts[i].elapsed_time(ends[i]) for i in range(steps)) if launch is not None else 0.0
         return allmax(med), allmax(total / steps)
 
     # ================= leg 1: `value` -- C ABI, block tables resident in HBM =================
@@ -640,7 +642,7 @@ def run_ours(args):
             "metric": "kv_transfer_gbs", "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": K_steps,
             "warmup": W, "ms_per_step": round(ms_per_step, 5), "ms_per_step_mean": round(value_ms_mean, 5),
             "value_of_mean_step": round(total_dst_bytes / (value_ms_mean * 1e-3) / 1e9, 2),
-            "timing": "median of the K per-step CUDA-event intervals on the launching stream, max over ranks; *_mean = the same K steps' total / K",
+            "timing": "K steps back to back; ms_per_step = median of the K per-launch CUDA-event intervals (one event pair per launch on the launching stream), max over ranks; *_mean = first-event-to-last-event of the same K steps / K (includes the gaps between launches)",
             "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": round(e2e_val, 2), "unit": "GB/s", "ms_per_step": round(e2e_ms, 5), "p50_ms": round(e2e_p50, 5),
