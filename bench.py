@@ -601,8 +601,16 @@ def run_ours(args):
         if rank == 0 and not CAST and not NVLS:
             extras["gpu_baselines"] = gpu_baselines(torch, K, mgr, h_src_local, h_dsts[0], sids[0], dids[0], dev, world)
         barrier()
-        if REPLICATE and world > 1 and rank == 0:
-            extras.setdefault("gpu_baselines", {})["nccl_bcast_per_region"] = nccl_bcast_baseline()
+        if REPLICATE and world > 1:
+            # the ncclBcast baseline is a separate single-process program that opens its own communicators on every GPU: the
+            # other ranks must leave their GPUs idle meanwhile, so they wait on the (CPU-side) rendezvous store, not in an
+            # NCCL barrier whose kernel would spin on the device
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                extras.setdefault("gpu_baselines", {})["nccl_bcast_per_region"] = nccl_bcast_baseline()
+                store.set("kvbm_bench_nccl_baseline_done", "1")
+            else:
+                store.wait(["kvbm_bench_nccl_baseline_done"])
         barrier()
 
     if rank == 0:
@@ -912,7 +920,7 @@ def nccl_bcast_baseline():
         return {"unavailable": "benchmarks/nccl_bcast_baseline not built (needs nccl.h at build time)"}
     try:
         r = subprocess.run([exe, "--blocks", str(N_BLOCKS), "--pool", str(POOL_BLOCKS), "--layers", str(NL), "--iters", "5", "--warmup", "1"],
-                           capture_output=True, text=True, timeout=240)
+                           capture_output=True, text=True, timeout=90)
         for ln in r.stdout.splitlines():
             if ln.startswith("{"):
                 return json.loads(ln)

@@ -8,5 +8,6 @@ timeout 200 python benchmarks/nvls_staged.py --steps 20 --out gpurun_out/r02_nvl
 if [ "$2" != "short" ]; then
   timeout 300 $TR bench.py --gpus $N --steps 20 --warmup 4 --replicate --no-cpu-baseline > gpurun_out/r02_bench_n${N}_rep.json 2> gpurun_out/r02_bench_n${N}_rep.err; echo "bench rep rc=$?"; cut -c1-600 gpurun_out/r02_bench_n${N}_rep.json
   timeout 300 $TR bench.py --gpus $N --steps 20 --warmup 4 --replicate --nvls --quick --no-cpu-baseline > gpurun_out/r02_bench_n${N}_nvls.json 2> gpurun_out/r02_bench_n${N}_nvls.err; echo "bench nvls rc=$?"; cut -c1-600 gpurun_out/r02_bench_n${N}_nvls.json; tail -n 3 gpurun_out/r02_bench_n${N}_nvls.err
+  timeout 120 benchmarks/nccl_bcast_baseline --iters 5 --warmup 1 > gpurun_out/r02_nccl_bcast_n${N}.json 2> gpurun_out/r02_nccl_bcast_n${N}.err; echo "nccl bcast rc=$?"; cat gpurun_out/r02_nccl_bcast_n${N}.json | cut -c1-500
   timeout 240 python benchmarks/mc_bench.py --sweep --iters 6 --out gpurun_out/r02_mc_sweep_n${N}.json > gpurun_out/r02_mc_sweep_n${N}.log 2>&1; echo "mc sweep rc=$?"; tail -n 12 gpurun_out/r02_mc_sweep_n${N}.log
 fi

@@ -207,3 +207,71 @@ def test_staged_broadcast_serves_receivers_with_their_own_block_tables(group):
         m.close()
     root.close()
     _reset(pools)
+
+
+def test_bind_addr_binds_memory_the_engine_allocated_itself():
+    """kvbm_mc_group_bind_addr = cuMulticastBindAddr: the engine's OWN cuMemCreate-backed pool (allocated here through
+    cuda-python, standing in for an engine allocator) becomes a member of the group -- no pool from the group's allocator."""
+    ndev = torch.cuda.device_count()
+    if ndev < 2 or not all(multicast_supported(d) for d in range(ndev)):
+        pytest.skip("needs >= 2 GPUs with NVLink multicast support")
+    drv = pytest.importorskip("cuda.bindings.driver")
+    nl, nb = 2, 32
+    per_layer = NO * nb * REGION
+    total = nl * per_layer                       # 4 MiB
+    for d in range(ndev):
+        torch.zeros(1, device=f"cuda:{d}")
+    torch.cuda.set_device(0)
+    g = MulticastGroup.create(ndev, total)
+    size = g.size
+    pools, keep = [], []
+
+    def ck(res):
+        assert int(res[0]) == 0, res[0]
+        return res[1:] if len(res) > 2 else (res[1] if len(res) == 2 else None)
+
+    for d in range(ndev):
+        g.add_device(d)
+    for d in range(ndev):
+        prop = drv.CUmemAllocationProp()
+        prop.type = drv.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
+        prop.location.type = drv.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        prop.location.id = d
+        gran = ck(drv.cuMemGetAllocationGranularity(prop, drv.CUmemAllocationGranularity_flags.CU_MEM_ALLOC_GRANULARITY_RECOMMENDED))
+        assert size % int(gran) == 0
+        handle = ck(drv.cuMemCreate(size, prop, 0))
+        va = ck(drv.cuMemAddressReserve(size, max(int(gran), 512 << 20), 0, 0))
+        ck(drv.cuMemMap(va, size, 0, handle, 0))
+        descs = []
+        for p in range(ndev):
+            ad = drv.CUmemAccessDesc()
+            ad.location.type = drv.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+            ad.location.id = p
+            ad.flags = drv.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
+            descs.append(ad)
+        ck(drv.cuMemSetAccess(va, size, descs, len(descs)))
+        g.bind_addr(d, int(va), size)            # <- the call under test
+        t = _view(int(va), size, d)
+        t.zero_()
+        pools.append(t)
+        keep.append((handle, va))
+    for d in range(ndev):
+        torch.cuda.synchronize(d)
+    mc = g.map(0)
+    cfg = LayoutConfig(nb, nl, NO, PAGE, INNER, dtype_width_bytes=DT)
+    mgr = TransferManager(device=0, worker_id=91)
+    src = [torch.randint(0, 256, (per_layer,), dtype=torch.uint8, device="cuda:0") for _ in range(nl)]
+    h_src = mgr.register_layer_separate(cfg, [b.data_ptr() for b in src], [per_layer] * nl, BlockDimension.BlockIsSecondDim, StorageKind.Device, 0)
+    h_mc = mgr.register_layer_separate(cfg, [mc + l * per_layer for l in range(nl)], [per_layer] * nl, BlockDimension.BlockIsSecondDim,
+                                       StorageKind.Device, 0)
+    sid, did = [3, 9, 30, 0, 17], [1, 2, 8, 31, 5]
+    mgr.execute_transfer(h_src, sid, h_mc, did, TransferOptions(multicast=1)).wait(30.0)
+    for d in range(ndev):
+        torch.cuda.synchronize(d)
+    for d in range(ndev):
+        for l in range(nl):
+            got = pools[d][l * per_layer:(l + 1) * per_layer].view(NO, nb, REGION)[:, did].cpu()
+            assert torch.equal(got, src[l].view(NO, nb, REGION)[:, sid].cpu()), f"engine-owned pool on cuda:{d}, layer {l}"
+    mgr.close()
+    del pools
+    g.detach()     # the driver reclaims the object at exit; unbinding takes seconds per member
