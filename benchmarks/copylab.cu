@@ -761,9 +761,15 @@ int main(int argc, char** argv)
       CK(cudaMemset(ws, 0, 4 * (layers + 4)));
       struct V {
         const char* name;
-        int ws, stat, warps, ctas, stages, tile, pend;
+        int ws, stat, warps, ctas, stages, tile, pend, flags = 0;
       };
+      uint32_t* d_flags;
+      CK(cudaMalloc(&d_flags, 256));
+      CK(cudaMemset(d_flags, 0, 256));
+      uint32_t* h_word;
+      CK(cudaHostAlloc(reinterpret_cast<void**>(&h_word), 64, cudaHostAllocMapped));
       const V vs[] = {{"default_pool", 0, 0, 0, 0, 0, 0, 0},      {"default_ws", 1, 0, 0, 0, 0, 0, 0},       {"static", 0, 1, 0, 0, 0, 0, 0},
+                      {"ws_done_flag", 1, 0, 0, 0, 0, 0, 0, 1},    {"ws_done_flag_host_word", 1, 0, 0, 0, 0, 0, 0, 3},
                       {"r1_148", 1, 0, 2, 148, 0, 0, 0},           {"r1_132_p1", 1, 0, 2, 132, 6, 16384, 1},  {"r2_74_p1", 1, 0, 4, 74, 6, 16384, 1},
                       {"r1_148_t32", 1, 0, 2, 148, 6, 32768, 2},   {"r2_148", 1, 0, 4, 148, 3, 16384, 1},     {"r4_74", 1, 0, 8, 74, 3, 16384, 1}};
       for (const V& v : vs) {
@@ -775,6 +781,10 @@ int main(int argc, char** argv)
         o.stages = v.stages;
         o.tile_bytes = v.tile;
         o.stores_in_flight = v.pend;
+        o.epoch = 1;
+        D.done_flag = (v.flags & 1) ? d_flags : nullptr;
+        o.completion_flag = (v.flags & 2) ? h_word : nullptr;
+        o.completion_value = 7;
         clear_dst();
         auto launch = [&]() { CK(paged(&L, &D, 1, blocks, 0, layers, 0, &o, st)); };
         launch();

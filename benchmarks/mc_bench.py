@@ -24,6 +24,7 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--ctas", type=int, default=0)
 ap.add_argument("--modes", default="1,2")
 ap.add_argument("--sweep", action="store_true", help="grid over CTAs / warps / stages / tile for the multicast modes (tuning)")
+ap.add_argument("--hybrid", action="store_true", help="split the payload: a fraction by multicast, the rest by unicast replicate, concurrently")
 ap.add_argument("--out", default="gpurun_out/mc_bench.json")
 a = ap.parse_args()
 
@@ -107,11 +108,11 @@ def t_ms(fn):
     return float(np.median(ts))
 
 
-def verify(tag):
+def verify(tag, devices=None):
     for d in range(nd):
         torch.cuda.synchronize(d)
     ref = [src[l].view(NO, NB, REGION)[:, sid.long()].cpu() for l in (0, NL - 1)]
-    for d in range(nd):
+    for d in (range(nd) if devices is None else devices):
         for k, l in enumerate((0, NL - 1)):
             got = pools[d][l * PER_LAYER:(l + 1) * PER_LAYER].view(NO, NB, REGION)[:, did.to(pools[d].device).long()].cpu()
             assert torch.equal(got, ref[k]), f"{tag}: pool on cuda:{d} layer {l} differs"
@@ -151,6 +152,39 @@ if a.sweep:
                 res["sweep"].append(row)
                 print(row, flush=True)
     verify("after sweep")
+
+if a.hybrid:
+    # The multicast path tops out at ~403 GB/s of egress whatever the kernel shape (sweep above) while the port carries ~740:
+    # send a fraction f of the blocks through the multicast mapping and the rest as unicast replicate, on two streams at once.
+    res["hybrid"] = []
+    sa, sb = torch.cuda.Stream(device="cuda:0"), torch.cuda.Stream(device="cuda:0")
+    recv = list(range(1, nd))[:7]
+    for f in (1.0, 0.95, 0.9, 0.85, 0.8, 0.7):
+        n_mc = max(1, min(n, int(round(n * f))))
+        n_uc = n - n_mc
+
+        def both():
+            e0 = torch.cuda.Event(enable_timing=True)
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(sa)
+            sb.wait_event(e0)
+            K.check(K.paged_copy(s_desc, [K.PagedDst(mc_desc, sid.data_ptr(), did.data_ptr(), 0, 0)], n_mc, 0, NL, 0,
+                                 K.PagedCopyOpts(multicast=1, max_ctas=32), int(sa.cuda_stream)))
+            ea.record(sa)
+            if n_uc:
+                dsts = [K.PagedDst(uc[d], sid[n_mc:].data_ptr(), did[n_mc:].data_ptr(), 0, 0) for d in recv]
+                K.check(K.paged_copy(s_desc, dsts, n_uc, 0, NL, 0, K.PagedCopyOpts(max_ctas=64), int(sb.cuda_stream)))
+            eb.record(sb)
+            torch.cuda.synchronize()
+            return max(e0.elapsed_time(ea), e0.elapsed_time(eb))
+        for _ in range(3):
+            both()
+        ms = float(np.median([both() for _ in range(a.iters)]))
+        row = {"fraction_multicast": f, "blocks_multicast": n_mc, "blocks_unicast": n_uc, "ms": ms,
+               "delivered_remote_GBps": payload * len(recv) / ms / 1e6}
+        res["hybrid"].append(row)
+        print(row, flush=True)
+    verify("after hybrid", devices=recv)
 recv = list(range(1, nd))[:7]
 run_unicast(recv)
 torch.cuda.synchronize()

@@ -37,6 +37,7 @@ struct Piece {
 // pointers allow, byte tail.  `tid`/`nthr` = the cooperating group (a warp or a whole CTA);
 // 8 independent 16 B loads in flight per thread on the aligned path.
 // ------------------------------------------------------------------------------------------
+template <int U = 8>
 __device__ __forceinline__ void group_copy_simt(uint8_t* dst, const uint8_t* src, size_t bytes, uint32_t tid, uint32_t nthr)
 {
   const uintptr_t both = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src);
@@ -46,7 +47,6 @@ __device__ __forceinline__ void group_copy_simt(uint8_t* dst, const uint8_t* src
     const uint4* s = reinterpret_cast<const uint4*>(src);
     uint4* d = reinterpret_cast<uint4*>(dst);
     size_t i = tid;
-    constexpr int U = 8;
     for (; i + static_cast<size_t>(U - 1) * nthr < n; i += static_cast<size_t>(U) * nthr) {
       uint4 v[U];
 #pragma unroll

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <mutex>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace kvbm {
@@ -189,12 +190,14 @@ static void sched_release(int dev, int slot, cudaStream_t stream)
 
 // ------------------------------------------------------------------------------------------------
 // K1: pointer-pair copy (legacy ABI).  Hardware-scheduled SIMT: one CTA per (pair, 32 KiB chunk) -- or one warp per
-// pair when pairs are small -- 8 independent 16 B loads in flight per thread, the alignment ladder of the reference.
+// pair when pairs are small -- 4 independent 16 B loads in flight per thread (8 and 4 are equal on HBM, 4 is a little
+// better when the source is pinned host memory: profiles/r02_k1_unroll_sweep.txt), the alignment ladder of the reference.
 // The CTA scheduler is the dynamic load balancer here, so the ABI needs no workspace and the library no state.
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kPairChunk = 32768;
 constexpr uint32_t kPairSmall = 4096;
 
+template <int U>
 __global__ void __launch_bounds__(256)
 kvbm_pair_copy_kernel(void* const* __restrict__ src_ptrs, void* const* __restrict__ dst_ptrs, size_t copy_size,
                       uint32_t chunks_per_pair, uint64_t num_pairs)
@@ -203,7 +206,7 @@ kvbm_pair_copy_kernel(void* const* __restrict__ src_ptrs, void* const* __restric
   if (copy_size <= kPairSmall) {  // warp per pair
     const uint64_t pair = bid * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pair >= num_pairs) return;
-    group_copy_simt(static_cast<uint8_t*>(dst_ptrs[pair]), static_cast<const uint8_t*>(src_ptrs[pair]), copy_size, threadIdx.x & 31, 32);
+    group_copy_simt<U>(static_cast<uint8_t*>(dst_ptrs[pair]), static_cast<const uint8_t*>(src_ptrs[pair]), copy_size, threadIdx.x & 31, 32);
     return;
   }
   const uint64_t pair = bid / chunks_per_pair;
@@ -212,8 +215,8 @@ kvbm_pair_copy_kernel(void* const* __restrict__ src_ptrs, void* const* __restric
   const size_t off = static_cast<size_t>(chunk) * kPairChunk;
   const size_t left = copy_size - off;
   // chunk boundaries are multiples of 32 KiB, so the alignment class of (src, dst) is the same for every chunk
-  group_copy_simt(static_cast<uint8_t*>(dst_ptrs[pair]) + off, static_cast<const uint8_t*>(src_ptrs[pair]) + off,
-                  left < kPairChunk ? left : kPairChunk, threadIdx.x, blockDim.x);
+  group_copy_simt<U>(static_cast<uint8_t*>(dst_ptrs[pair]) + off, static_cast<const uint8_t*>(src_ptrs[pair]) + off,
+                     left < kPairChunk ? left : kPairChunk, threadIdx.x, blockDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -556,7 +559,10 @@ static cudaError_t preload_kernels()
   cudaError_t e;
 #define KVBM_PRELOAD(k) \
   if ((e = cudaFuncGetAttributes(&attr, k)) != cudaSuccess) return e;
-  KVBM_PRELOAD(kvbm_pair_copy_kernel)
+  KVBM_PRELOAD(kvbm_pair_copy_kernel<8>)
+  KVBM_PRELOAD(kvbm_pair_copy_kernel<4>)
+  KVBM_PRELOAD(kvbm_pair_copy_kernel<2>)
+  KVBM_PRELOAD(kvbm_pair_copy_kernel<1>)
   KVBM_PRELOAD((kvbm_paged_copy_kernel<KVBM_CAST_NONE, false>))
   KVBM_PRELOAD((kvbm_paged_copy_kernel<KVBM_CAST_FP8E4M3_TO_BF16, false>))
   KVBM_PRELOAD((kvbm_paged_copy_kernel<KVBM_CAST_BF16_TO_FP8E4M3, false>))
@@ -640,8 +646,17 @@ kvbm_kernels_launch_vectorized_copy(void** src_ptrs, void** dst_ptrs, size_t cop
   const uint64_t gx = std::min<uint64_t>(ctas, 1ull << 30);
   const uint64_t gy = (ctas + gx - 1) / gx;
   if (gy > 65535) return cudaErrorInvalidValue;
-  kvbm_pair_copy_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(gy)), 256, 0, stream>>>(src_ptrs, dst_ptrs, copy_size_bytes,
-                                                                                                    chunks_per_pair, pairs);
+  // tuning knobs for experiments (benchmarks/kvbench.py): loads in flight per thread and CTA width
+  static const int k1_unroll = [] { const char* e = std::getenv("KVBM_K1_UNROLL"); return e ? std::atoi(e) : 4; }();
+  static const int k1_threads = [] { const char* e = std::getenv("KVBM_K1_THREADS"); const int t = e ? std::atoi(e) : 256; return t >= 32 && t <= 256 && t % 32 == 0 ? t : 256; }();
+  if (copy_size_bytes <= kPairSmall) ctas = (pairs + (k1_threads / 32) - 1) / (k1_threads / 32);
+  const dim3 grid(static_cast<unsigned>(std::min<uint64_t>(ctas, 1ull << 30)), static_cast<unsigned>((ctas + std::min<uint64_t>(ctas, 1ull << 30) - 1) / std::min<uint64_t>(ctas, 1ull << 30)));
+  switch (k1_unroll) {
+    case 1: kvbm_pair_copy_kernel<1><<<grid, k1_threads, 0, stream>>>(src_ptrs, dst_ptrs, copy_size_bytes, chunks_per_pair, pairs); break;
+    case 2: kvbm_pair_copy_kernel<2><<<grid, k1_threads, 0, stream>>>(src_ptrs, dst_ptrs, copy_size_bytes, chunks_per_pair, pairs); break;
+    case 8: kvbm_pair_copy_kernel<8><<<grid, k1_threads, 0, stream>>>(src_ptrs, dst_ptrs, copy_size_bytes, chunks_per_pair, pairs); break;
+    default: kvbm_pair_copy_kernel<4><<<grid, k1_threads, 0, stream>>>(src_ptrs, dst_ptrs, copy_size_bytes, chunks_per_pair, pairs); break;
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();  // :570
 }
