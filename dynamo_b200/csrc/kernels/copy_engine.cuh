@@ -185,7 +185,7 @@ __device__ __forceinline__ void arrive_layer(const StreamSync& ss, int layer, ui
     ptx::fence_acq_rel_sys();      // once per layer for the whole grid: everything acquired above is released below
 #pragma unroll
     for (int d = 0; d < kMaxDst; ++d)
-      if (d < ss.ndst && ss.layer_done[d] != nullptr) ptx::st_release_sys(ss.layer_done[d] + layer, ss.epoch);
+      if (d < ss.ndst && ss.layer_done[d] != nullptr) ptx::st_relaxed_sys(ss.layer_done[d] + layer, ss.epoch);
   }
 }
 
@@ -206,10 +206,10 @@ __device__ __forceinline__ void arrive_transfer(const StreamSync& ss)
   if (!aborted) {
 #pragma unroll
     for (int d = 0; d < kMaxDst; ++d)
-      if (d < ss.ndst && ss.done_flag[d] != nullptr) ptx::st_release_sys(ss.done_flag[d], ss.epoch);
+      if (d < ss.ndst && ss.done_flag[d] != nullptr) ptx::st_relaxed_sys(ss.done_flag[d], ss.epoch);
   }
   // 0xFFFFFFFF = "this transfer gave up waiting for a layer": destinations are NOT told it completed
-  if (ss.completion_flag != nullptr) ptx::st_release_sys(ss.completion_flag, aborted ? 0xFFFFFFFFu : ss.completion_value);
+  if (ss.completion_flag != nullptr) ptx::st_relaxed_sys(ss.completion_flag, aborted ? 0xFFFFFFFFu : ss.completion_value);
 }
 
 // smem -> global by the whole warp (variant 1): 16 B per lane

@@ -145,6 +145,12 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
 {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// relaxed system-scope store: pair with ONE preceding fence_acq_rel_sys() when several flags are published together
+// (a st.release.sys per flag would repeat the fence)
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v)
+{
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
 {
   uint32_t v;
