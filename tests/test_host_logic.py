@@ -512,3 +512,34 @@ def test_layout_ids_are_reused_and_never_overwrite_a_live_layout(mgr):
         mgr.unregister(h)
     assert len(seen) > 60000
     assert mgr.memory_region(keep, 1, 0, 0)[1] == cfg.region_size()    # the early layout is still the same layout
+
+
+def test_ctypes_mirrors_have_the_c_struct_layouts(tmp_path):
+    """A Python mirror that silently drops (or mis-orders) trailing fields still "works" with zeros -- round 2 lost the
+    per-destination flag arrays that way.  Compile a C program that prints sizeof / offsetof of the option structs and
+    compare with the ctypes mirrors field by field."""
+    import shutil
+    from dynamo_b200 import physical as PH
+    gcc = shutil.which("gcc")
+    cuda_inc = "/usr/local/cuda/include"
+    if not gcc or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime_api.h")):
+        pytest.skip("gcc or the CUDA headers are not installed")
+    structs = {"kvbm_paged_copy_opts": K.PagedCopyOpts, "kvbm_paged_layout": K.PagedLayout, "kvbm_paged_dst": K.PagedDst,
+               "kvbm_transfer_options": PH._COptions, "kvbm_layout_config": PH._CConfig, "kvbm_transfer_plan": PH._CPlan,
+               "kvbm_transfer_capabilities": PH._CCaps}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "kvbm_kernels.h"', '#include "kvbm_physical.h"', "int main(void) {"]
+    for cname, mirror in structs.items():
+        lines.append(f'  printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in mirror._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines))
+    r = subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), "-I", cuda_inc, "-o", str(exe), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr        # a field the mirror names but the header lacks fails right here
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    c = {(a, b): int(v) for a, b, v in (ln.split() for ln in out.splitlines())}
+    for cname, mirror in structs.items():
+        assert C.sizeof(mirror) == c[(cname, "sizeof")], f"{cname}: ctypes {C.sizeof(mirror)} vs C {c[(cname, 'sizeof')]} bytes"
+        for fname, _ in mirror._fields_:
+            assert getattr(mirror, fname).offset == c[(cname, fname)], f"{cname}.{fname}"
