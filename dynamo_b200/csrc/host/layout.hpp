@@ -54,6 +54,7 @@ struct Layout {
   int device_id = 0;     // where the memory lives (Device storage)
   bool remote = false;   // imported from another process (peer-mapped)
   bool unmapped = false; // remote AND without a mapping in this process: descriptor only, no transfer may touch it
+  int kv_block_layout = KVBM_KV_UNKNOWN;  // KvBlockLayout of one block (kv_block_layout.rs:40-76); Unknown = builder default
   size_t region = 0, block_stride = 0, layer_stride = 0, outer_stride = 0;
   std::vector<Allocation> allocs;        // 1 (FC) or num_layers (LW)
   std::vector<uint64_t> layer_base;      // address of (block 0, layer l, outer 0)

@@ -161,6 +161,35 @@ static int select_direct_strategy(int src, int dst, const kvbm_transfer_capabili
 }
 
 // ---------------------------------------------------------------------------------------------------
+// KvBlockLayout::requires_transform (kv_block_layout.rs:107-119) and select_transform_kernel (executor/mod.rs:46-100)
+// ---------------------------------------------------------------------------------------------------
+static bool kv_known(int k) { return k >= KVBM_KV_UNIVERSAL_TP && k <= KVBM_KV_CUSTOM; }
+static bool kv_requires_transform(int a, int b)
+{
+  if (kv_known(a) && kv_known(b)) return a != b;  // dim orders of the four named formats are pairwise different
+  if (!kv_known(a) && !kv_known(b)) return false; // Unknown -> Unknown: compatible (the reference warns)
+  return true;                                    // Unknown <-> known: conservative
+}
+static int select_transform_kernel(int src, int dst)
+{
+  if (!kv_requires_transform(src, dst)) return KVBM_TRANSFORM_NONE;
+  if (!kv_known(src) || !kv_known(dst)) return KVBM_TRANSFORM_UNSUPPORTED;
+  const bool s_op = src == KVBM_KV_OPERATIONAL_NHD || src == KVBM_KV_OPERATIONAL_HND;
+  const bool d_op = dst == KVBM_KV_OPERATIONAL_NHD || dst == KVBM_KV_OPERATIONAL_HND;
+  const bool s_un = src == KVBM_KV_UNIVERSAL_TP || src == KVBM_KV_UNIVERSAL_PP;
+  const bool d_un = dst == KVBM_KV_UNIVERSAL_TP || dst == KVBM_KV_UNIVERSAL_PP;
+  if (s_op && d_un) return KVBM_TRANSFORM_BLOCK_TO_UNIVERSAL;
+  if (s_un && d_op) return KVBM_TRANSFORM_UNIVERSAL_TO_BLOCK;
+  if (s_op && d_op) return KVBM_TRANSFORM_OPERATIONAL_TRANSPOSE;
+  return KVBM_TRANSFORM_UNSUPPORTED;  // Custom, and Universal <-> Universal (a TODO in the reference, :87-91)
+}
+static const char* kv_name(int k)
+{
+  static const char* n[] = {"Unknown", "UniversalTP", "UniversalPP", "OperationalHND", "OperationalNHD", "Custom"};
+  return n[k >= 0 && k <= 5 ? k : 0];
+}
+
+// ---------------------------------------------------------------------------------------------------
 // TransferManager
 // ---------------------------------------------------------------------------------------------------
 constexpr int kSlots = 64;     // in-flight transfers before the host has to wait for the oldest
@@ -547,6 +576,39 @@ static int launch_cuda(kvbm_transfer_manager* m, Layout* S, Layout* const* D, in
   return KVBM_OK;
 }
 
+// The layout-transforming transfer: what select_transform_kernel's result would drive if the reference ran it inside
+// execute_transfer (it rejects the pair instead, transfer/mod.rs:128-147).  One kvbm_kernels_paged_permute launch:
+// block tables uploaded like launch_cuda's, no pointer tables, completion word written by a trailing signal kernel.
+static int launch_transform(kvbm_transfer_manager* m, Layout* S, Layout* D, int src_kv, int dst_kv, const size_t* src_ids,
+                            const size_t* dst_ids, size_t n, size_t lb, size_t le, const kvbm_transfer_options& o,
+                            cudaStream_t stream, Slot** slot_out, uint64_t* seq_out)
+{
+  Slot* sl;
+  uint64_t seq;
+  int rc = acquire_slot(m, 2 * n, 4, &sl, &seq);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; ++i) {
+    sl->pinned_ids[i] = static_cast<int32_t>(src_ids[i]);
+    sl->pinned_ids[n + i] = static_cast<int32_t>(dst_ids[i]);
+  }
+  CU(cudaMemcpyAsync(sl->dev_ids, sl->pinned_ids, 2 * n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  m->h2d_bytes += 2 * n * sizeof(int32_t);
+  kvbm_permute_side ps{descriptor(*S), sl->dev_ids, src_kv}, pd{descriptor(*D), sl->dev_ids + n, dst_kv};
+  const size_t nh = S->cfg.num_heads;
+  const size_t row = S->cfg.inner_dim / nh * S->cfg.dtype_width_bytes;
+  cudaError_t e = kvbm_kernels_paged_permute(&ps, &pd, static_cast<int>(n), static_cast<int>(lb), static_cast<int>(le),
+                                             static_cast<uint32_t>(nh), static_cast<uint32_t>(S->cfg.page_size),
+                                             static_cast<uint32_t>(row), o.done_flag, o.epoch, sl->host_flag,
+                                             static_cast<uint32_t>(seq), stream);
+  if (e != cudaSuccess) return fail_cuda(e, "kvbm_kernels_paged_permute");
+  CU(cudaEventRecord(sl->ev, stream));
+  sl->in_flight = true;
+  m->bytes_moved += n * (le - lb) * S->cfg.outer_dim * D->region;
+  *slot_out = sl;
+  *seq_out = seq;
+  return KVBM_OK;
+}
+
 static bool cuda_strategy(int s) { return s == KVBM_STRATEGY_CUDA_ASYNC_H2D || s == KVBM_STRATEGY_CUDA_ASYNC_D2H || s == KVBM_STRATEGY_CUDA_ASYNC_D2D; }
 
 // execute_two_hop_transfer (executor/mod.rs:477-571) with handle_buffered_transfer's two bounce groups (:357-416): the
@@ -609,10 +671,6 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
   Layout* S = m->find(src_h);
   if (!S) return fail(KVBM_ERR_HANDLE, "invalid source handle");
   if (S->unmapped) return fail(KVBM_ERR_UNSUPPORTED, "source layout is a descriptor of another process's host memory: not addressable from this process");
-  // transfer/mod.rs:128-147: the KV block layout overrides exist in the options, but any pair that would need a
-  // transformation is rejected (select_transform_kernel is dead code in the reference, executor/mod.rs:46-100)
-  if (o.src_kv_layout != o.dst_kv_layout && o.src_kv_layout != 0 && o.dst_kv_layout != 0)
-    return fail(KVBM_ERR_UNSUPPORTED, "Layout transformation not supported: source and destination KV block layouts differ");
   std::vector<Layout*> D(nd);
   for (int d = 0; d < nd; ++d) {
     D[d] = m->find(dst_h[d]);
@@ -624,6 +682,47 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
     rc = validate_block_transfer(src_ids[d], n, dst_ids[d], n, S->cfg.num_blocks, D[d]->cfg.num_blocks, src_h == dst_h[d]);
     if (rc) return rc;
   }
+  // effective_src_layout / effective_dst_layout (executor/mod.rs:103-119): the option overrides the layout's own format.
+  // The reference rejects every pair that needs a transformation (validate_layout_compatibility, transfer/mod.rs:128-147);
+  // here the pairs select_transform_kernel names -- plus UniversalTP <-> UniversalPP, its TODO -- run as ONE permuting launch.
+  const int src_kv = o.src_kv_layout ? o.src_kv_layout : S->kv_block_layout;
+  int transform = KVBM_TRANSFORM_NONE;
+  for (int d = 0; d < nd; ++d) {
+    const int dst_kv = o.dst_kv_layout ? o.dst_kv_layout : D[d]->kv_block_layout;
+    int t = select_transform_kernel(src_kv, dst_kv);
+    if (t == KVBM_TRANSFORM_UNSUPPORTED && (src_kv == KVBM_KV_UNIVERSAL_TP || src_kv == KVBM_KV_UNIVERSAL_PP) &&
+        (dst_kv == KVBM_KV_UNIVERSAL_TP || dst_kv == KVBM_KV_UNIVERSAL_PP))
+      t = KVBM_TRANSFORM_UNIVERSAL_TO_UNIVERSAL;
+    if (t == KVBM_TRANSFORM_UNSUPPORTED)
+      return fail(KVBM_ERR_UNSUPPORTED, std::string("Layout transformation not supported: src=") + kv_name(src_kv) + ", dst=" + kv_name(dst_kv));
+    if (t != KVBM_TRANSFORM_NONE) {
+      if (nd != 1) return fail(KVBM_ERR_UNSUPPORTED, "a layout-transforming transfer takes one destination");
+      if (o.cast_mode != KVBM_CAST_NONE) return fail(KVBM_ERR_UNSUPPORTED, "the fused cast and a layout transformation cannot be combined");
+      if (o.layer_ready_flags || o.layer_done_flags || o.per_dst_done_flags || o.per_dst_layer_done_flags || o.multicast)
+        return fail(KVBM_ERR_UNSUPPORTED, "layer streaming / multicast are not available on a layout-transforming transfer");
+      const kvbm_layout_config &sc = S->cfg, &dc = D[d]->cfg;
+      if (!sc.num_heads || !dc.num_heads) return fail(KVBM_ERR_CONFIG, "num_heads_required_for_kv_block_layout");  // config.rs:118-126
+      if (sc.num_heads != dc.num_heads || sc.page_size != dc.page_size || sc.inner_dim != dc.inner_dim || sc.dtype_width_bytes != dc.dtype_width_bytes)
+        return fail(KVBM_ERR_INCOMPATIBLE, "a layout transformation needs equal num_heads, page_size, inner_dim and dtype on both sides");
+      if (sc.inner_dim % sc.num_heads) return fail(KVBM_ERR_CONFIG, "inner_dim_must_be_divisible_by_num_heads");
+      const size_t row = sc.inner_dim / sc.num_heads * sc.dtype_width_bytes;
+      if (row < 16 || row > 4096 || (row & (row - 1)))
+        return fail(KVBM_ERR_UNSUPPORTED, "layout transformation: head_dim * dtype width must be a power of two in 16..4096 bytes, got " + std::to_string(row));
+      const bool s_uni = src_kv == KVBM_KV_UNIVERSAL_TP || src_kv == KVBM_KV_UNIVERSAL_PP;
+      const bool d_uni = dst_kv == KVBM_KV_UNIVERSAL_TP || dst_kv == KVBM_KV_UNIVERSAL_PP;
+      if ((s_uni && !S->fully_contiguous) || (d_uni && !D[d]->fully_contiguous))
+        return fail(KVBM_ERR_INCOMPATIBLE, "a universal KV block layout needs a fully contiguous pool");
+      auto aligned16 = [](const Layout& L) {
+        if ((L.block_stride | L.outer_stride) & 15) return false;
+        for (uint64_t b : L.layer_base)
+          if (b & 15) return false;
+        return true;
+      };
+      if (!aligned16(*S) || !aligned16(*D[d])) return fail(KVBM_ERR_UNSUPPORTED, "layout transformation needs 16-byte aligned pools and strides");
+    }
+    transform = t;
+  }
+  const int dst_kv0 = o.dst_kv_layout ? o.dst_kv_layout : D[0]->kv_block_layout;
   size_t lb = 0, le = S->cfg.num_layers;
   if (o.has_layer_range) {
     lb = o.layer_begin;
@@ -654,6 +753,7 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
     if (nd != 1) return fail(KVBM_ERR_UNSUPPORTED, "two-hop transfers take one destination");
     if (o.use_caller_stream) return fail(KVBM_ERR_UNSUPPORTED, "Two-hop transfers don't support caller-provided streams");  // executor/mod.rs:441
     if (o.cast_mode != KVBM_CAST_NONE) return fail(KVBM_ERR_UNSUPPORTED, "the fused cast is not available on two-hop transfers");
+    if (transform != KVBM_TRANSFORM_NONE) return fail(KVBM_ERR_UNSUPPORTED, "a layout transformation is not available on two-hop transfers");
     if (!o.bounce_layout || !o.bounce_block_ids || o.num_bounce_blocks == 0)
       return fail(KVBM_ERR, "Two-hop transfers require a bounce buffer.");  // executor/mod.rs:514-519
     Layout* B = m->find(o.bounce_layout);
@@ -673,6 +773,7 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
 
   if (plan.first == KVBM_STRATEGY_MEMCPY) {
     if (o.cast_mode != KVBM_CAST_NONE) return fail(KVBM_ERR_UNSUPPORTED, "the fused cast exists only on the CUDA strategies");
+    if (transform != KVBM_TRANSFORM_NONE) return fail(KVBM_ERR_UNSUPPORTED, "layout transformations exist only on the CUDA strategies");
     if (o.use_caller_stream) return fail(KVBM_ERR_UNSUPPORTED, "cuda_stream option is not supported for Memcpy strategy");  // executor/mod.rs:272-276
     for (int d = 0; d < nd; ++d) {
       int rc = host_memcpy_transfer(*S, *D[d], src_ids[d], dst_ids[d], n, o.has_layer_range != 0, lb, le);
@@ -696,7 +797,8 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
     stream = m->h2d[m->rr_h2d++ % kStreams];
   Slot* sl;
   uint64_t seq;
-  int rc = launch_cuda(m, S, D.data(), nd, src_ids, dst_ids, n, replicate, lb, le, o, stream, nullptr, &sl, &seq);
+  int rc = transform != KVBM_TRANSFORM_NONE ? launch_transform(m, S, D[0], src_kv, dst_kv0, src_ids[0], dst_ids[0], n, lb, le, o, stream, &sl, &seq)
+                                            : launch_cuda(m, S, D.data(), nd, src_ids, dst_ids, n, replicate, lb, le, o, stream, nullptr, &sl, &seq);
   if (rc) return rc;
   // caller-provided stream: caller manages sync, completed() is returned (cuda.rs:139-141)
   if (out) *out = o.use_caller_stream ? 0 : seq;
@@ -922,7 +1024,7 @@ extern "C" int kvbm_manager_export_metadata(kvbm_transfer_manager* m, kvbm_layou
   hd.pid = process_identity();
   const kvbm_layout_config& c = L->cfg;
   const uint64_t cfg[9] = {c.num_blocks, c.num_layers, c.outer_dim, c.page_size, c.inner_dim, c.alignment, c.dtype_width_bytes, c.num_heads,
-                           static_cast<uint64_t>(c.allow_fp8)};
+                           static_cast<uint64_t>(c.allow_fp8 ? 1 : 0) | (static_cast<uint64_t>(L->kv_block_layout) << 8)};
   std::memcpy(hd.cfg, cfg, sizeof(cfg));
   auto* p = static_cast<unsigned char*>(buf);
   std::memcpy(p, &hd, sizeof(hd));
@@ -970,7 +1072,7 @@ extern "C" int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void
   cfg.alignment = hd.cfg[5];
   cfg.dtype_width_bytes = hd.cfg[6];
   cfg.num_heads = hd.cfg[7];
-  cfg.allow_fp8 = static_cast<int>(hd.cfg[8]);
+  cfg.allow_fp8 = static_cast<int>(hd.cfg[8] & 0xff);
   const bool same_process = hd.pid == process_identity();
   std::vector<uintptr_t> bases(hd.n_allocs);
   std::vector<size_t> sizes(hd.n_allocs);
@@ -1016,8 +1118,41 @@ extern "C" int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void
   if (rc) return fail(rc, why);
   L.remote = !same_process;
   L.unmapped = unmapped;
+  L.kv_block_layout = static_cast<int>((hd.cfg[8] >> 8) & 0xff);
   return finish_register(m, std::move(L), static_cast<int>(hd.storage), hd.device_id, out);
 }
+
+// FullyContiguousLayoutBuilder::kv_block_layout / LayerSeparateLayoutBuilder::inner_shape (fully_contiguous.rs:83-88,
+// layer_separate.rs:91-101): the format of one block of a registered layout; Unknown until set.
+extern "C" int kvbm_manager_set_kv_block_layout(kvbm_transfer_manager* m, kvbm_layout_handle h, int kv_layout)
+{
+  if (!m) return fail(KVBM_ERR, "null manager");
+  if (kv_layout < KVBM_KV_UNKNOWN || kv_layout > KVBM_KV_OPERATIONAL_NHD) return fail(KVBM_ERR, "unknown KvBlockLayout");
+  std::lock_guard<std::mutex> lk(m->mu);
+  Layout* L = m->find(h);
+  if (!L) return fail(KVBM_ERR_HANDLE, "invalid layout handle");
+  if (kv_layout != KVBM_KV_UNKNOWN) {
+    // LayoutConfig::validate_for_kv_block_layout (config.rs:114-140); the head dimension is inner_dim / num_heads, the
+    // figure consistent with required_bytes (:64-71) and with the chunk size K2 / K3 take
+    if (!L->cfg.num_heads) return fail(KVBM_ERR_CONFIG, "num_heads_required_for_kv_block_layout");
+    if (L->cfg.inner_dim % L->cfg.num_heads) return fail(KVBM_ERR_CONFIG, "inner_dim_must_be_divisible_by_num_heads");
+    if ((kv_layout == KVBM_KV_UNIVERSAL_TP || kv_layout == KVBM_KV_UNIVERSAL_PP) && !L->fully_contiguous)
+      return fail(KVBM_ERR_CONFIG, "universal KV block layouts exist only on fully contiguous layouts");  // layer_separate.rs:91-101
+  }
+  L->kv_block_layout = kv_layout;
+  return KVBM_OK;
+}
+
+extern "C" int kvbm_manager_kv_block_layout(kvbm_transfer_manager* m, kvbm_layout_handle h)
+{
+  if (!m) return -1;
+  std::lock_guard<std::mutex> lk(m->mu);
+  Layout* L = m->find(h);
+  return L ? L->kv_block_layout : -1;
+}
+
+extern "C" int kvbm_select_transform_kernel(int src_kv_layout, int dst_kv_layout) { return select_transform_kernel(src_kv_layout, dst_kv_layout); }
+extern "C" int kvbm_kv_layout_requires_transform(int a, int b) { return kv_requires_transform(a, b) ? 1 : 0; }
 
 extern "C" int kvbm_manager_set_capabilities(kvbm_transfer_manager* m, const kvbm_transfer_capabilities* caps)
 {
@@ -1125,7 +1260,7 @@ static kvbm_wire::Descriptor to_wire(const Layout& L, const std::string& agent)
   for (const Allocation& a : L.allocs) d.regions.push_back({a.addr, a.size});
   d.fully_contiguous = L.fully_contiguous;
   d.block_dim = L.block_dim == KVBM_BLOCK_IS_SECOND_DIM ? 1u : 0u;
-  d.kv_block_layout = kvbm_wire::kKvUnknown;
+  d.kv_block_layout = L.kv_block_layout >= KVBM_KV_UNIVERSAL_TP && L.kv_block_layout <= KVBM_KV_CUSTOM ? static_cast<uint32_t>(L.kv_block_layout - 1) : kvbm_wire::kKvUnknown;
   return d;
 }
 
@@ -1202,6 +1337,7 @@ extern "C" int kvbm_manager_import_descriptor_json(kvbm_transfer_manager* m, con
     rc = make_layer_separate(cfg, bases.data(), sizes.data(), bases.size(), d.block_dim ? KVBM_BLOCK_IS_SECOND_DIM : KVBM_BLOCK_IS_FIRST_DIM, &L, &why);
   }
   if (rc) return fail(rc, why);
+  L.kv_block_layout = d.kv_block_layout <= kvbm_wire::kCustom ? static_cast<int>(d.kv_block_layout) + 1 : KVBM_KV_UNKNOWN;
   const int storage = d.location == kvbm_wire::kDevice ? KVBM_STORAGE_DEVICE
                       : d.location == kvbm_wire::kPinned ? KVBM_STORAGE_PINNED
                       : d.location == kvbm_wire::kDisk   ? KVBM_STORAGE_DISK

@@ -463,6 +463,68 @@ kvbm_permute_rows_kernel(void* const* __restrict__ universal_ptrs, void* const* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Paged permute: the K2 / K3 walk with the addresses computed from the pools' layouts and block tables instead of
+// host-built pointer tables, and for any pair of KvBlockLayouts (kv_block_layout.rs:85-95).  For a fixed
+// (block, layer, outer, head) the nt rows of one head sit at  base + head * head_stride + t * tok_stride  on either side:
+//   UniversalTP [nh,nl,no,nt,hd]  base = block + (l*no + o)*nt*row     head_stride = nl*no*nt*row  tok_stride = row
+//   UniversalPP [nl,nh,no,nt,hd]  base = block + l*nh*no*nt*row + o*nt*row   head_stride = no*nt*row   tok_stride = row
+//   OperationalHND [nl,no,nh,nt,hd]  base = region(l, o)               head_stride = nt*row        tok_stride = row
+//   OperationalNHD [nl,no,nt,nh,hd]  base = region(l, o)               head_stride = row           tok_stride = nh*row
+// One CTA per (block pair, layer, outer), one warp per head, 8 independent 16 B loads per lane before the first store.
+// ------------------------------------------------------------------------------------------------
+struct PermuteSide {
+  const uint64_t* layer_base;
+  const int32_t* ids;
+  uint64_t block_stride;
+  uint64_t layer_step;   // added per layer on top of layer_base[universal ? 0 : l]
+  uint64_t outer_step;
+  uint64_t head_stride;
+  uint64_t tok_stride;
+  int universal;
+};
+
+__global__ void __launch_bounds__(256)
+kvbm_paged_permute_kernel(const __grid_constant__ PermuteSide S, const __grid_constant__ PermuteSide D, uint32_t layer_begin,
+                          uint32_t nlayers, uint32_t no, uint32_t nh, uint32_t nt, uint32_t log2_v)
+{
+  const uint32_t unit = blockIdx.x;  // (pair * nlayers + l) * no + o
+  const uint32_t pair = unit / (nlayers * no);
+  const uint32_t rem = unit - pair * (nlayers * no);
+  const uint32_t l = layer_begin + rem / no, o = rem % no;
+  auto base_of = [&](const PermuteSide& X) {
+    return reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(__ldg(X.layer_base + (X.universal ? 0 : l)))) +
+           static_cast<uint64_t>(__ldg(X.ids + pair)) * X.block_stride + l * X.layer_step + o * X.outer_step;
+  };
+  const uint8_t* sb = base_of(S);
+  uint8_t* db = base_of(D);
+  const uint32_t V = 1u << log2_v;
+  const uint32_t run = nt << log2_v;  // 16 B vectors of one head
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (uint32_t h = warp; h < nh; h += nwarps) {
+    const uint8_t* sh = sb + h * S.head_stride;
+    uint8_t* dh = db + h * D.head_stride;
+    auto off = [&](const PermuteSide& X, uint32_t v) { return static_cast<uint64_t>(v >> log2_v) * X.tok_stride + ((v & (V - 1)) << 4); };
+    constexpr int U = 8;
+    uint32_t v = lane;
+    for (; v + (U - 1) * 32 < run; v += U * 32) {
+      uint4 x[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) x[k] = ptx::ld_stream_v4(sh + off(S, v + k * 32));
+#pragma unroll
+      for (int k = 0; k < U; ++k) ptx::st_stream_v4(dh + off(D, v + k * 32), x[k]);
+    }
+    for (; v < run; v += 32) ptx::st_stream_v4(dh + off(D, v), ptx::ld_stream_v4(sh + off(S, v)));
+  }
+}
+
+__global__ void kvbm_signal_kernel(uint32_t* a, uint32_t va, uint32_t* b, uint32_t vb)
+{
+  __threadfence_system();
+  if (a) ptx::st_release_sys(a, va);
+  if (b) ptx::st_release_sys(b, vb);
+}
+
 static size_t dtype_size(int dtype)
 {
   switch (dtype) {
@@ -571,6 +633,8 @@ static cudaError_t preload_kernels()
   KVBM_PRELOAD((kvbm_paged_copy_kernel<KVBM_CAST_BF16_TO_FP8E4M3, true>))
   KVBM_PRELOAD(kvbm_set_flags_kernel)
   KVBM_PRELOAD(kvbm_wait_flag_kernel)
+  KVBM_PRELOAD(kvbm_paged_permute_kernel)
+  KVBM_PRELOAD(kvbm_signal_kernel)
   KVBM_PRELOAD((kvbm_permute_rows_kernel<true>))
   KVBM_PRELOAD((kvbm_permute_rows_kernel<false>))
   KVBM_PRELOAD((kvbm_permute_kernel<16, true>))
@@ -722,6 +786,84 @@ kvbm_kernels_launch_block_from_universal(const void* const* universal_ptrs, void
 {
   return launch_permute<false>(const_cast<void* const*>(reinterpret_cast<const void* const*>(universal_ptrs)), block_ptrs,
                                num_blocks, nh, nl, no, nt, hd, dtype, layout, stream);
+}
+
+static bool fill_permute_side(const kvbm_permute_side& in, uint32_t nl, uint32_t no, uint32_t nh, uint32_t nt, uint32_t row, PermuteSide* out)
+{
+  const uint64_t head_run = static_cast<uint64_t>(nt) * row;
+  PermuteSide p{};
+  p.layer_base = in.layout.layer_base;
+  p.ids = in.block_ids;
+  p.block_stride = in.layout.block_stride;
+  switch (in.kv_layout) {
+    case KVBM_KV_UNIVERSAL_TP:
+      p.universal = 1;
+      p.layer_step = no * head_run;
+      p.outer_step = head_run;
+      p.head_stride = static_cast<uint64_t>(nl) * no * head_run;
+      p.tok_stride = row;
+      break;
+    case KVBM_KV_UNIVERSAL_PP:
+      p.universal = 1;
+      p.layer_step = static_cast<uint64_t>(nh) * no * head_run;
+      p.outer_step = head_run;
+      p.head_stride = no * head_run;
+      p.tok_stride = row;
+      break;
+    case KVBM_KV_OPERATIONAL_HND:
+      p.outer_step = in.layout.outer_stride;
+      p.head_stride = head_run;
+      p.tok_stride = row;
+      break;
+    case KVBM_KV_OPERATIONAL_NHD:
+      p.outer_step = in.layout.outer_stride;
+      p.head_stride = row;
+      p.tok_stride = static_cast<uint64_t>(nh) * row;
+      break;
+    default:
+      return false;
+  }
+  if ((p.block_stride | p.outer_step) & 15) return false;
+  *out = p;
+  return true;
+}
+
+extern "C" cudaError_t
+kvbm_kernels_paged_permute(const kvbm_permute_side* src, const kvbm_permute_side* dst, int num_blocks, int layer_begin,
+                           int layer_end, uint32_t num_heads, uint32_t page_size, uint32_t row_bytes, uint32_t* done_flag,
+                           uint32_t epoch, uint32_t* completion_flag, uint32_t completion_value, cudaStream_t stream)
+{
+  if (num_blocks < 0 || layer_begin < 0 || layer_end < layer_begin) return cudaErrorInvalidValue;
+  const bool signal = done_flag || completion_flag;
+  auto finish = [&]() -> cudaError_t {
+    if (!signal) return cudaSuccess;
+    kvbm_signal_kernel<<<1, 1, 0, stream>>>(done_flag, epoch, completion_flag, completion_value);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+  };
+  if (num_blocks == 0 || layer_end == layer_begin) return finish();
+  if (!src || !dst || !src->block_ids || !dst->block_ids || !src->layout.layer_base || !dst->layout.layer_base) return cudaErrorInvalidValue;
+  const uint32_t nl = src->layout.num_layers, no = src->layout.outer_dim;
+  if (nl != dst->layout.num_layers || no != dst->layout.outer_dim || static_cast<uint32_t>(layer_end) > nl) return cudaErrorInvalidValue;
+  if (row_bytes < 16 || row_bytes > 4096 || (row_bytes & (row_bytes - 1)) || num_heads == 0 || page_size == 0) return cudaErrorInvalidValue;
+  const uint64_t region = static_cast<uint64_t>(page_size) * num_heads * row_bytes;
+  if (region != src->layout.region_bytes || region != dst->layout.region_bytes) return cudaErrorInvalidValue;
+  PermuteSide S, D;
+  if (!fill_permute_side(*src, nl, no, num_heads, page_size, row_bytes, &S) ||
+      !fill_permute_side(*dst, nl, no, num_heads, page_size, row_bytes, &D))
+    return cudaErrorInvalidValue;
+  const uint64_t units = static_cast<uint64_t>(num_blocks) * (layer_end - layer_begin) * no;
+  if (units >= (1ull << 31)) return cudaErrorInvalidValue;
+  uint32_t log2_v = 0;
+  while ((16u << log2_v) < row_bytes) ++log2_v;
+  const int threads = static_cast<int>(std::min<uint32_t>(8, num_heads)) * 32;
+  kvbm_paged_permute_kernel<<<static_cast<unsigned>(units), threads, 0, stream>>>(S, D, static_cast<uint32_t>(layer_begin),
+                                                                                  static_cast<uint32_t>(layer_end - layer_begin), no,
+                                                                                  num_heads, page_size, log2_v);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return finish();
 }
 
 extern "C" bool

@@ -38,6 +38,16 @@ class MemcpyBatchMode(enum.IntEnum):
     BatchWithoutFallback = 2
 
 
+class KvBlockLayout(enum.IntEnum):
+    """KVBM_KV_* -- lib/kvbm-physical/src/layout/kv_block_layout.rs:40-76 (dimension order of one block, head_dim innermost)"""
+    Unknown = 0
+    UniversalTP = 1      # [nh, nl, no, nt, hd]
+    UniversalPP = 2      # [nl, nh, no, nt, hd]
+    OperationalHND = 3   # [nl, no, nh, nt, hd]
+    OperationalNHD = 4   # [nl, no, nt, nh, hd]
+    Custom = 5
+
+
 class CastMode(enum.IntEnum):
     NONE = 0
     FP8E4M3_TO_BF16 = 1
@@ -81,6 +91,11 @@ class PagedDst(C.Structure):
         ("done_flag", C.c_void_p),
         ("layer_done_flags", C.c_void_p),
     ]
+
+
+class PermuteSide(C.Structure):
+    """struct kvbm_permute_side"""
+    _fields_ = [("layout", PagedLayout), ("block_ids", C.c_void_p), ("kv_layout", C.c_int)]
 
 
 class PagedCopyOpts(C.Structure):
@@ -131,6 +146,9 @@ def lib() -> C.CDLL:
         L.kvbm_kernels_paged_copy_v2.argtypes = [C.POINTER(PagedLayout), C.POINTER(PagedDst), i, i, i, i, i,
                                                  C.POINTER(PagedCopyOpts), vp]
         L.kvbm_kernels_paged_copy_v2.restype = i
+        L.kvbm_kernels_paged_permute.argtypes = [C.POINTER(PermuteSide), C.POINTER(PermuteSide), i, i, i, C.c_uint32, C.c_uint32,
+                                                 C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp]
+        L.kvbm_kernels_paged_permute.restype = i
         L.kvbm_kernels_set_flags.argtypes = [vp, i, i, C.c_uint32, vp]
         L.kvbm_kernels_set_flags.restype = i
         L.kvbm_kernels_wait_flag.argtypes = [vp, C.c_uint32, vp]
@@ -148,7 +166,7 @@ EXPORTED_SYMBOLS = [
     "kvbm_kernels_launch_universal_from_block", "kvbm_kernels_launch_block_from_universal",
     "kvbm_kernels_has_memcpy_batch_async", "kvbm_kernels_is_stub_build",
     "kvbm_kernels_paged_copy_v2", "kvbm_kernels_set_flags", "kvbm_kernels_wait_flag", "kvbm_kernels_stream_wait_event",
-    "kvbm_kernels_launch_count", "kvbm_kernels_build_info", "kvbm_kernels_gate_would_spin",
+    "kvbm_kernels_launch_count", "kvbm_kernels_build_info", "kvbm_kernels_gate_would_spin", "kvbm_kernels_paged_permute",
 ]
 
 GATE_AUTO, GATE_SPIN, GATE_STREAM_WAIT = 0, 1, 2
@@ -201,6 +219,15 @@ def paged_copy(src: PagedLayout, dsts: Sequence[PagedDst], num_blocks: int, laye
     arr = (PagedDst * max(1, len(dsts)))(*dsts)
     return lib().kvbm_kernels_paged_copy_v2(C.byref(src), arr, len(dsts), num_blocks, layer_begin, layer_end,
                                             int(cast_mode), C.byref(opts) if opts is not None else None, stream)
+
+
+def paged_permute(src: PermuteSide, dst: PermuteSide, num_blocks: int, layer_begin: int, layer_end: int, num_heads: int,
+                  page_size: int, row_bytes: int, done_flag: int = 0, epoch: int = 0, completion_flag: int = 0,
+                  completion_value: int = 0, stream: int = 0) -> int:
+    """Blocks src.block_ids[i] -> dst.block_ids[i], every element moved from its place under src.kv_layout to its place under
+    dst.kv_layout; row_bytes = head_dim * element size.  include/kvbm_kernels.h (kvbm_kernels_paged_permute)."""
+    return lib().kvbm_kernels_paged_permute(C.byref(src), C.byref(dst), num_blocks, layer_begin, layer_end, num_heads, page_size,
+                                            row_bytes, done_flag or None, epoch, completion_flag or None, completion_value, stream)
 
 
 def set_flags(flags_ptr: int, first: int, count: int, value: int, stream: int) -> int:

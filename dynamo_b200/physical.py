@@ -150,7 +150,7 @@ class TransferOptions:
     multicast: int = 0                    # destination layout lives in a MulticastGroup.map() range (NVLS)
     done_flag: int = 0                    # word on the destination GPU that receives `epoch` on completion (cf. nixl_write_notification)
     bounce_buffer: Optional[tuple] = None # (layout handle, block ids): BounceBuffer of options.rs:45-51 for two-hop transfers
-    src_kv_layout: int = 0                # KvBlockLayout overrides (options.rs:63-80); a pair needing a transform is rejected
+    src_kv_layout: int = 0                # KvBlockLayout overrides (options.rs:63-80); a pair needing a transform runs the permuting launch
     dst_kv_layout: int = 0
     gate_mode: int = 0                    # kernels.GATE_AUTO / GATE_SPIN / GATE_STREAM_WAIT
     per_dst_done_flags: Optional[Sequence[int]] = None        # fan-out: one done-flag address per destination (0 = none)
@@ -201,7 +201,8 @@ EXPORTED_SYMBOLS = [
     "kvbm_manager_execute_fanout", "kvbm_notification_is_complete", "kvbm_notification_wait",
     "kvbm_manager_bytes_moved", "kvbm_manager_h2d_bytes", "kvbm_manager_set_capabilities",
     "kvbm_manager_export_serialized_layout", "kvbm_manager_import_serialized_layout", "kvbm_layout_descriptor_json",
-    "kvbm_manager_import_descriptor_json",
+    "kvbm_manager_import_descriptor_json", "kvbm_select_transform_kernel", "kvbm_kv_layout_requires_transform",
+    "kvbm_manager_set_kv_block_layout", "kvbm_manager_kv_block_layout",
     "kvbm_mc_supported", "kvbm_mc_group_create", "kvbm_mc_group_export_fd", "kvbm_mc_group_import_fd",
     "kvbm_mc_group_size", "kvbm_mc_group_add_device", "kvbm_mc_group_bind_local", "kvbm_mc_group_bind_addr", "kvbm_mc_group_map",
     "kvbm_mc_group_destroy",
@@ -243,6 +244,10 @@ def lib() -> C.CDLL:
         L.kvbm_manager_execute_transfer.argtypes = [vp, u64, vp, u64, vp, sz, P(_COptions), P(u64)]
         L.kvbm_manager_execute_fanout.argtypes = [vp, u64, i, P(u64), P(P(sz)), P(P(sz)), sz, i, P(_COptions), P(u64)]
         L.kvbm_manager_set_capabilities.argtypes = [vp, P(_CCaps)]
+        L.kvbm_manager_set_kv_block_layout.argtypes = [vp, u64, i]
+        L.kvbm_manager_kv_block_layout.argtypes = [vp, u64]
+        L.kvbm_select_transform_kernel.argtypes = [i, i]
+        L.kvbm_kv_layout_requires_transform.argtypes = [i, i]
         L.kvbm_notification_is_complete.argtypes = [vp, u64]
         L.kvbm_notification_wait.argtypes = [vp, u64, C.c_int64]
         L.kvbm_manager_bytes_moved.argtypes = [vp]
@@ -313,6 +318,26 @@ def select_direct_strategy(src: StorageKind, dst: StorageKind, allow_gds: bool =
         return TransferPlan(True, TransferStrategy(plan.first), StorageKind(plan.bounce_location),
                             TransferStrategy(plan.second))
     return TransferPlan(False, TransferStrategy(plan.first))
+
+
+class TransformKernel(enum.IntEnum):
+    """TransformKernel (transfer/executor/mod.rs:27-41)"""
+    NONE = 0
+    BlockToUniversal = 1
+    UniversalToBlock = 2
+    OperationalTranspose = 3
+    Unsupported = 4
+    UniversalToUniversal = 5   # extension (a TODO in the reference); executed by transfers, never selected by the function below
+
+
+def select_transform_kernel(src: "kernels.KvBlockLayout", dst: "kernels.KvBlockLayout") -> TransformKernel:
+    """select_transform_kernel (transfer/executor/mod.rs:46-100)."""
+    return TransformKernel(lib().kvbm_select_transform_kernel(int(src), int(dst)))
+
+
+def requires_transform(a: "kernels.KvBlockLayout", b: "kernels.KvBlockLayout") -> bool:
+    """KvBlockLayout::requires_transform (layout/kv_block_layout.rs:107-119)."""
+    return bool(lib().kvbm_kv_layout_requires_transform(int(a), int(b)))
 
 
 def validate_block_transfer(src_ids: Sequence[int], dst_ids: Sequence[int], src_num_blocks: int,
@@ -392,6 +417,17 @@ class TransferManager:
         if rc < 0:
             raise KvbmError(ErrorCode.HANDLE, "invalid handle")
         return bool(rc)
+
+    def set_kv_block_layout(self, handle: int, kv_layout: "kernels.KvBlockLayout") -> None:
+        """The format of one block of this layout (builder `.kv_block_layout()` / `.inner_shape()` in the reference).  A transfer
+        between layouts whose formats differ is executed as ONE permuting launch (the reference rejects it)."""
+        _check(lib().kvbm_manager_set_kv_block_layout(self._h, handle, int(kv_layout)))
+
+    def kv_block_layout(self, handle: int) -> "kernels.KvBlockLayout":
+        rc = lib().kvbm_manager_kv_block_layout(self._h, handle)
+        if rc < 0:
+            raise KvbmError(ErrorCode.HANDLE, "invalid handle")
+        return kernels.KvBlockLayout(rc)
 
     def enable_peer_access(self, peer_device: int) -> None:
         _check(lib().kvbm_manager_enable_peer_access(self._h, peer_device))

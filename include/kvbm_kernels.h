@@ -170,6 +170,39 @@ cudaError_t kvbm_kernels_paged_copy_v2(const kvbm_paged_layout* src, const kvbm_
                                        int layer_end, int cast_mode,
                                        const kvbm_paged_copy_opts* opts, cudaStream_t stream);
 
+/* ---- layout-transforming hand-off (TP / PP re-shard while the blocks move) ------------------------------------------------
+ * KvBlockLayout (lib/kvbm-physical/src/layout/kv_block_layout.rs:40-95): the order of the four permutable dimensions of one
+ * block, head_dim (one "row" of row_bytes) always innermost.  The reference selects a transform kernel for a pair of these
+ * (transfer/executor/mod.rs:46-100) but never runs one inside a transfer -- validate_layout_compatibility rejects the pair
+ * (executor/cuda.rs:69) and K2 / K3 are only reachable through host-built pointer tables.  Here the transform is part of the
+ * paged gather -> scatter: no pointer tables, block ids resolved on the device, either pool may be a peer's (NVLink). */
+enum {
+  KVBM_KV_UNKNOWN = 0,
+  KVBM_KV_UNIVERSAL_TP = 1,    /* [nh, nl, no, nt, hd] */
+  KVBM_KV_UNIVERSAL_PP = 2,    /* [nl, nh, no, nt, hd] */
+  KVBM_KV_OPERATIONAL_HND = 3, /* [nl, no, nh, nt, hd] */
+  KVBM_KV_OPERATIONAL_NHD = 4, /* [nl, no, nt, nh, hd] */
+  KVBM_KV_CUSTOM = 5,          /* named by the wire format only; no kernel */
+};
+
+typedef struct kvbm_permute_side {
+  kvbm_paged_layout layout;  /* operational formats: any paged pool, the (block, layer, outer) region holds [nt, nh, hd] or
+                                [nh, nt, hd].  Universal formats: the pool must be fully contiguous -- layer_base[0] +
+                                id * block_stride is the start of num_layers * outer_dim * region_bytes contiguous bytes */
+  const int32_t* block_ids;  /* device-accessible int32[num_blocks] */
+  int kv_layout;             /* KVBM_KV_* (1..4) */
+} kvbm_permute_side;
+
+/* Block src.block_ids[i] of `src` -> block dst.block_ids[i] of `dst`, layers [layer_begin, layer_end), every element moved
+ * from its position under src.kv_layout to its position under dst.kv_layout (equal layouts = plain copy).  Both sides must
+ * agree on num_layers, outer_dim and region_bytes = page_size * num_heads * row_bytes; row_bytes (head_dim * element size)
+ * must be a power of two in 16..4096 and every stride a multiple of 16 (cudaErrorInvalidValue otherwise).  `done_flag`
+ * (nullable, device-visible) receives `epoch` with system scope after the last byte landed.  One launch, stream-ordered. */
+cudaError_t kvbm_kernels_paged_permute(const kvbm_permute_side* src, const kvbm_permute_side* dst, int num_blocks,
+                                       int layer_begin, int layer_end, uint32_t num_heads, uint32_t page_size,
+                                       uint32_t row_bytes, uint32_t* done_flag, uint32_t epoch, uint32_t* completion_flag,
+                                       uint32_t completion_value, cudaStream_t stream);
+
 /* 1 when KVBM_GATE_AUTO would let the transfer's warps spin on the ready flags (eager module loading detected through
  * cuModuleGetLoadingMode), 0 when it would gate on the stream instead. */
 int kvbm_kernels_gate_would_spin(void);

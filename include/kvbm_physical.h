@@ -111,8 +111,9 @@ typedef struct kvbm_transfer_options {
   uint64_t bounce_layout;            /* kvbm_layout_handle; 0 = none */
   const size_t* bounce_block_ids;
   size_t num_bounce_blocks;
-  int src_kv_layout, dst_kv_layout;  /* KvBlockLayout overrides (options.rs:63-80): 0 = the layout's own; a pair that would
-                                        need a transformation is rejected exactly as transfer/mod.rs:128-147 does */
+  int src_kv_layout, dst_kv_layout;  /* KvBlockLayout overrides, KVBM_KV_* (options.rs:63-80): 0 = the layout's own.  A pair that
+                                        needs a transformation is EXECUTED as one permuting launch (the reference rejects it,
+                                        transfer/mod.rs:128-147): see kvbm_select_transform_kernel */
   int gate_mode;                     /* see kvbm_paged_copy_opts.gate_mode */
   /* fan-out only: per-destination signals (arrays of num_dsts pointers, entries may be NULL).  When set they replace
    * done_flag / layer_done_flags, which only reach destination 0.  With `multicast` they name the flags of every receiver of
@@ -183,6 +184,24 @@ int kvbm_manager_import_serialized_layout(kvbm_transfer_manager* m, const void* 
                                           size_t cap, size_t* n_out);
 int kvbm_layout_descriptor_json(kvbm_transfer_manager* m, kvbm_layout_handle h, char* buf, size_t cap, size_t* len);
 int kvbm_manager_import_descriptor_json(kvbm_transfer_manager* m, const char* json, size_t len, kvbm_layout_handle* out);
+
+/* TransformKernel (transfer/executor/mod.rs:27-41) as select_transform_kernel (:46-100) returns it. */
+enum {
+  KVBM_TRANSFORM_NONE = 0,
+  KVBM_TRANSFORM_BLOCK_TO_UNIVERSAL = 1,
+  KVBM_TRANSFORM_UNIVERSAL_TO_BLOCK = 2,
+  KVBM_TRANSFORM_OPERATIONAL_TRANSPOSE = 3,
+  KVBM_TRANSFORM_UNSUPPORTED = 4,
+  KVBM_TRANSFORM_UNIVERSAL_TO_UNIVERSAL = 5, /* extension: UniversalTP <-> UniversalPP, a TODO in the reference (:87-91);
+                                                never returned by kvbm_select_transform_kernel, but executed by transfers */
+};
+int kvbm_select_transform_kernel(int src_kv_layout, int dst_kv_layout);       /* pure; KVBM_KV_* in, KVBM_TRANSFORM_* out */
+int kvbm_kv_layout_requires_transform(int a, int b);                          /* kv_block_layout.rs:107-119 */
+/* The format of one block of a registered layout (FullyContiguousLayoutBuilder::kv_block_layout, fully_contiguous.rs:83-88;
+ * LayerSeparateLayoutBuilder::inner_shape, layer_separate.rs:91-101).  Needs num_heads in the config; universal formats need
+ * a fully contiguous layout.  Travels with export_metadata / the SerializedLayout. */
+int kvbm_manager_set_kv_block_layout(kvbm_transfer_manager* m, kvbm_layout_handle h, int kv_layout);
+int kvbm_manager_kv_block_layout(kvbm_transfer_manager* m, kvbm_layout_handle h);  /* KVBM_KV_*, -1 = unknown handle */
 
 /* TransferCapabilities (transfer/strategy.rs:245-278).  Default {allow_gds 0, allow_gpu_rdma 1}.  With allow_gpu_rdma = 0 a
  * Device -> Device transfer between different GPUs follows the reference's TwoHop plan (strategy.rs:222-233):

@@ -269,3 +269,48 @@ def cast_bf16_to_e4m3(src: np.ndarray) -> np.ndarray:
     out = np.empty(src.shape, dtype=np.uint8)
     lib().oracle_cast_bf16_to_e4m3(src.ctypes.data, out.ctypes.data, src.size)
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# KvBlockLayout transforms -- lib/kvbm-physical/src/layout/kv_block_layout.rs:85-95 (dim_order), the definition the
+# reference's select_transform_kernel (transfer/executor/mod.rs:46-100) pairs kernels with.  The reference only HAS kernels
+# for Operational{NHD,HND} <-> UniversalTP (K2 / K3, restated in kvbm_oracle.c and pinned there); for those pairs
+# `kv_layout_permute` is checked against that restatement in tests/test_oracle_kernels.py.  The other pairs (UniversalPP,
+# NHD <-> HND) have no reference kernel: their oracle is the dim_order definition itself -- parity unpinned beyond it.
+# ----------------------------------------------------------------------------------------------------------------------
+KV_UNKNOWN, KV_UNIVERSAL_TP, KV_UNIVERSAL_PP, KV_OPERATIONAL_HND, KV_OPERATIONAL_NHD = 0, 1, 2, 3, 4
+KV_DIM_ORDER = {KV_UNIVERSAL_TP: "hlot", KV_UNIVERSAL_PP: "lhot", KV_OPERATIONAL_HND: "loht", KV_OPERATIONAL_NHD: "loth"}
+
+
+def kv_layout_permute(block: np.ndarray, src_kv: int, dst_kv: int, nl: int, no: int, nt: int, nh: int, row_bytes: int,
+                      layers: Optional[range] = None, dst_old: Optional[np.ndarray] = None) -> np.ndarray:
+    """One contiguous block (uint8[nl*no*nt*nh*row_bytes]) re-ordered from `src_kv` to `dst_kv`.  With `layers`, only
+    elements of those layers move; every other byte keeps `dst_old`'s value (a partial, layer-wise transfer)."""
+    size = {"h": nh, "l": nl, "o": no, "t": nt}
+    so, do = KV_DIM_ORDER[src_kv], KV_DIM_ORDER[dst_kv]
+    a = np.ascontiguousarray(block, dtype=np.uint8).reshape([size[c] for c in so] + [row_bytes])
+    perm = [so.index(c) for c in do] + [4]
+    out = np.ascontiguousarray(a.transpose(perm))
+    if layers is not None:
+        keep = np.ascontiguousarray(dst_old, dtype=np.uint8).reshape(out.shape).copy()
+        sel = [slice(None)] * 5
+        sel[do.index("l")] = slice(layers.start, layers.stop)
+        keep[tuple(sel)] = out[tuple(sel)]
+        out = keep
+    return out.reshape(-1)
+
+
+def read_logical_block(layout: "Layout", block: int) -> np.ndarray:
+    """The (layer, outer) regions of one block concatenated layer-major: for a fully contiguous layout this IS the block's
+    memory (so also the right view of a universal-format block); for a layer-separate one it is the operational block
+    [nl, no, region] the regions spell."""
+    return np.concatenate([layout.region_bytes(block, l, o) for l in range(layout.num_layers) for o in range(layout.outer_dim)])
+
+
+def write_logical_block(layout: "Layout", block: int, data: np.ndarray) -> None:
+    r = layout.region_size
+    k = 0
+    for l in range(layout.num_layers):
+        for o in range(layout.outer_dim):
+            layout.region_bytes(block, l, o)[:] = data[k * r:(k + 1) * r]
+            k += 1

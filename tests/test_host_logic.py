@@ -474,10 +474,22 @@ def test_two_hop_plan_needs_a_bounce_buffer_and_kv_layout_overrides_are_rejected
     b = np.zeros(cfg.required_bytes(), dtype=np.uint8)
     ha = mgr.register_fully_contiguous(cfg, a.ctypes.data, a.size, StorageKind.System)
     hb = mgr.register_fully_contiguous(cfg, b.ctypes.data, b.size, StorageKind.System)
+    # Unknown <-> known is "Unsupported" (executor/mod.rs:56-60) and rejected with the reference's text
     with pytest.raises(KvbmError) as e:
-        mgr.execute_transfer(ha, [0], hb, [1], TransferOptions(src_kv_layout=1, dst_kv_layout=2))
-    assert e.value.code == ErrorCode.UNSUPPORTED and "Layout transformation not supported" in e.value.msg
+        mgr.execute_transfer(ha, [0], hb, [1], TransferOptions(dst_kv_layout=2))
+    assert e.value.code == ErrorCode.UNSUPPORTED and "Layout transformation not supported: src=Unknown, dst=UniversalPP" in e.value.msg
+    # a supported pair needs num_heads (config.rs:118-126) ...
+    with pytest.raises(KvbmError) as e:
+        mgr.execute_transfer(ha, [0], hb, [1], TransferOptions(src_kv_layout=4, dst_kv_layout=1))
+    assert e.value.code == ErrorCode.CONFIG and "num_heads_required_for_kv_block_layout" in e.value.msg
     mgr.execute_transfer(ha, [0], hb, [1], TransferOptions(src_kv_layout=2, dst_kv_layout=2))   # same layout: plain copy
+    # ... and a CUDA strategy: the permuting launch has no CPU twin in the product (the oracle is test infrastructure)
+    cfg_h = std_cfg(4, num_heads=2)
+    hc = mgr.register_fully_contiguous(cfg_h, a.ctypes.data, a.size, StorageKind.System)
+    hd = mgr.register_fully_contiguous(cfg_h, b.ctypes.data, b.size, StorageKind.System)
+    with pytest.raises(KvbmError) as e:
+        mgr.execute_transfer(hc, [0], hd, [1], TransferOptions(src_kv_layout=4, dst_kv_layout=1))
+    assert e.value.code == ErrorCode.UNSUPPORTED and "only on the CUDA strategies" in e.value.msg
     # Device<->System stay "not supported", exactly like strategy.rs:150-160 (there is no implicit staging)
     dev_like = mgr.register_fully_contiguous(cfg, a.ctypes.data, a.size, StorageKind.Device)
     with pytest.raises(KvbmError) as e:
@@ -497,6 +509,72 @@ def test_two_hop_plan_needs_a_bounce_buffer_and_kv_layout_overrides_are_rejected
         assert e.value.code == ErrorCode.CUDA and "no CPU fallback" in e.value.msg
     finally:
         mgr.set_capabilities(allow_gpu_rdma=True)
+
+
+def test_select_transform_kernel_and_requires_transform_kats():
+    """transfer/executor/mod.rs:578-655 and layout/kv_block_layout.rs:376-391, case by case."""
+    from dynamo_b200.kernels import KvBlockLayout as KV
+    from dynamo_b200.physical import TransformKernel as T, requires_transform, select_transform_kernel as sel
+    assert sel(KV.OperationalNHD, KV.OperationalNHD) == T.NONE and sel(KV.UniversalTP, KV.UniversalTP) == T.NONE
+    assert sel(KV.OperationalNHD, KV.UniversalTP) == T.BlockToUniversal and sel(KV.OperationalHND, KV.UniversalTP) == T.BlockToUniversal
+    assert sel(KV.OperationalNHD, KV.UniversalPP) == T.BlockToUniversal and sel(KV.OperationalHND, KV.UniversalPP) == T.BlockToUniversal
+    assert sel(KV.UniversalTP, KV.OperationalNHD) == T.UniversalToBlock and sel(KV.UniversalTP, KV.OperationalHND) == T.UniversalToBlock
+    assert sel(KV.UniversalPP, KV.OperationalNHD) == T.UniversalToBlock and sel(KV.UniversalPP, KV.OperationalHND) == T.UniversalToBlock
+    assert sel(KV.OperationalNHD, KV.OperationalHND) == T.OperationalTranspose
+    assert sel(KV.OperationalHND, KV.OperationalNHD) == T.OperationalTranspose
+    assert sel(KV.Unknown, KV.OperationalNHD) == T.Unsupported and sel(KV.OperationalNHD, KV.Unknown) == T.Unsupported
+    assert sel(KV.Custom, KV.OperationalNHD) == T.Unsupported
+    assert sel(KV.UniversalTP, KV.UniversalPP) == T.Unsupported and sel(KV.UniversalPP, KV.UniversalTP) == T.Unsupported  # :87-91 TODO
+    assert sel(KV.Unknown, KV.Unknown) == T.NONE
+    assert not requires_transform(KV.OperationalNHD, KV.OperationalNHD)
+    assert requires_transform(KV.OperationalNHD, KV.UniversalTP) and requires_transform(KV.OperationalHND, KV.OperationalNHD)
+    assert requires_transform(KV.Unknown, KV.OperationalNHD) and requires_transform(KV.OperationalNHD, KV.Unknown)
+    assert not requires_transform(KV.Unknown, KV.Unknown)
+
+
+def test_kv_block_layout_of_a_layout_validates_and_travels_with_the_metadata(mgr):
+    """fully_contiguous.rs:83-88 / layer_separate.rs:91-101 / config.rs:114-140; serialize.rs carries kv_block_layout."""
+    import json
+    from dynamo_b200.kernels import KvBlockLayout as KV
+    cfg = std_cfg(4, num_heads=2)
+    a = np.zeros(cfg.required_bytes(), dtype=np.uint8)
+    fc = mgr.register_fully_contiguous(cfg, a.ctypes.data, a.size, StorageKind.System)
+    assert mgr.kv_block_layout(fc) == KV.Unknown        # builder default
+    mgr.set_kv_block_layout(fc, KV.UniversalTP)
+    assert mgr.kv_block_layout(fc) == KV.UniversalTP
+    # same-process metadata round trip keeps it
+    again = mgr.import_metadata(mgr.export_metadata(fc))
+    assert mgr.kv_block_layout(again) == KV.UniversalTP
+    # the reference's JSON descriptor names it ("kv_block_layout": "UniversalTP")
+    text = mgr.layout_descriptor_json(fc)
+    desc = json.loads(text)
+    assert mgr.kv_block_layout(mgr.import_descriptor_json(text)) == KV.UniversalTP
+    assert "UniversalTP" in json.dumps(desc)
+    # layer-separate layouts only carry operational formats
+    lay = [np.zeros(cfg.required_bytes() // cfg.num_layers, dtype=np.uint8) for _ in range(cfg.num_layers)]
+    lw = mgr.register_layer_separate(cfg, [x.ctypes.data for x in lay], [x.size for x in lay], BlockDimension.BlockIsFirstDim, StorageKind.System)
+    mgr.set_kv_block_layout(lw, KV.OperationalNHD)
+    with pytest.raises(KvbmError) as e:
+        mgr.set_kv_block_layout(lw, KV.UniversalTP)
+    assert e.value.code == ErrorCode.CONFIG and "fully contiguous" in e.value.msg
+    # num_heads is required, and must divide inner_dim
+    plain = mgr.register_fully_contiguous(std_cfg(4), a.ctypes.data, a.size, StorageKind.System)
+    with pytest.raises(KvbmError) as e:
+        mgr.set_kv_block_layout(plain, KV.OperationalNHD)
+    assert "num_heads_required_for_kv_block_layout" in e.value.msg
+    odd = mgr.register_fully_contiguous(std_cfg(4, num_heads=3), a.ctypes.data, a.size, StorageKind.System)
+    with pytest.raises(KvbmError) as e:
+        mgr.set_kv_block_layout(odd, KV.OperationalNHD)
+    assert "inner_dim_must_be_divisible" in e.value.msg
+    with pytest.raises(KvbmError):
+        mgr.set_kv_block_layout(0xdead, KV.OperationalNHD)
+    # layouts whose own formats differ: the transfer is a transformation, not a copy -> needs CUDA here
+    b = np.zeros(cfg.required_bytes(), dtype=np.uint8)
+    nhd = mgr.register_fully_contiguous(cfg, b.ctypes.data, b.size, StorageKind.System)
+    mgr.set_kv_block_layout(nhd, KV.OperationalNHD)
+    with pytest.raises(KvbmError) as e:
+        mgr.execute_transfer(nhd, [0], fc, [1])
+    assert e.value.code == ErrorCode.UNSUPPORTED and "only on the CUDA strategies" in e.value.msg
 
 
 def test_layout_ids_are_reused_and_never_overwrite_a_live_layout(mgr):

@@ -117,3 +117,56 @@ def test_cast_transfer_config3_small():
                 want = table[src.region_bytes(int(s), l, o)]
                 got = dst.region_bytes(int(d), l, o).view(np.uint16)
                 assert np.array_equal(got, want)
+
+
+# ---- KvBlockLayout transforms (kv_block_layout.rs:85-95): the numpy definition vs the pinned K2 / K3 restatement ----
+@pytest.mark.parametrize("layout,kv", [(kats.NHD, O.KV_OPERATIONAL_NHD), (kats.HND, O.KV_OPERATIONAL_HND)])
+@pytest.mark.parametrize("dims", [(3, 2, 4, 5, 8, 2), (2, 1, 16, 8, 64, 2), (1, 2, 3, 1, 16, 4)])
+def test_kv_layout_permute_agrees_with_k2_k3(layout, kv, dims):
+    nl, no, nt, nh, hd, elem = dims
+    row = hd * elem
+    rng = np.random.default_rng(nl * 100 + nh)
+    blk = rng.integers(0, 256, nl * no * nt * nh * row, dtype=np.uint8)
+    chunk = nt * nh * row
+    chunks = [blk[i * chunk:(i + 1) * chunk].copy() for i in range(nl * no)]
+    uni = np.zeros_like(blk)
+    O.universal_from_block([uni], chunks, nh, nl, no, nt, hd, elem, layout)
+    assert np.array_equal(uni, O.kv_layout_permute(blk, kv, O.KV_UNIVERSAL_TP, nl, no, nt, nh, row))
+    back = [np.zeros(chunk, dtype=np.uint8) for _ in range(nl * no)]
+    O.block_from_universal([uni], back, nh, nl, no, nt, hd, elem, layout)
+    assert np.array_equal(np.concatenate(back), O.kv_layout_permute(uni, O.KV_UNIVERSAL_TP, kv, nl, no, nt, nh, row))
+
+
+def test_kv_layout_permute_first_principles_and_layer_ranges():
+    nl, no, nt, nh, row = 3, 2, 4, 5, 16
+    n = nl * no * nt * nh
+    # element e of the NHD block carries its own (l, o, t, h) in its first four bytes
+    blk = np.zeros((nl, no, nt, nh, row), dtype=np.uint8)
+    for l in range(nl):
+        for o in range(no):
+            for t in range(nt):
+                for h in range(nh):
+                    blk[l, o, t, h, :4] = (l, o, t, h)
+    flat = blk.reshape(-1)
+    pp = O.kv_layout_permute(flat, O.KV_OPERATIONAL_NHD, O.KV_UNIVERSAL_PP, nl, no, nt, nh, row).reshape(nl, nh, no, nt, row)
+    hnd = O.kv_layout_permute(flat, O.KV_OPERATIONAL_NHD, O.KV_OPERATIONAL_HND, nl, no, nt, nh, row).reshape(nl, no, nh, nt, row)
+    tp = O.kv_layout_permute(flat, O.KV_OPERATIONAL_NHD, O.KV_UNIVERSAL_TP, nl, no, nt, nh, row).reshape(nh, nl, no, nt, row)
+    for l in range(nl):
+        for o in range(no):
+            for t in range(nt):
+                for h in range(nh):
+                    assert tuple(pp[l, h, o, t, :4]) == (l, o, t, h)
+                    assert tuple(hnd[l, o, h, t, :4]) == (l, o, t, h)
+                    assert tuple(tp[h, l, o, t, :4]) == (l, o, t, h)
+    # every pair composes to the identity
+    for a in O.KV_DIM_ORDER:
+        for b in O.KV_DIM_ORDER:
+            x = O.kv_layout_permute(flat, O.KV_OPERATIONAL_NHD, a, nl, no, nt, nh, row)
+            y = O.kv_layout_permute(x, a, b, nl, no, nt, nh, row)
+            assert np.array_equal(O.kv_layout_permute(y, b, O.KV_OPERATIONAL_NHD, nl, no, nt, nh, row), flat)
+    # a layer range moves only that layer's elements
+    old = np.full(n * row, 0xEE, dtype=np.uint8)
+    part = O.kv_layout_permute(flat, O.KV_OPERATIONAL_NHD, O.KV_UNIVERSAL_TP, nl, no, nt, nh, row, layers=range(1, 2), dst_old=old)
+    part = part.reshape(nh, nl, no, nt, row)
+    assert (part[:, 0] == 0xEE).all() and (part[:, 2] == 0xEE).all()
+    assert np.array_equal(part[:, 1], tp[:, 1])
