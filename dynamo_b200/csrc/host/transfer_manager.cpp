@@ -130,8 +130,28 @@ static int validate_block_transfer(const size_t* src_ids, size_t n_src, const si
 // ---------------------------------------------------------------------------------------------------
 // strategy.rs:138-210 (local-to-local rows).  Device index is ignored exactly like strategy.rs:168.
 // ---------------------------------------------------------------------------------------------------
-static int select_direct_strategy(int src, int dst, const kvbm_transfer_capabilities* caps, kvbm_transfer_plan* out)
+// select_remote_strategy (strategy.rs:213-243): the source is local, the destination another agent's
+static int select_remote_strategy(int src, const kvbm_transfer_capabilities* caps, kvbm_transfer_plan* out)
 {
+  if (src == KVBM_STORAGE_SYSTEM || src == KVBM_STORAGE_PINNED) {
+    *out = kvbm_transfer_plan{0, KVBM_STRATEGY_NIXL_WRITE, 0, KVBM_STRATEGY_INVALID};
+  } else if (src == KVBM_STORAGE_DEVICE) {
+    if (caps && caps->allow_gpu_rdma)
+      *out = kvbm_transfer_plan{0, KVBM_STRATEGY_NIXL_WRITE, 0, KVBM_STRATEGY_INVALID};
+    else
+      *out = kvbm_transfer_plan{1, KVBM_STRATEGY_CUDA_ASYNC_D2H, KVBM_STORAGE_PINNED, KVBM_STRATEGY_NIXL_WRITE};
+  } else {
+    *out = kvbm_transfer_plan{1, KVBM_STRATEGY_NIXL_WRITE, KVBM_STORAGE_PINNED, KVBM_STRATEGY_NIXL_WRITE};  // Disk -> Remote
+  }
+  return KVBM_OK;
+}
+
+static int select_direct_strategy(int src, int dst, const kvbm_transfer_capabilities* caps, kvbm_transfer_plan* out, bool dst_is_remote = false)
+{
+  if (dst_is_remote) {  // strategy.rs:147-150
+    if (src < 0 || src > KVBM_STORAGE_DISK || dst < 0 || dst > KVBM_STORAGE_DISK) return fail(KVBM_ERR, "unknown StorageKind");
+    return select_remote_strategy(src, caps, out);
+  }
   auto direct = [&](int s) {
     *out = kvbm_transfer_plan{0, s, 0, KVBM_STRATEGY_INVALID};
     return KVBM_OK;
@@ -158,6 +178,20 @@ static int select_direct_strategy(int src, int dst, const kvbm_transfer_capabili
   if (src == KVBM_STORAGE_DISK && dst == KVBM_STORAGE_DEVICE)
     return gds ? direct(KVBM_STRATEGY_NIXL_READ) : two_hop(KVBM_STRATEGY_NIXL_READ_FLIPPED, KVBM_STRATEGY_CUDA_ASYNC_H2D);
   return fail(KVBM_ERR, "unreachable strategy");
+}
+
+// select_strategy (strategy.rs:78-108) + select_remote_strategy_v2 (:245-281): locality = whose agent owns the layout
+static int select_strategy(int src, bool src_local, int dst, bool dst_local, const kvbm_transfer_capabilities* caps, kvbm_transfer_plan* out)
+{
+  if (src < 0 || src > KVBM_STORAGE_DISK || dst < 0 || dst > KVBM_STORAGE_DISK) return fail(KVBM_ERR, "unknown StorageKind");
+  if (!src_local && !dst_local) return fail(KVBM_ERR_UNSUPPORTED, "Both src and dst are remote - this is not supported.");
+  if (src_local && dst_local) return select_direct_strategy(src, dst, caps, out);
+  if (src == KVBM_STORAGE_DISK || dst == KVBM_STORAGE_DISK)
+    return fail(KVBM_ERR_UNSUPPORTED, "Neither local nor remote disk transfers are supported over NIXL at this time.");
+  if (!(caps && caps->allow_gpu_rdma) && (src == KVBM_STORAGE_DEVICE || dst == KVBM_STORAGE_DEVICE))
+    return fail(KVBM_ERR_UNSUPPORTED, "GPU RDMA is disabled - this transfer requires GPU RDMA.");
+  *out = kvbm_transfer_plan{0, src_local ? KVBM_STRATEGY_NIXL_WRITE : KVBM_STRATEGY_NIXL_READ_FLIPPED, 0, KVBM_STRATEGY_INVALID};
+  return KVBM_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -682,6 +716,8 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
     rc = validate_block_transfer(src_ids[d], n, dst_ids[d], n, S->cfg.num_blocks, D[d]->cfg.num_blocks, src_h == dst_h[d]);
     if (rc) return rc;
   }
+  for (int d = 0; d < nd; ++d)  // select_strategy, strategy.rs:86-90
+    if (S->remote && D[d]->remote) return fail(KVBM_ERR_UNSUPPORTED, "Both src and dst are remote - this is not supported.");
   // effective_src_layout / effective_dst_layout (executor/mod.rs:103-119): the option overrides the layout's own format.
   // The reference rejects every pair that needs a transformation (validate_layout_compatibility, transfer/mod.rs:128-147);
   // here the pairs select_transform_kernel names -- plus UniversalTP <-> UniversalPP, its TODO -- run as ONE permuting launch.
@@ -826,6 +862,29 @@ extern "C" int kvbm_select_direct_strategy(int src_kind, int dst_kind, const kvb
 {
   if (!out) return fail(KVBM_ERR, "null plan");
   return select_direct_strategy(src_kind, dst_kind, caps, out);
+}
+
+extern "C" int kvbm_select_direct_strategy_remote(int src_kind, int dst_kind, int dst_is_remote, const kvbm_transfer_capabilities* caps,
+                                                  kvbm_transfer_plan* out)
+{
+  if (!out) return fail(KVBM_ERR, "null plan");
+  return select_direct_strategy(src_kind, dst_kind, caps, out, dst_is_remote != 0);
+}
+
+extern "C" int kvbm_select_strategy(int src_kind, int src_is_local, int dst_kind, int dst_is_local, const kvbm_transfer_capabilities* caps,
+                                    kvbm_transfer_plan* out)
+{
+  if (!out) return fail(KVBM_ERR, "null plan");
+  return select_strategy(src_kind, src_is_local != 0, dst_kind, dst_is_local != 0, caps, out);
+}
+
+extern "C" int kvbm_manager_select_strategy(kvbm_transfer_manager* m, kvbm_layout_handle src, kvbm_layout_handle dst, kvbm_transfer_plan* out)
+{
+  if (!m || !out) return fail(KVBM_ERR, "null argument");
+  std::lock_guard<std::mutex> lk(m->mu);
+  Layout *S = m->find(src), *D = m->find(dst);
+  if (!S || !D) return fail(KVBM_ERR_HANDLE, "invalid layout handle");
+  return select_strategy(S->storage, !S->remote, D->storage, !D->remote, &m->caps, out);
 }
 
 extern "C" int kvbm_validate_block_transfer(const size_t* src_ids, size_t n_src, const size_t* dst_ids, size_t n_dst,

@@ -203,6 +203,7 @@ EXPORTED_SYMBOLS = [
     "kvbm_manager_export_serialized_layout", "kvbm_manager_import_serialized_layout", "kvbm_layout_descriptor_json",
     "kvbm_manager_import_descriptor_json", "kvbm_select_transform_kernel", "kvbm_kv_layout_requires_transform",
     "kvbm_manager_set_kv_block_layout", "kvbm_manager_kv_block_layout",
+    "kvbm_select_direct_strategy_remote", "kvbm_select_strategy", "kvbm_manager_select_strategy",
     "kvbm_mc_supported", "kvbm_mc_group_create", "kvbm_mc_group_export_fd", "kvbm_mc_group_import_fd",
     "kvbm_mc_group_size", "kvbm_mc_group_add_device", "kvbm_mc_group_bind_local", "kvbm_mc_group_bind_addr", "kvbm_mc_group_map",
     "kvbm_mc_group_destroy",
@@ -228,6 +229,9 @@ def lib() -> C.CDLL:
         L.kvbm_layout_bytes_per_block.argtypes = [P(_CConfig)]
         L.kvbm_layout_bytes_per_block.restype = sz
         L.kvbm_select_direct_strategy.argtypes = [i, i, P(_CCaps), P(_CPlan)]
+        L.kvbm_select_direct_strategy_remote.argtypes = [i, i, i, P(_CCaps), P(_CPlan)]
+        L.kvbm_select_strategy.argtypes = [i, i, i, i, P(_CCaps), P(_CPlan)]
+        L.kvbm_manager_select_strategy.argtypes = [vp, u64, u64, P(_CPlan)]
         L.kvbm_validate_block_transfer.argtypes = [P(sz), sz, P(sz), sz, sz, sz, i]
         L.kvbm_manager_create.argtypes = [i, u64, P(vp)]
         L.kvbm_manager_destroy.argtypes = [vp]
@@ -309,15 +313,29 @@ class _NpView:
         return C.cast(self.addr, C.POINTER(C.c_size_t))
 
 
-def select_direct_strategy(src: StorageKind, dst: StorageKind, allow_gds: bool = False,
-                           allow_gpu_rdma: bool = False) -> TransferPlan:
-    plan = _CPlan()
-    caps = _CCaps(int(allow_gds), int(allow_gpu_rdma))
-    _check(lib().kvbm_select_direct_strategy(int(src), int(dst), C.byref(caps), C.byref(plan)))
+def _plan(plan: _CPlan) -> TransferPlan:
     if plan.two_hop:
         return TransferPlan(True, TransferStrategy(plan.first), StorageKind(plan.bounce_location),
                             TransferStrategy(plan.second))
     return TransferPlan(False, TransferStrategy(plan.first))
+
+
+def select_direct_strategy(src: StorageKind, dst: StorageKind, allow_gds: bool = False,
+                           allow_gpu_rdma: bool = False, dst_is_remote: bool = False) -> TransferPlan:
+    """select_direct_strategy(src, dst, dst_is_remote, capabilities) -- transfer/strategy.rs:138-243."""
+    plan = _CPlan()
+    caps = _CCaps(int(allow_gds), int(allow_gpu_rdma))
+    _check(lib().kvbm_select_direct_strategy_remote(int(src), int(dst), int(dst_is_remote), C.byref(caps), C.byref(plan)))
+    return _plan(plan)
+
+
+def select_strategy(src: StorageKind, src_is_local: bool, dst: StorageKind, dst_is_local: bool, allow_gds: bool = False,
+                    allow_gpu_rdma: bool = False) -> TransferPlan:
+    """select_strategy + select_remote_strategy_v2 -- transfer/strategy.rs:78-108,245-281."""
+    plan = _CPlan()
+    caps = _CCaps(int(allow_gds), int(allow_gpu_rdma))
+    _check(lib().kvbm_select_strategy(int(src), int(src_is_local), int(dst), int(dst_is_local), C.byref(caps), C.byref(plan)))
+    return _plan(plan)
 
 
 class TransformKernel(enum.IntEnum):
@@ -417,6 +435,12 @@ class TransferManager:
         if rc < 0:
             raise KvbmError(ErrorCode.HANDLE, "invalid handle")
         return bool(rc)
+
+    def select_strategy(self, src: int, dst: int) -> TransferPlan:
+        """The plan select_strategy (strategy.rs:78-108) gives for two of this manager's layouts."""
+        plan = _CPlan()
+        _check(lib().kvbm_manager_select_strategy(self._h, src, dst, C.byref(plan)))
+        return _plan(plan)
 
     def set_kv_block_layout(self, handle: int, kv_layout: "kernels.KvBlockLayout") -> None:
         """The format of one block of this layout (builder `.kv_block_layout()` / `.inner_shape()` in the reference).  A transfer

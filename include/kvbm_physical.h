@@ -135,6 +135,15 @@ size_t kvbm_layout_bytes_per_block(const kvbm_layout_config* cfg);  /* config.rs
 /* select_direct_strategy (strategy.rs:138-210).  Device ids are ignored exactly as strategy.rs:168 does. */
 int kvbm_select_direct_strategy(int src_kind, int dst_kind, const kvbm_transfer_capabilities* caps,
                                 kvbm_transfer_plan* out);
+/* The same with select_direct_strategy's `dst_is_remote` argument (strategy.rs:138-150, select_remote_strategy :213-243): a local
+ * source to another agent's memory is NixlWrite, staged through Pinned for Device (without GPU RDMA) and Disk. */
+int kvbm_select_direct_strategy_remote(int src_kind, int dst_kind, int dst_is_remote, const kvbm_transfer_capabilities* caps,
+                                       kvbm_transfer_plan* out);
+/* select_strategy (strategy.rs:78-108) with select_remote_strategy_v2 (:245-281): both local = the table above; exactly one
+ * side local = NixlWrite (push) or NixlReadFlipped (pull) -- executed here as the push / pull launch over the IPC-mapped pool;
+ * both remote, Disk, or a Device side without allow_gpu_rdma = the reference's errors. */
+int kvbm_select_strategy(int src_kind, int src_is_local, int dst_kind, int dst_is_local, const kvbm_transfer_capabilities* caps,
+                         kvbm_transfer_plan* out);
 /* validate_block_transfer, debug flavour (validation.rs:168-225). */
 int kvbm_validate_block_transfer(const size_t* src_ids, size_t n_src, const size_t* dst_ids, size_t n_dst,
                                  size_t src_num_blocks, size_t dst_num_blocks, int same_layout);
@@ -184,6 +193,9 @@ int kvbm_manager_import_serialized_layout(kvbm_transfer_manager* m, const void* 
                                           size_t cap, size_t* n_out);
 int kvbm_layout_descriptor_json(kvbm_transfer_manager* m, kvbm_layout_handle h, char* buf, size_t cap, size_t* len);
 int kvbm_manager_import_descriptor_json(kvbm_transfer_manager* m, const char* json, size_t len, kvbm_layout_handle* out);
+
+/* select_strategy for two registered layouts (local = registered or imported in-process; remote = imported from another process) */
+int kvbm_manager_select_strategy(kvbm_transfer_manager* m, kvbm_layout_handle src, kvbm_layout_handle dst, kvbm_transfer_plan* out);
 
 /* TransformKernel (transfer/executor/mod.rs:27-41) as select_transform_kernel (:46-100) returns it. */
 enum {

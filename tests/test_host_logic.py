@@ -194,6 +194,38 @@ def test_two_hop_and_gds_strategies():
         assert e.value.code == ErrorCode.UNSUPPORTED and "not supported" in e.value.msg
 
 
+def test_remote_strategies():
+    """strategy.rs:443-503 (select_direct_strategy with dst_is_remote) and select_strategy / select_remote_strategy_v2 (:78-108, 245-281)."""
+    W, RF = TransferStrategy.NixlWrite, TransferStrategy.NixlReadFlipped
+    # test_host_to_remote
+    for k in (S, Pn):
+        p = P.select_direct_strategy(k, k, dst_is_remote=True)
+        assert not p.two_hop and p.first == W
+    # test_device_to_remote_without_rdma / with_rdma
+    p = P.select_direct_strategy(D, S, dst_is_remote=True)
+    assert p.two_hop and (p.first, p.bounce_location, p.second) == (TransferStrategy.CudaAsyncD2H, Pn, W)
+    p = P.select_direct_strategy(D, D, allow_gpu_rdma=True, dst_is_remote=True)
+    assert not p.two_hop and p.first == W
+    # test_disk_to_remote
+    p = P.select_direct_strategy(Dk, S, dst_is_remote=True)
+    assert p.two_hop and (p.first, p.bounce_location, p.second) == (W, Pn, W)
+    # select_strategy: both local = the direct table
+    assert P.select_strategy(D, True, D, True).first == TransferStrategy.CudaAsyncD2D
+    assert P.select_strategy(Pn, True, S, True).first == TransferStrategy.Memcpy
+    # exactly one side local: push = NixlWrite, pull = NixlReadFlipped
+    assert P.select_strategy(Pn, True, Pn, False).first == W
+    assert P.select_strategy(S, False, Pn, True).first == RF
+    assert P.select_strategy(D, True, D, False, allow_gpu_rdma=True).first == W
+    assert P.select_strategy(D, False, D, True, allow_gpu_rdma=True).first == RF
+    for args, text in [((D, False, D, False), "Both src and dst are remote"),
+                       ((Dk, True, S, False), "Neither local nor remote disk transfers are supported over NIXL"),
+                       ((S, False, Dk, True), "Neither local nor remote disk transfers are supported over NIXL"),
+                       ((D, True, S, False), "GPU RDMA is disabled"), ((Pn, False, D, True), "GPU RDMA is disabled")]:
+        with pytest.raises(KvbmError) as e:
+            P.select_strategy(*args)
+        assert e.value.code == ErrorCode.UNSUPPORTED and text in e.value.msg
+
+
 # ------------------------------------------------------------------ validation.rs
 def test_validate_block_transfer_codes():
     P.validate_block_transfer([0, 1], [2, 3], 4, 4)
