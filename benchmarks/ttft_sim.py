@@ -68,22 +68,41 @@ def fit_ours():
     return max(0.0, float(icpt)), 1e-6 / slope, f"fit over {len(pts)} measured 1->1 pushes"
 
 
+def _bench_line(name):
+    for line in open(os.path.join(ROOT, "profiles", name)):
+        if line.startswith("{"):
+            return json.loads(line)
+    raise ValueError(name)
+
+
 def cpu_rate():
-    path = os.path.join(ROOT, "profiles", "r01_bench_n1_b.json")
+    for name in ("r02_bench_n1.json", "r01_bench_n1_b.json"):
+        try:
+            return float(_bench_line(name)["cpu_baseline"]["value"]), f"profiles/{name} cpu_baseline"
+        except Exception:
+            continue
+    return 47.0, "fallback"
+
+
+def pull_rate():
+    """round 2: the decode GPU pulls (reads the prefill pool over NVLink) -- measured 1 -> 1 rate of the bench line"""
     try:
-        d = json.loads(open(path).read().strip().splitlines()[-1])
-        return float(d["cpu_baseline"]["value"]), "profiles/r01_bench_n1_b.json cpu_baseline"
+        return float(_bench_line("r02_bench_n2_pull.json")["value"]), "profiles/r02_bench_n2_pull.json"
     except Exception:
-        return 47.0, "fallback"
+        return None, "no pull bench line"
 
 
 LAT_MS, BW_GBS, ours_src = fit_ours()
 CPU_GBS, cpu_src = cpu_rate()
+PULL_GBS, pull_src = pull_rate()
 PLANES = {
     "mocker64": dict(serial=False, ms=lambda b: b / 64e9 * 1e3),
     "cpu": dict(serial=True, ms=lambda b: b / (CPU_GBS * 1e9) * 1e3),
     "ours": dict(serial=True, ms=lambda b: (LAT_MS + b / (BW_GBS * 1e9) * 1e3) if b else 0.0),
 }
+if PULL_GBS:
+    # same launch latency as the fitted push, the pull direction's bandwidth; the prefill GPU's port stays the shared resource
+    PLANES["ours_pull"] = dict(serial=True, ms=lambda b: (LAT_MS + b / (PULL_GBS * 1e9) * 1e3) if b else 0.0)
 
 # ---- request trace (identical for every data plane) ----
 rng = np.random.default_rng(a.seed)
@@ -160,7 +179,8 @@ print(f"{c['requests']} requests, Poisson {c['rate']}/s, prompts {c['prompt_toke
       f"{c['prefill_tok_per_s']:.0f} tok/s, first decode step {c['first_decode_ms']} ms, {c['kv_bytes_per_token'] // 1024} KiB of KV per token.")
 print(f"Decode worker = best prefix overlap in the RadixTree (libkvbm_router.so); prefix-hit rate that results: "
       f"{res['planes']['ours']['prefix_hit_rate']:.1%} of blocks never move.\n")
-print(f"`ours` = {LAT_MS * 1e3:.0f} us + bytes / {BW_GBS:.0f} GB/s ({ours_src}); `cpu` = {CPU_GBS:.1f} GB/s ({cpu_src}).\n")
+print(f"`ours` = {LAT_MS * 1e3:.0f} us + bytes / {BW_GBS:.0f} GB/s ({ours_src}); `cpu` = {CPU_GBS:.1f} GB/s ({cpu_src})"
+      + (f"; `ours_pull` = the same latency + bytes / {PULL_GBS:.0f} GB/s ({pull_src})" if PULL_GBS else "") + ".\n")
 print("| data plane | hand-off p50 / p90 / p99 (ms) | TTFT p50 (ms) | TTFT p90 | TTFT p99 | TTFT p50 above `ours` (ms) |")
 print("|---|---|---:|---:|---:|---:|")
 for name, r in res["planes"].items():
