@@ -23,14 +23,16 @@ p.add_argument("--heads", type=int, default=8)
 p.add_argument("--head-dim", type=int, default=128)
 p.add_argument("--page", type=int, default=16)
 p.add_argument("--iters", type=int, default=20)
-p.add_argument("--peer", type=int, default=-1, help="destination pool on this GPU (launch on GPU 0 = push); -1 = same GPU")
+p.add_argument("--peer", type=int, default=-1, help="put one pool on this GPU (the launch stays on GPU 0); -1 = same GPU")
+p.add_argument("--peer-side", choices=["dst", "src"], default="dst", help="dst: universal pool on the peer (push); src: engine pool on the peer (pull)")
 a = p.parse_args()
 nl, no, nt, nh, hd, elem = a.layers, 2, a.page, a.heads, a.head_dim, 2
 row, region = hd * elem, nt * nh * hd * elem
 nb, n = a.pool, a.blocks
 dev = torch.device("cuda:0")
 torch.cuda.set_device(0)
-ddev = torch.device(f"cuda:{a.peer}") if a.peer >= 0 else dev
+ddev = torch.device(f"cuda:{a.peer}") if a.peer >= 0 and a.peer_side == "dst" else dev
+sdev = torch.device(f"cuda:{a.peer}") if a.peer >= 0 and a.peer_side == "src" else dev
 if a.peer >= 0:
     import ctypes
     rt = ctypes.CDLL("libcudart.so")
@@ -42,7 +44,8 @@ except Exception:
     pass
 
 # engine pool: layer-separate, block-is-second-dim (vLLM), NHD inside a region; universal pool: fully contiguous
-op = [torch.randint(0, 256, (no * nb * region,), dtype=torch.uint8, device=dev) for _ in range(nl)]
+op = [torch.randint(0, 256, (no * nb * region,), dtype=torch.uint8, device=sdev) for _ in range(nl)]
+torch.cuda.synchronize(sdev)
 uni = torch.zeros(nb * nl * no * region, dtype=torch.uint8, device=ddev)
 op_base = torch.tensor([t.data_ptr() for t in op], dtype=torch.int64, device=dev)
 op_desc = K.PagedLayout(op_base.data_ptr(), region, nb * region, region, nl, no, nb)
@@ -110,6 +113,7 @@ legacy_flow()
 torch.cuda.synchronize()
 a_ref = uni.clone()
 uni.zero_()
+torch.cuda.synchronize(ddev)      # the zero fill runs on the pool's own device: order it before the launch on GPU 0
 paged()
 torch.cuda.synchronize()
 same = bool(torch.equal(a_ref, uni))
@@ -127,7 +131,7 @@ def wall(fn, iters=a.iters):
 
 
 res = {"geometry": {"blocks": n, "layers": nl, "outer": no, "page": nt, "heads": nh, "head_dim": hd, "elem": elem, "MiB_moved": moved / 2**20},
-       "peer": a.peer, "paged_equals_legacy": same}
+       "peer": a.peer, "peer_side": a.peer_side if a.peer >= 0 else None, "paged_equals_legacy": same}
 for name, fn in (("paged_permute_to_universal", paged), ("paged_permute_from_universal", paged_back), ("legacy_k2_kernel_only", legacy_kernel_only),
                  ("plain_paged_copy", plain_copy)):
     ms = timed(fn)
