@@ -471,3 +471,62 @@ def test_gate_on_the_stream_when_nothing_may_spin():
     assert done.tolist() == [4] and layer_done.tolist() == [4] * nl and int(host_word[0]) == 77
     assert ws.tolist() == [0] * K.sync_workspace_words(nl)
     check_against_oracle(src_h, dst_h, dst_p, sid, did)
+
+
+def test_launches_can_be_captured_into_a_cuda_graph_and_replayed():
+    """An engine that runs its decode step from a CUDA graph can capture the hand-off with it: every entry point is plain
+    stream work (kernel launches only; with a caller workspace the tile scheduler stays dynamic, without one a capturing
+    stream gets the static split because the library's pool is event-guarded).  Replays must move the CURRENT bytes."""
+    nl, no, nt, nh, hd = 4, 2, 16, 4, 64
+    nb, n = 24, 16
+    mk = lambda fill=0: make_layout(O.LW, nb, nl=nl, no=no, page=nt, inner=nh * hd, dt=2, block_dim=O.BLOCK_IS_SECOND_DIM, fill=fill)
+    src_h, dst_a, dst_b = mk(), mk(), mk()
+    uni_h = make_layout(O.FC, nb, nl=nl, no=no, page=nt, inner=nh * hd, dt=2)
+    randomize(src_h, 5)
+    src_p, a_p, b_p, u_p = DevicePool(src_h), DevicePool(dst_a), DevicePool(dst_b), DevicePool(uni_h)
+    rng = np.random.default_rng(8)
+    sid, did = rng.permutation(nb)[:n], rng.permutation(nb)[:n]
+    s, d = ids_dev(sid), ids_dev(did)
+    ws = torch.zeros(K.sync_workspace_words(nl), dtype=torch.int32, device="cuda:0")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+
+    def enqueue(sp):
+        o = K.PagedCopyOpts(epoch=3, sync_workspace=ws.data_ptr())
+        assert K.paged_copy(src_p.desc, [K.PagedDst(a_p.desc, s.data_ptr(), d.data_ptr(), flag.data_ptr(), 0)], n, 0, nl, 0, o, sp) == 0
+        assert K.paged_copy(src_p.desc, [K.PagedDst(b_p.desc, s.data_ptr(), d.data_ptr(), 0, 0)], n, 0, nl, 0, None, sp) == 0
+        assert K.paged_permute(K.PermuteSide(src_p.desc, s.data_ptr(), int(K.KvBlockLayout.OperationalNHD)),
+                               K.PermuteSide(u_p.desc, d.data_ptr(), int(K.KvBlockLayout.UniversalTP)), n, 0, nl, nh, nt, hd * 2, stream=sp) == 0
+
+    enqueue(stream_ptr())            # warm-up outside the capture: kernels loaded, attributes set
+    torch.cuda.synchronize()
+    for p in (a_p, b_p, u_p):
+        for t in p.bufs:
+            t.zero_()
+    flag.zero_()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.graph(graph, stream=side):
+        enqueue(stream_ptr(torch.cuda.current_stream()))
+    torch.cuda.synchronize()
+    assert int(flag.item()) == 0 and not any(bool(t.any()) for t in a_p.bufs)      # captured, not executed
+    for round_ in range(2):
+        if round_:                                                              # new bytes in the same source pool
+            randomize(src_h, 99)
+            for t, b in zip(src_p.bufs, src_h.buffers):
+                t.copy_(torch.from_numpy(b))
+            for p in (a_p, b_p, u_p):
+                for t in p.bufs:
+                    t.zero_()
+            flag.zero_()
+            torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert int(flag.item()) == 3 and ws.tolist() == [0] * K.sync_workspace_words(nl)
+        want = {int(b): src_h.block_checksum(int(a)) for a, b in zip(sid, did)}
+        for p, h in ((a_p, dst_a), (b_p, dst_b)):
+            p.download()
+            assert h.block_checksums(did) == want
+        u_p.download()
+        for a, b in zip(sid, did):
+            blk = O.kv_layout_permute(O.read_logical_block(src_h, int(a)), O.KV_OPERATIONAL_NHD, O.KV_UNIVERSAL_TP, nl, no, nt, nh, hd * 2)
+            assert np.array_equal(O.read_logical_block(uni_h, int(b)), blk)
