@@ -200,6 +200,7 @@ static int select_strategy(int src, bool src_local, int dst, bool dst_local, con
 static bool kv_known(int k) { return k >= KVBM_KV_UNIVERSAL_TP && k <= KVBM_KV_CUSTOM; }
 static bool kv_requires_transform(int a, int b)
 {
+  if (a == KVBM_KV_CUSTOM || b == KVBM_KV_CUSTOM) return true;  // the int does not carry Custom's dimension order: never assume equality
   if (kv_known(a) && kv_known(b)) return a != b;  // dim orders of the four named formats are pairwise different
   if (!kv_known(a) && !kv_known(b)) return false; // Unknown -> Unknown: compatible (the reference warns)
   return true;                                    // Unknown <-> known: conservative

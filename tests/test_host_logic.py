@@ -556,6 +556,7 @@ def test_select_transform_kernel_and_requires_transform_kats():
     assert sel(KV.OperationalHND, KV.OperationalNHD) == T.OperationalTranspose
     assert sel(KV.Unknown, KV.OperationalNHD) == T.Unsupported and sel(KV.OperationalNHD, KV.Unknown) == T.Unsupported
     assert sel(KV.Custom, KV.OperationalNHD) == T.Unsupported
+    assert sel(KV.Custom, KV.Custom) == T.Unsupported     # the C enum does not carry Custom's dimension order: never assumed equal
     assert sel(KV.UniversalTP, KV.UniversalPP) == T.Unsupported and sel(KV.UniversalPP, KV.UniversalTP) == T.Unsupported  # :87-91 TODO
     assert sel(KV.Unknown, KV.Unknown) == T.NONE
     assert not requires_transform(KV.OperationalNHD, KV.OperationalNHD)
