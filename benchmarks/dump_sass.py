@@ -12,7 +12,8 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "dynamo_b200", "libkvbm_kernels.so")
 WANT = {"paged_copy_kernelILi0": "paged_copy_cast0", "paged_copy_kernelILi1": "paged_copy_fp8_to_bf16", "paged_copy_kernelILi2": "paged_copy_bf16_to_fp8",
-        "pair_copy_kernel": "pair_copy_k1", "permute_rows_kernelILb1": "permute_rows_to_universal", "permute_rows_kernelILb0": "permute_rows_from_universal"}
+        "pair_copy_kernel": "pair_copy_k1", "permute_rows_kernelILb1": "permute_rows_to_universal", "permute_rows_kernelILb0": "permute_rows_from_universal",
+        "paged_permute_kernel": "paged_permute"}
 KEYS = ["UBLKCP.S.G", "UBLKCP.G.S", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "SYNCS.ARRIVE", "UTMACMDFLUSH", "FENCE.VIEW.ASYNC",
             "F2FP", "ATOMG", "LDG.E.NA.128", "STG.E.NA.128", "LDS.128", "STS.128", "NANOSLEEP", "SHFL"]
 
