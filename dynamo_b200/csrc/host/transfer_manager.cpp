@@ -1113,7 +1113,26 @@ extern "C" int kvbm_manager_export_metadata(kvbm_transfer_manager* m, kvbm_layou
   return KVBM_OK;
 }
 
+static int import_metadata_impl(kvbm_transfer_manager* m, const void* buf, size_t len, const void* const* local_bases, size_t num_local_bases,
+                                kvbm_layout_handle* out);
+
 extern "C" int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void* buf, size_t len, kvbm_layout_handle* out)
+{
+  return import_metadata_impl(m, buf, len, nullptr, 0, out);
+}
+
+// Host pools of another process that THIS process has mapped itself (POSIX / SysV shared memory, a hugetlbfs file, memory
+// shared across fork): the importer names its own view of every allocation.  The CPU twin of the CUDA-IPC mapping above --
+// what makes BASELINE configs[0] (two worker processes, CPU memcpy hand-off) a one-sided push like the NVLink path.
+extern "C" int kvbm_manager_import_metadata_mapped(kvbm_transfer_manager* m, const void* buf, size_t len, const void* const* local_bases,
+                                                   size_t num_local_bases, kvbm_layout_handle* out)
+{
+  if (!local_bases || num_local_bases == 0) return fail(KVBM_ERR, "local_bases: one address per allocation of the layout");
+  return import_metadata_impl(m, buf, len, local_bases, num_local_bases, out);
+}
+
+static int import_metadata_impl(kvbm_transfer_manager* m, const void* buf, size_t len, const void* const* local_bases, size_t num_local_bases,
+                                kvbm_layout_handle* out)
 {
   if (!m || !buf || !out) return fail(KVBM_ERR, "null argument");
   if (len < sizeof(BlobHeader)) return fail(KVBM_ERR, "metadata blob truncated");
@@ -1145,6 +1164,12 @@ extern "C" int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void
     sizes[i] = ba.size;
     if (same_process) {
       bases[i] = ba.addr;  // same address space (peer access is enabled with kvbm_manager_enable_peer_access)
+    } else if (!ba.has_ipc && local_bases) {
+      if (hd.storage == KVBM_STORAGE_DEVICE) return fail(KVBM_ERR_UNSUPPORTED, "device allocations travel as CUDA IPC handles, not as caller-provided mappings");
+      if (num_local_bases != hd.n_allocs)
+        return fail(KVBM_ERR, "local_bases has " + std::to_string(num_local_bases) + " entries, the layout has " + std::to_string(hd.n_allocs) + " allocations");
+      if (!local_bases[i]) return fail(KVBM_ERR, "null local mapping for allocation " + std::to_string(i));
+      bases[i] = reinterpret_cast<uintptr_t>(local_bases[i]);  // this process's own mapping of the peer's shared memory
     } else if (!ba.has_ipc) {
       // Another process's System / Pinned pool (or device memory that could not be exported): its virtual addresses mean
       // nothing here.  The layout is registered as a DESCRIPTOR (geometry, handle, memory_region arithmetic) that no

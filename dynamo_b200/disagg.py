@@ -57,8 +57,10 @@ class HandoffGroup:
         self.roles = assign_roles(world, topology)
         self.remote: Dict[int, int] = {}     # destination rank -> handle usable from this process
 
-    def publish(self, local_dst_handle: Optional[int]) -> Dict[int, int]:
-        """Collective: every rank contributes the metadata of the pool it receives into (or None)."""
+    def publish(self, local_dst_handle: Optional[int], local_views: Optional[Dict[int, Sequence[int]]] = None) -> Dict[int, int]:
+        """Collective: every rank contributes the metadata of the pool it receives into (or None).
+        `local_views[rank]` = this process's own mappings (one address per allocation) of that rank's HOST pool when the pools
+        live in shared memory; device pools travel as CUDA IPC handles inside the metadata and need nothing here."""
         blob = self.mgr.export_metadata(local_dst_handle) if local_dst_handle is not None else b""
         if self.world == 1:
             blobs = [blob]
@@ -73,7 +75,7 @@ class HandoffGroup:
             else:
                 if not blobs[dst]:
                     raise RuntimeError(f"rank {dst} published no layout")
-                self.remote[dst] = self.mgr.import_metadata(blobs[dst])
+                self.remote[dst] = self.mgr.import_metadata(blobs[dst], (local_views or {}).get(dst))
         return self.remote
 
     def push(self, src_handle: int, src_block_ids: Sequence[Sequence[int]], dst_block_ids: Sequence[Sequence[int]],

@@ -197,7 +197,7 @@ EXPORTED_SYMBOLS = [
     "kvbm_select_direct_strategy", "kvbm_validate_block_transfer", "kvbm_manager_create", "kvbm_manager_destroy",
     "kvbm_manager_register_fully_contiguous", "kvbm_manager_register_layer_separate", "kvbm_manager_unregister",
     "kvbm_layout_memory_region", "kvbm_layout_is_fully_contiguous", "kvbm_manager_enable_peer_access",
-    "kvbm_manager_export_metadata", "kvbm_manager_import_metadata", "kvbm_manager_execute_transfer",
+    "kvbm_manager_export_metadata", "kvbm_manager_import_metadata", "kvbm_manager_import_metadata_mapped", "kvbm_manager_execute_transfer",
     "kvbm_manager_execute_fanout", "kvbm_notification_is_complete", "kvbm_notification_wait",
     "kvbm_manager_bytes_moved", "kvbm_manager_h2d_bytes", "kvbm_manager_set_capabilities",
     "kvbm_manager_export_serialized_layout", "kvbm_manager_import_serialized_layout", "kvbm_layout_descriptor_json",
@@ -244,6 +244,7 @@ def lib() -> C.CDLL:
         L.kvbm_manager_enable_peer_access.argtypes = [vp, i]
         L.kvbm_manager_export_metadata.argtypes = [vp, u64, vp, sz, P(sz)]
         L.kvbm_manager_import_metadata.argtypes = [vp, vp, sz, P(u64)]
+        L.kvbm_manager_import_metadata_mapped.argtypes = [vp, vp, sz, P(vp), sz, P(u64)]
         # the id lists are `const size_t*`; declared void* so a raw address (numpy buffer) passes without a ctypes cast
         L.kvbm_manager_execute_transfer.argtypes = [vp, u64, vp, u64, vp, sz, P(_COptions), P(u64)]
         L.kvbm_manager_execute_fanout.argtypes = [vp, u64, i, P(u64), P(P(sz)), P(P(sz)), sz, i, P(_COptions), P(u64)]
@@ -463,10 +464,16 @@ class TransferManager:
         _check(lib().kvbm_manager_export_metadata(self._h, handle, buf, n.value, C.byref(n)))
         return buf.raw[:n.value]
 
-    def import_metadata(self, blob: bytes) -> int:
+    def import_metadata(self, blob: bytes, local_bases: Optional[Sequence[int]] = None) -> int:
+        """`local_bases`: this process's own mappings of another process's HOST pool (shared memory), one address per
+        allocation; without it a foreign host pool is imported as a descriptor only."""
         out = C.c_uint64()
         buf = C.create_string_buffer(blob, len(blob))
-        _check(lib().kvbm_manager_import_metadata(self._h, buf, len(blob), C.byref(out)))
+        if local_bases is None:
+            _check(lib().kvbm_manager_import_metadata(self._h, buf, len(blob), C.byref(out)))
+        else:
+            arr = (C.c_void_p * max(1, len(local_bases)))(*[int(b) for b in local_bases])
+            _check(lib().kvbm_manager_import_metadata_mapped(self._h, buf, len(blob), arr, len(local_bases), C.byref(out)))
         return out.value
 
     # -- the reference's wire formats (SURVEY.md 8 f3) ----------------------------------------------

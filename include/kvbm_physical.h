@@ -176,6 +176,12 @@ int kvbm_manager_enable_peer_access(kvbm_transfer_manager* m, int peer_device);
 int kvbm_manager_export_metadata(kvbm_transfer_manager* m, kvbm_layout_handle h, void* buf, size_t cap,
                                  size_t* len);
 int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void* buf, size_t len, kvbm_layout_handle* out);
+/* The same for HOST pools (System / Pinned) of another process that this process has mapped itself -- shared memory, a file
+ * mapping, memory shared across fork: local_bases[i] is this process's address of the layout's i-th allocation (1 for fully
+ * contiguous, num_layers for layer-separate).  Without it such a layout is imported as a descriptor only (no transfer may touch
+ * it).  The CPU twin of the CUDA-IPC mapping: BASELINE configs[0]'s two-process memcpy hand-off is a one-sided push too. */
+int kvbm_manager_import_metadata_mapped(kvbm_transfer_manager* m, const void* buf, size_t len, const void* const* local_bases,
+                                        size_t num_local_bases, kvbm_layout_handle* out);
 
 /* The reference's own wire formats for the handshake:
  *   kvbm_manager_export_serialized_layout / import_serialized_layout = TransferManager::export_metadata / import_metadata

@@ -496,6 +496,24 @@ def test_remote_host_layout_without_mapping_is_descriptor_only(mgr):
         with pytest.raises(KvbmError) as e:
             mgr.execute_transfer(a, [0], b, [1])
         assert e.value.code == ErrorCode.UNSUPPORTED and "not addressable" in e.value.msg
+    # ... unless the importer names its OWN mapping of that memory (shared memory between worker processes): then the layout
+    # is a usable remote -- a push into it is select_strategy's NixlWrite, executed as the memcpy it is on one host
+    view = np.zeros(cfg.required_bytes(), dtype=np.uint8)               # stands for this process's mapping of the peer's pool
+    mapped = mgr.import_metadata(_blob_with_identity(blob, me ^ (0x5a5a << 32)), local_bases=[view.ctypes.data])
+    buf[:] = np.arange(buf.size, dtype=np.uint64).astype(np.uint8)
+    mgr.execute_transfer(local, [2], mapped, [3])
+    bpb = cfg.required_bytes() // cfg.num_blocks
+    assert np.array_equal(view[3 * bpb:4 * bpb], buf[2 * bpb:3 * bpb]) and not view[:3 * bpb].any()
+    plan = mgr.select_strategy(local, mapped)
+    assert not plan.two_hop and plan.first == TransferStrategy.NixlWrite
+    assert mgr.select_strategy(mapped, local).first == TransferStrategy.NixlReadFlipped
+    assert mgr.select_strategy(local, same).first == TransferStrategy.Memcpy
+    with pytest.raises(KvbmError) as e:                                 # both sides another process's: the reference's error
+        mgr.execute_transfer(mapped, [0], mapped, [1])
+    assert "Both src and dst are remote" in e.value.msg
+    with pytest.raises(KvbmError) as e:                                 # one address per allocation
+        mgr.import_metadata(_blob_with_identity(blob, me ^ (0x5a5a << 32)), local_bases=[view.ctypes.data, view.ctypes.data])
+    assert "allocations" in e.value.msg
 
 
 def test_two_hop_plan_needs_a_bounce_buffer_and_kv_layout_overrides_are_rejected(mgr):

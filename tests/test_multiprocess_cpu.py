@@ -4,8 +4,8 @@ CPU-only memcpy KV hand-off -- plumbing, runs without a GPU).
 Two forked processes rendezvous over gloo (127.0.0.1).  The decode rank registers its pool and publishes
 layout metadata; the prefill rank imports it and pushes 8 blocks with the Memcpy strategy; the decode rank
 verifies BLAKE3 block checksums against the oracle's Sequential fill.  The pools live in MAP_SHARED
-anonymous mappings created before fork, so both processes see them at the same virtual address (what CUDA
-IPC peer mappings provide on the GPU path)."""
+anonymous mappings created before fork; the prefill rank names its own view of the decode pool when it imports
+the metadata (`import_metadata(blob, local_bases)`), the CPU twin of the CUDA IPC peer mapping of the GPU path."""
 import mmap
 import multiprocessing as mp
 import os
@@ -54,7 +54,7 @@ def _worker(rank, port, src_addrs, dst_addrs, q):
         if rank == 0:   # prefill worker
             h_src = mgr.register_layer_separate(cfg, src_addrs, [PER_LAYER] * NL, BlockDimension.BlockIsSecondDim, StorageKind.System)
             O.Layout(O.LW, NB, NL, NO, PAGE, INNER, DT, block_dim=O.BLOCK_IS_SECOND_DIM, bases=src_addrs).fill_blocks(range(NB), -1)
-            grp.publish(None)
+            grp.publish(None, local_views={1: dst_addrs})     # the decode pool is shared memory, mapped here at dst_addrs
             note = grp.push(h_src, [sid], [did])
             note.wait()
             dist.barrier()
