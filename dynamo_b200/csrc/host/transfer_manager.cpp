@@ -743,8 +743,8 @@ static int execute(kvbm_transfer_manager* m, kvbm_layout_handle src_h, int nd, c
         return fail(KVBM_ERR_INCOMPATIBLE, "a layout transformation needs equal num_heads, page_size, inner_dim and dtype on both sides");
       if (sc.inner_dim % sc.num_heads) return fail(KVBM_ERR_CONFIG, "inner_dim_must_be_divisible_by_num_heads");
       const size_t row = sc.inner_dim / sc.num_heads * sc.dtype_width_bytes;
-      if (row < 16 || row > 4096 || (row & (row - 1)))
-        return fail(KVBM_ERR_UNSUPPORTED, "layout transformation: head_dim * dtype width must be a power of two in 16..4096 bytes, got " + std::to_string(row));
+      if (row < 16 || row > 65536 || (row & 15))
+        return fail(KVBM_ERR_UNSUPPORTED, "layout transformation: head_dim * dtype width must be a multiple of 16 bytes in 16..65536, got " + std::to_string(row));
       const bool s_uni = src_kv == KVBM_KV_UNIVERSAL_TP || src_kv == KVBM_KV_UNIVERSAL_PP;
       const bool d_uni = dst_kv == KVBM_KV_UNIVERSAL_TP || dst_kv == KVBM_KV_UNIVERSAL_PP;
       if ((s_uni && !S->fully_contiguous) || (d_uni && !D[d]->fully_contiguous))

@@ -484,9 +484,11 @@ struct PermuteSide {
   int universal;
 };
 
+template <bool POW2>
 __global__ void __launch_bounds__(256)
 kvbm_paged_permute_kernel(const __grid_constant__ PermuteSide S, const __grid_constant__ PermuteSide D, uint32_t layer_begin,
-                          uint32_t nlayers, uint32_t no, uint32_t nh, uint32_t nt, uint32_t log2_v)
+                          uint32_t nlayers, uint32_t no, uint32_t nh, uint32_t nt, uint32_t vpr /* POW2: log2 of, else: 16 B vectors per row */,
+                          uint32_t magic /* !POW2: ceil(2^32 / vpr) */)
 {
   const uint32_t unit = blockIdx.x;  // (pair * nlayers + l) * no + o
   const uint32_t pair = unit / (nlayers * no);
@@ -498,23 +500,52 @@ kvbm_paged_permute_kernel(const __grid_constant__ PermuteSide S, const __grid_co
   };
   const uint8_t* sb = base_of(S);
   uint8_t* db = base_of(D);
-  const uint32_t V = 1u << log2_v;
-  const uint32_t run = nt << log2_v;  // 16 B vectors of one head
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (uint32_t h = warp; h < nh; h += nwarps) {
-    const uint8_t* sh = sb + h * S.head_stride;
-    uint8_t* dh = db + h * D.head_stride;
-    auto off = [&](const PermuteSide& X, uint32_t v) { return static_cast<uint64_t>(v >> log2_v) * X.tok_stride + ((v & (V - 1)) << 4); };
-    constexpr int U = 8;
-    uint32_t v = lane;
-    for (; v + (U - 1) * 32 < run; v += U * 32) {
-      uint4 x[U];
+  constexpr int U = 8;
+  if (POW2) {
+    const uint32_t log2_v = vpr;
+    const uint32_t V = 1u << log2_v;
+    const uint32_t run = nt << log2_v;  // 16 B vectors of one head
+    for (uint32_t h = warp; h < nh; h += nwarps) {
+      const uint8_t* sh = sb + h * S.head_stride;
+      uint8_t* dh = db + h * D.head_stride;
+      auto off = [&](const PermuteSide& X, uint32_t v) { return static_cast<uint64_t>(v >> log2_v) * X.tok_stride + ((v & (V - 1)) << 4); };
+      uint32_t v = lane;
+      for (; v + (U - 1) * 32 < run; v += U * 32) {
+        uint4 x[U];
 #pragma unroll
-      for (int k = 0; k < U; ++k) x[k] = ptx::ld_stream_v4(sh + off(S, v + k * 32));
+        for (int k = 0; k < U; ++k) x[k] = ptx::ld_stream_v4(sh + off(S, v + k * 32));
 #pragma unroll
-      for (int k = 0; k < U; ++k) ptx::st_stream_v4(dh + off(D, v + k * 32), x[k]);
+        for (int k = 0; k < U; ++k) ptx::st_stream_v4(dh + off(D, v + k * 32), x[k]);
+      }
+      for (; v < run; v += 32) ptx::st_stream_v4(dh + off(D, v), ptx::ld_stream_v4(sh + off(S, v)));
     }
-    for (; v < run; v += 32) ptx::st_stream_v4(dh + off(D, v), ptx::ld_stream_v4(sh + off(S, v)));
+  } else {
+    // rows of any whole number of 16 B vectors (head_dim 80, 96, 192, MLA's 576 ...): token = v / V by a multiply-high with
+    // ceil(2^32 / V) (exact for v < 2^32 / V; the host checks nt * V against it), so the 8 loads stay independent
+    const uint32_t V = vpr;
+    const uint32_t run = nt * V;
+    for (uint32_t h = warp; h < nh; h += nwarps) {
+      const uint8_t* sh = sb + h * S.head_stride;
+      uint8_t* dh = db + h * D.head_stride;
+      uint32_t v = lane;
+      for (; v + (U - 1) * 32 < run; v += U * 32) {
+        uint4 x[U];
+        uint64_t od[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const uint32_t vk = v + k * 32, t = __umulhi(vk, magic), c = vk - t * V;
+          x[k] = ptx::ld_stream_v4(sh + static_cast<uint64_t>(t) * S.tok_stride + (c << 4));
+          od[k] = static_cast<uint64_t>(t) * D.tok_stride + (c << 4);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) ptx::st_stream_v4(dh + od[k], x[k]);
+      }
+      for (; v < run; v += 32) {
+        const uint32_t t = __umulhi(v, magic), c = v - t * V;
+        ptx::st_stream_v4(dh + static_cast<uint64_t>(t) * D.tok_stride + (c << 4), ptx::ld_stream_v4(sh + static_cast<uint64_t>(t) * S.tok_stride + (c << 4)));
+      }
+    }
   }
 }
 
@@ -633,7 +664,8 @@ static cudaError_t preload_kernels()
   KVBM_PRELOAD((kvbm_paged_copy_kernel<KVBM_CAST_BF16_TO_FP8E4M3, true>))
   KVBM_PRELOAD(kvbm_set_flags_kernel)
   KVBM_PRELOAD(kvbm_wait_flag_kernel)
-  KVBM_PRELOAD(kvbm_paged_permute_kernel)
+  KVBM_PRELOAD(kvbm_paged_permute_kernel<true>)
+  KVBM_PRELOAD(kvbm_paged_permute_kernel<false>)
   KVBM_PRELOAD(kvbm_signal_kernel)
   KVBM_PRELOAD((kvbm_permute_rows_kernel<true>))
   KVBM_PRELOAD((kvbm_permute_rows_kernel<false>))
@@ -845,7 +877,7 @@ kvbm_kernels_paged_permute(const kvbm_permute_side* src, const kvbm_permute_side
   if (!src || !dst || !src->block_ids || !dst->block_ids || !src->layout.layer_base || !dst->layout.layer_base) return cudaErrorInvalidValue;
   const uint32_t nl = src->layout.num_layers, no = src->layout.outer_dim;
   if (nl != dst->layout.num_layers || no != dst->layout.outer_dim || static_cast<uint32_t>(layer_end) > nl) return cudaErrorInvalidValue;
-  if (row_bytes < 16 || row_bytes > 4096 || (row_bytes & (row_bytes - 1)) || num_heads == 0 || page_size == 0) return cudaErrorInvalidValue;
+  if (row_bytes < 16 || row_bytes > 65536 || (row_bytes & 15) || num_heads == 0 || page_size == 0) return cudaErrorInvalidValue;
   const uint64_t region = static_cast<uint64_t>(page_size) * num_heads * row_bytes;
   if (region != src->layout.region_bytes || region != dst->layout.region_bytes) return cudaErrorInvalidValue;
   PermuteSide S, D;
@@ -854,12 +886,19 @@ kvbm_kernels_paged_permute(const kvbm_permute_side* src, const kvbm_permute_side
     return cudaErrorInvalidValue;
   const uint64_t units = static_cast<uint64_t>(num_blocks) * (layer_end - layer_begin) * no;
   if (units >= (1ull << 31)) return cudaErrorInvalidValue;
-  uint32_t log2_v = 0;
-  while ((16u << log2_v) < row_bytes) ++log2_v;
   const int threads = static_cast<int>(std::min<uint32_t>(8, num_heads)) * 32;
-  kvbm_paged_permute_kernel<<<static_cast<unsigned>(units), threads, 0, stream>>>(S, D, static_cast<uint32_t>(layer_begin),
-                                                                                  static_cast<uint32_t>(layer_end - layer_begin), no,
-                                                                                  num_heads, page_size, log2_v);
+  const unsigned grid = static_cast<unsigned>(units);
+  const uint32_t lb = static_cast<uint32_t>(layer_begin), nlay = static_cast<uint32_t>(layer_end - layer_begin);
+  if ((row_bytes & (row_bytes - 1)) == 0) {
+    uint32_t log2_v = 0;
+    while ((16u << log2_v) < row_bytes) ++log2_v;
+    kvbm_paged_permute_kernel<true><<<grid, threads, 0, stream>>>(S, D, lb, nlay, no, num_heads, page_size, log2_v, 0u);
+  } else {
+    const uint32_t V = row_bytes >> 4;
+    const uint64_t magic = ((1ull << 32) + V - 1) / V;
+    if (static_cast<uint64_t>(page_size) * V >= (1ull << 32) / V) return cudaErrorInvalidValue;  // exactness bound of the multiply-high division
+    kvbm_paged_permute_kernel<false><<<grid, threads, 0, stream>>>(S, D, lb, nlay, no, num_heads, page_size, V, static_cast<uint32_t>(magic));
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

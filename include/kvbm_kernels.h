@@ -196,7 +196,8 @@ typedef struct kvbm_permute_side {
 /* Block src.block_ids[i] of `src` -> block dst.block_ids[i] of `dst`, layers [layer_begin, layer_end), every element moved
  * from its position under src.kv_layout to its position under dst.kv_layout (equal layouts = plain copy).  Both sides must
  * agree on num_layers, outer_dim and region_bytes = page_size * num_heads * row_bytes; row_bytes (head_dim * element size)
- * must be a power of two in 16..4096 and every stride a multiple of 16 (cudaErrorInvalidValue otherwise).  `done_flag`
+ * must be a multiple of 16 in 16..65536 (powers of two take the shift-and-mask walk) and every stride a multiple of 16
+ * (cudaErrorInvalidValue otherwise).  `done_flag`
  * (nullable, device-visible) receives `epoch` with system scope after the last byte landed.  One launch, stream-ordered. */
 cudaError_t kvbm_kernels_paged_permute(const kvbm_permute_side* src, const kvbm_permute_side* dst, int num_blocks,
                                        int layer_begin, int layer_end, uint32_t num_heads, uint32_t page_size,

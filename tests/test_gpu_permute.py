@@ -63,13 +63,15 @@ def test_every_pair_of_layouts_matches_the_oracle(src_kv, dst_kv, kinds):
         assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("geom", [(1, 1, 1, 1, 8, 2), (2, 2, 5, 3, 128, 1), (2, 1, 64, 8, 128, 2), (1, 2, 3, 2, 1024, 4), (4, 2, 16, 40, 64, 2)],
+@pytest.mark.parametrize("geom", [(1, 1, 1, 1, 8, 2), (2, 2, 5, 3, 128, 1), (2, 1, 64, 8, 128, 2), (1, 2, 3, 2, 1024, 4), (4, 2, 16, 40, 64, 2),
+                                  (2, 2, 16, 8, 80, 2), (2, 2, 16, 4, 96, 2), (2, 1, 16, 1, 576, 2), (1, 2, 7, 3, 24, 2), (2, 2, 33, 2, 40, 2)],
                          ids=lambda g: "nl%d-no%d-nt%d-nh%d-hd%d-e%d" % g)
 @pytest.mark.parametrize("src_kv,dst_kv", [(KV.OperationalNHD, KV.UniversalTP), (KV.UniversalTP, KV.OperationalHND),
                                            (KV.OperationalHND, KV.OperationalNHD), (KV.UniversalPP, KV.UniversalTP)], ids=lambda k: k.name)
 def test_row_sizes_head_counts_and_odd_pages(geom, src_kv, dst_kv):
     """16 B ... 4 KiB rows, one head (a single warp) ... 40 heads (warps loop), page sizes that are not powers of two,
-    fp8 (1-byte) elements."""
+    fp8 (1-byte) elements; rows that are not a power of two (head_dim 80 / 96 / 40 / 24, MLA's 576-wide single head) take the
+    incremental (token, column) walk."""
     nl, no, nt, nh, hd, elem = geom
     row = hd * elem
     sk = "FC" if src_kv in UNIVERSAL else "LWs"
@@ -102,8 +104,10 @@ def test_layer_ranges_signals_and_argument_checks():
     assert flag.cpu().tolist() == [7, 9]
     # contract violations are cudaErrorInvalidValue, nothing is launched
     inval = K.CUDA_ERROR_INVALID_VALUE
-    assert _run_kernel(src, dst, [0], [1], KV.OperationalNHD, KV.UniversalTP, nl, nh, nt, 48) == inval          # row not a power of two
+    assert _run_kernel(src, dst, [0], [1], KV.OperationalNHD, KV.UniversalTP, nl, nh, nt, 48) == inval          # region != nt*nh*row
     assert _run_kernel(src, dst, [0], [1], KV.OperationalNHD, KV.UniversalTP, nl, nh, nt, 8) == inval           # row < 16 B
+    assert _run_kernel(src, dst, [0], [1], KV.OperationalNHD, KV.UniversalTP, nl, nh, nt * 16, 8) == inval      # ... even when the region size fits
+    assert _run_kernel(src, dst, [0], [1], KV.OperationalNHD, KV.UniversalTP, nl, nh * 16, nt, 8) == inval
     assert _run_kernel(src, dst, [0], [1], KV.OperationalNHD, KV.UniversalTP, nl, nh * 2, nt, row) == inval     # region != nt*nh*row
     assert _run_kernel(src, dst, [0], [1], KV.Unknown, KV.UniversalTP, nl, nh, nt, row) == inval
     assert _run_kernel(src, dst, [0], [1], KV.Custom, KV.UniversalTP, nl, nh, nt, row) == inval
