@@ -9,6 +9,7 @@
 #include <memory>
 #include <unordered_map>
 #include <unordered_set>
+#include <utility>
 #include <vector>
 
 #include "../../../include/kvbm_router.h"
@@ -266,6 +267,52 @@ extern "C" size_t kvr_tree_get_workers(kvr_radix_tree* t, uint64_t* out, size_t 
   ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
   for (size_t i = 0; i < ids.size() && i < cap; ++i) out[i] = ids[i];
   return ids.size();
+}
+
+// RadixTree::current_size (radix_tree.rs:567-569): blocks held, summed over (worker, dp_rank)
+extern "C" size_t kvr_tree_current_size(kvr_radix_tree* t)
+{
+  if (!t) return 0;
+  size_t n = 0;
+  for (auto& kv : t->lookup) n += kv.second.size();
+  return n;
+}
+
+// RadixTree::dump_tree_as_events (radix_tree.rs:505-565): breadth-first, one single-block Stored event per (block, worker),
+// event ids 0, 1, 2, ... -- replaying them into an empty tree rebuilds this one (the order among siblings and among a
+// block's workers is the hash maps' there as well).
+extern "C" size_t kvr_tree_dump_events(kvr_radix_tree* t, kvr_dump_event* out, size_t cap)
+{
+  if (!t) return 0;
+  struct Item {
+    BlockPtr block;
+    bool has_parent;
+    uint64_t parent_hash;
+    uint64_t tokens_hash;
+  };
+  std::deque<Item> queue;
+  for (auto& kv : t->root->children) queue.push_back({kv.second, false, 0, kv.first});
+  // With real sequence hashes the structure is a tree.  Hand-made hashes can make a block reachable along several edges
+  // or even close a cycle (a block is re-used by hash, radix_tree.rs:366-395); every EDGE is walked once so the dump ends.
+  struct EdgeHash {
+    size_t operator()(const std::pair<const Block*, const Block*>& e) const
+    {
+      return std::hash<const void*>()(e.first) * 0x9e3779b97f4a7c15ull ^ std::hash<const void*>()(e.second);
+    }
+  };
+  std::unordered_set<std::pair<const Block*, const Block*>, EdgeHash> walked;
+  size_t n = 0;
+  while (!queue.empty()) {
+    Item it = queue.front();
+    queue.pop_front();
+    for (const Worker& w : it.block->workers) {
+      if (out && n < cap) out[n] = kvr_dump_event{w.id, w.dp, it.has_parent ? 1u : 0u, static_cast<uint64_t>(n), it.parent_hash, it.block->block_hash, it.tokens_hash};
+      ++n;
+    }
+    for (auto& kv : it.block->children)
+      if (walked.insert({it.block.get(), kv.second.get()}).second) queue.push_back({kv.second, true, it.block->block_hash, kv.first});
+  }
+  return n;
 }
 
 extern "C" size_t kvr_tree_find_matches(kvr_radix_tree* t, const uint64_t* sequence, size_t n, int early_exit, uint64_t* worker_ids,

@@ -32,6 +32,12 @@ class KvCacheEventError(RuntimeError):
 _cfg = False
 
 
+class _DumpEvent(C.Structure):
+    """struct kvr_dump_event"""
+    _fields_ = [("worker_id", C.c_uint64), ("dp_rank", C.c_uint32), ("has_parent", C.c_uint32), ("event_id", C.c_uint64),
+                ("parent_hash", C.c_uint64), ("block_hash", C.c_uint64), ("tokens_hash", C.c_uint64)]
+
+
 def lib() -> C.CDLL:
     global _cfg
     L = _lib.load(ROUTER_SO)
@@ -64,6 +70,10 @@ def lib() -> C.CDLL:
         L.kvr_tree_lookup_len.argtypes = [vp]
         L.kvr_tree_lookup_len.restype = sz
         L.kvr_tree_node_info.argtypes = [vp, P(u64), sz, P(sz), P(sz)]
+        L.kvr_tree_current_size.argtypes = [vp]
+        L.kvr_tree_current_size.restype = sz
+        L.kvr_tree_dump_events.argtypes = [vp, P(_DumpEvent), sz]
+        L.kvr_tree_dump_events.restype = sz
         L.kvr_tree_find_matches.argtypes = [vp, P(u64), sz, i, P(u64), P(u32), P(u32), P(u64), sz, P(u64), sz, P(sz)]
         L.kvr_tree_find_matches.restype = sz
         _cfg = True
@@ -171,6 +181,21 @@ class RadixTree:
         out = (C.c_uint64 * 4096)()
         n = lib().kvr_tree_get_workers(self._h, out, 4096)
         return [out[i] for i in range(min(n, 4096))]
+
+    def current_size(self) -> int:
+        """RadixTree::current_size (radix_tree.rs:567-569)."""
+        return lib().kvr_tree_current_size(self._h)
+
+    def dump_tree_as_events(self) -> List[dict]:
+        """RadixTree::dump_tree_as_events (radix_tree.rs:505-565) as the RouterEvent dicts `apply_event` takes (serde shape)."""
+        n = lib().kvr_tree_dump_events(self._h, None, 0)
+        buf = (_DumpEvent * max(1, n))()
+        n = min(n, lib().kvr_tree_dump_events(self._h, buf, n))
+        return [{"worker_id": e.worker_id, "storage_tier": "device",
+                 "event": {"event_id": e.event_id, "dp_rank": e.dp_rank,
+                           "data": {"stored": {"parent_hash": e.parent_hash if e.has_parent else None,
+                                               "blocks": [{"block_hash": e.block_hash, "tokens_hash": e.tokens_hash}]}}}}
+                for e in buf[:n]]
 
     # -- queries ------------------------------------------------------------------------------------------
     def find_matches(self, sequence: Sequence[int], early_exit: bool = False) -> OverlapScores:

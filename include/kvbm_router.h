@@ -60,6 +60,22 @@ void kvr_tree_clear_all_blocks(kvr_radix_tree* t, uint64_t worker_id);
 /* get_workers: sorted unique worker ids; returns count (writes up to cap) */
 size_t kvr_tree_get_workers(kvr_radix_tree* t, uint64_t* out, size_t cap);
 
+/* current_size (radix_tree.rs:567-569): blocks held, summed over (worker, dp_rank) -- what the pruning policy watches */
+size_t kvr_tree_current_size(kvr_radix_tree* t);
+/* dump_tree_as_events (radix_tree.rs:505-565): the tree as single-block Stored events in breadth-first order, event ids
+ * 0..n-1; replaying them into an empty tree rebuilds it (router replica sync, kv_indexer.rs:243).  Returns the number of
+ * events; writes the first `cap`. */
+typedef struct kvr_dump_event {
+  uint64_t worker_id;
+  uint32_t dp_rank;
+  uint32_t has_parent;
+  uint64_t event_id;
+  uint64_t parent_hash; /* ExternalSequenceBlockHash of the parent block (has_parent) */
+  uint64_t block_hash;  /* ExternalSequenceBlockHash */
+  uint64_t tokens_hash; /* LocalBlockHash */
+} kvr_dump_event;
+size_t kvr_tree_dump_events(kvr_radix_tree* t, kvr_dump_event* out, size_t cap);
+
 /* introspection used by the tests (the reference's tests read `trie.lookup` / `trie.root` directly) */
 int64_t kvr_tree_lookup_size(kvr_radix_tree* t, uint64_t worker_id, uint32_t dp_rank); /* -1: worker not in lookup */
 size_t kvr_tree_lookup_len(kvr_radix_tree* t);

@@ -309,3 +309,64 @@ def test_event_publish_stored_and_removed_feed_the_radix_tree_and_emit_router_ev
     finally:
         pub.shutdown()
         tree.close()
+
+
+def test_dump_tree_as_events_rebuilds_the_tree_and_current_size_counts_blocks():
+    """radix_tree.rs:505-569: a breadth-first dump of single-block Stored events (ids 0..n-1, parents before children)
+    replayed into an empty tree gives the same scores, sizes and structure (router replica sync, kv_indexer.rs:243)."""
+    t = R.RadixTree()
+    assert t.current_size() == 0 and t.dump_tree_as_events() == []
+    t.apply_stored(0, [100, 200, 300], [1, 2, 3])
+    t.apply_stored(1, [100, 200, 400], [1, 2, 4], dp_rank=1)
+    t.apply_stored(0, [500], [5], parent_hash=200)
+    assert t.current_size() == 3 + 3 + 1
+    ev = t.dump_tree_as_events()
+    assert [e["event"]["event_id"] for e in ev] == list(range(len(ev))) and len(ev) == t.current_size()
+    assert all(e["storage_tier"] == "device" and len(e["event"]["data"]["stored"]["blocks"]) == 1 for e in ev)
+    seen = set()
+    for e in ev:                                       # breadth-first: a block's parent was announced by an earlier event
+        st = e["event"]["data"]["stored"]
+        assert st["parent_hash"] is None or st["parent_hash"] in seen
+        seen.add(st["blocks"][0]["block_hash"])
+    roots = [e for e in ev if e["event"]["data"]["stored"]["parent_hash"] is None]
+    assert {(e["worker_id"], e["event"]["dp_rank"]) for e in roots} == {(0, 0), (1, 1)}
+    assert all(e["event"]["data"]["stored"]["blocks"][0] == {"block_hash": 100, "tokens_hash": 1} for e in roots)
+    # random trees over real sequence hashes (block hash = hash of the whole prefix, so the structure is a tree)
+    rng = np.random.default_rng(7)
+    for trial in range(25):
+        a = R.RadixTree()
+        held = {}                                      # (w, dp) -> {block hash: parent hash or None}
+        for step in range(80):
+            w, dp = int(rng.integers(0, 4)), int(rng.integers(0, 2))
+            mine = held.setdefault((w, dp), {})
+            if not mine or rng.integers(0, 4):
+                toks = [int(x) for x in rng.integers(1, 6, int(rng.integers(1, 7)))]
+                seq = R.compute_seq_hash_for_block(toks)
+                a.apply_stored(w, seq, toks, None, dp)
+                for i, h in enumerate(seq):
+                    mine.setdefault(h, seq[i - 1] if i else None)
+            else:                                       # engines evict leaves: a held block none of whose children is held
+                leaves = [h for h in mine if h not in set(mine.values())]
+                h = leaves[int(rng.integers(0, len(leaves)))]
+                a.apply_removed(w, [h], dp)
+                del mine[h]
+        b = R.RadixTree()
+        for e in a.dump_tree_as_events():
+            b.apply_event(json.dumps(e))               # through the serde shape, as it would cross the wire
+        assert b.current_size() == a.current_size()
+        for w in range(4):
+            for dp in range(2):
+                assert (b.lookup_size(w, dp) or 0) == (a.lookup_size(w, dp) or 0)   # a worker whose blocks are all gone is not re-created
+        for _ in range(40):
+            q = [int(x) for x in rng.integers(1, 6, int(rng.integers(1, 7)))]
+            assert b.find_matches(q).scores == a.find_matches(q).scores
+            ia, ib = a.node_info(q), b.node_info(q)
+            # emptied blocks (no worker left) stay in the original as dead children and are not re-created by the replay
+            assert (ia is None or ia[0] == 0) if ib is None else (ia is not None and ia[0] == ib[0] and ia[1] >= ib[1])
+        a.close()
+        b.close()
+    # hand-made hashes that close a cycle (100 -> 200 -> 100): the dump still ends
+    c = R.RadixTree()
+    c.apply_stored(0, [100, 200], [1, 2])
+    c.apply_stored(0, [200, 100], [2, 1])
+    assert 0 < len(c.dump_tree_as_events()) < 64
