@@ -89,6 +89,29 @@ int main(void)
   /* System <-> Device has no direct strategy, exactly as the reference's table (strategy.rs:138-210) */
   CHECK(kvbm_manager_execute_transfer(m, hs, sids, hdev, dids, 3, NULL, &note) != KVBM_OK);
 
+  /* strategy and transform selection are pure functions of plain ints (strategy.rs:78-108,245-281; executor/mod.rs:46-100) */
+  {
+    kvbm_transfer_capabilities caps = {0, 1};
+    kvbm_transfer_plan plan;
+    CHECK(kvbm_select_strategy(KVBM_STORAGE_DEVICE, 1, KVBM_STORAGE_DEVICE, 0, &caps, &plan) == KVBM_OK && !plan.two_hop && plan.first == KVBM_STRATEGY_NIXL_WRITE);
+    CHECK(kvbm_select_strategy(KVBM_STORAGE_DEVICE, 0, KVBM_STORAGE_DEVICE, 1, &caps, &plan) == KVBM_OK && plan.first == KVBM_STRATEGY_NIXL_READ_FLIPPED);
+    CHECK(kvbm_select_strategy(KVBM_STORAGE_DEVICE, 0, KVBM_STORAGE_DEVICE, 0, &caps, &plan) == KVBM_ERR_UNSUPPORTED);
+    CHECK(strstr(kvbm_last_error(), "Both src and dst are remote") != NULL);
+    caps.allow_gpu_rdma = 0;
+    CHECK(kvbm_select_direct_strategy_remote(KVBM_STORAGE_DEVICE, KVBM_STORAGE_SYSTEM, 1, &caps, &plan) == KVBM_OK && plan.two_hop &&
+          plan.first == KVBM_STRATEGY_CUDA_ASYNC_D2H && plan.bounce_location == KVBM_STORAGE_PINNED && plan.second == KVBM_STRATEGY_NIXL_WRITE);
+    CHECK(kvbm_manager_select_strategy(m, hs, hd, &plan) == KVBM_OK && plan.first == KVBM_STRATEGY_MEMCPY);
+    CHECK(kvbm_select_transform_kernel(KVBM_KV_OPERATIONAL_NHD, KVBM_KV_UNIVERSAL_TP) == KVBM_TRANSFORM_BLOCK_TO_UNIVERSAL);
+    CHECK(kvbm_select_transform_kernel(KVBM_KV_UNIVERSAL_TP, KVBM_KV_OPERATIONAL_HND) == KVBM_TRANSFORM_UNIVERSAL_TO_BLOCK);
+    CHECK(kvbm_select_transform_kernel(KVBM_KV_OPERATIONAL_NHD, KVBM_KV_OPERATIONAL_HND) == KVBM_TRANSFORM_OPERATIONAL_TRANSPOSE);
+    CHECK(kvbm_select_transform_kernel(KVBM_KV_UNKNOWN, KVBM_KV_UNKNOWN) == KVBM_TRANSFORM_NONE);
+    CHECK(kvbm_select_transform_kernel(KVBM_KV_UNKNOWN, KVBM_KV_UNIVERSAL_TP) == KVBM_TRANSFORM_UNSUPPORTED);
+    CHECK(kvbm_kv_layout_requires_transform(KVBM_KV_OPERATIONAL_NHD, KVBM_KV_OPERATIONAL_NHD) == 0);
+    CHECK(kvbm_manager_set_kv_block_layout(m, hs, KVBM_KV_OPERATIONAL_NHD) == KVBM_ERR_CONFIG);   /* this config has no num_heads */
+    CHECK(strstr(kvbm_last_error(), "num_heads_required_for_kv_block_layout") != NULL);
+    CHECK(kvbm_manager_kv_block_layout(m, hs) == KVBM_KV_UNKNOWN);
+  }
+
   kvbm_manager_destroy(peer);
   kvbm_manager_destroy(m);
   free(blob);
