@@ -876,7 +876,7 @@ kvbm_kernels_paged_permute(const kvbm_permute_side* src, const kvbm_permute_side
   if (num_blocks == 0 || layer_end == layer_begin) return finish();
   if (!src || !dst || !src->block_ids || !dst->block_ids || !src->layout.layer_base || !dst->layout.layer_base) return cudaErrorInvalidValue;
   const uint32_t nl = src->layout.num_layers, no = src->layout.outer_dim;
-  if (nl != dst->layout.num_layers || no != dst->layout.outer_dim || static_cast<uint32_t>(layer_end) > nl) return cudaErrorInvalidValue;
+  if (nl == 0 || no == 0 || nl != dst->layout.num_layers || no != dst->layout.outer_dim || static_cast<uint32_t>(layer_end) > nl) return cudaErrorInvalidValue;
   if (row_bytes < 16 || row_bytes > 65536 || (row_bytes & 15) || num_heads == 0 || page_size == 0) return cudaErrorInvalidValue;
   const uint64_t region = static_cast<uint64_t>(page_size) * num_heads * row_bytes;
   if (region != src->layout.region_bytes || region != dst->layout.region_bytes) return cudaErrorInvalidValue;
