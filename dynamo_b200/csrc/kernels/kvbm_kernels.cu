@@ -860,6 +860,27 @@ static bool fill_permute_side(const kvbm_permute_side& in, uint32_t nl, uint32_t
   return true;
 }
 
+// Host-only view of the stride table the permuting kernel walks with (no GPU needed): lets the CPU suite check the
+// address arithmetic of every KvBlockLayout against the oracle's dim_order definition, at sizes no GPU test allocates.
+extern "C" int
+kvbm_kernels_permute_strides(int kv_layout, uint32_t num_layers, uint32_t outer_dim, uint32_t num_heads, uint32_t page_size,
+                             uint32_t row_bytes, uint64_t block_stride, uint64_t outer_stride, uint64_t out[5])
+{
+  if (!out) return 1;
+  kvbm_permute_side side{};
+  side.layout.block_stride = block_stride;
+  side.layout.outer_stride = outer_stride;
+  side.kv_layout = kv_layout;
+  PermuteSide p;
+  if (!fill_permute_side(side, num_layers, outer_dim, num_heads, page_size, row_bytes, &p)) return 1;
+  out[0] = p.universal ? 1 : 0;  // 1: offsets are relative to the block's start; 0: relative to the (layer, outer) region
+  out[1] = p.layer_step;
+  out[2] = p.outer_step;
+  out[3] = p.head_stride;
+  out[4] = p.tok_stride;
+  return 0;
+}
+
 extern "C" cudaError_t
 kvbm_kernels_paged_permute(const kvbm_permute_side* src, const kvbm_permute_side* dst, int num_blocks, int layer_begin,
                            int layer_end, uint32_t num_heads, uint32_t page_size, uint32_t row_bytes, uint32_t* done_flag,

@@ -149,6 +149,9 @@ def lib() -> C.CDLL:
         L.kvbm_kernels_paged_permute.argtypes = [C.POINTER(PermuteSide), C.POINTER(PermuteSide), i, i, i, C.c_uint32, C.c_uint32,
                                                  C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp]
         L.kvbm_kernels_paged_permute.restype = i
+        L.kvbm_kernels_permute_strides.argtypes = [i, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64,
+                                                   C.POINTER(C.c_uint64)]
+        L.kvbm_kernels_permute_strides.restype = i
         L.kvbm_kernels_set_flags.argtypes = [vp, i, i, C.c_uint32, vp]
         L.kvbm_kernels_set_flags.restype = i
         L.kvbm_kernels_wait_flag.argtypes = [vp, C.c_uint32, vp]
@@ -167,6 +170,7 @@ EXPORTED_SYMBOLS = [
     "kvbm_kernels_has_memcpy_batch_async", "kvbm_kernels_is_stub_build",
     "kvbm_kernels_paged_copy_v2", "kvbm_kernels_set_flags", "kvbm_kernels_wait_flag", "kvbm_kernels_stream_wait_event",
     "kvbm_kernels_launch_count", "kvbm_kernels_build_info", "kvbm_kernels_gate_would_spin", "kvbm_kernels_paged_permute",
+    "kvbm_kernels_permute_strides",
 ]
 
 GATE_AUTO, GATE_SPIN, GATE_STREAM_WAIT = 0, 1, 2
@@ -228,6 +232,16 @@ def paged_permute(src: PermuteSide, dst: PermuteSide, num_blocks: int, layer_beg
     dst.kv_layout; row_bytes = head_dim * element size.  include/kvbm_kernels.h (kvbm_kernels_paged_permute)."""
     return lib().kvbm_kernels_paged_permute(C.byref(src), C.byref(dst), num_blocks, layer_begin, layer_end, num_heads, page_size,
                                             row_bytes, done_flag or None, epoch, completion_flag or None, completion_value, stream)
+
+
+def permute_strides(kv_layout: int, num_layers: int, outer_dim: int, num_heads: int, page_size: int, row_bytes: int,
+                    block_stride: int, outer_stride: int):
+    """Host-only: (universal, layer_step, outer_step, head_stride, tok_stride) of one side of `paged_permute`, or None."""
+    out = (C.c_uint64 * 5)()
+    if lib().kvbm_kernels_permute_strides(int(kv_layout), num_layers, outer_dim, num_heads, page_size, row_bytes, block_stride,
+                                          outer_stride, out):
+        return None
+    return bool(out[0]), int(out[1]), int(out[2]), int(out[3]), int(out[4])
 
 
 def set_flags(flags_ptr: int, first: int, count: int, value: int, stream: int) -> int:

@@ -204,6 +204,13 @@ cudaError_t kvbm_kernels_paged_permute(const kvbm_permute_side* src, const kvbm_
                                        uint32_t row_bytes, uint32_t* done_flag, uint32_t epoch, uint32_t* completion_flag,
                                        uint32_t completion_value, cudaStream_t stream);
 
+/* Host-only (no GPU): the stride table kvbm_kernels_paged_permute walks with for one side.  out[0] = 1 when offsets count
+ * from the block's first byte (universal formats) or 0 when they count from the (layer, outer) region's first byte; the
+ * element (layer l, outer o, head h, token t) then sits at  [out[0] ? l * out[1] + o * out[2] : 0] + h * out[3] + t * out[4].
+ * Returns non-zero for formats without a kernel or strides that are not multiples of 16. */
+int kvbm_kernels_permute_strides(int kv_layout, uint32_t num_layers, uint32_t outer_dim, uint32_t num_heads, uint32_t page_size,
+                                 uint32_t row_bytes, uint64_t block_stride, uint64_t outer_stride, uint64_t out[5]);
+
 /* 1 when KVBM_GATE_AUTO would let the transfer's warps spin on the ready flags (eager module loading detected through
  * cuModuleGetLoadingMode), 0 when it would gate on the stream instead. */
 int kvbm_kernels_gate_would_spin(void);

@@ -672,3 +672,36 @@ def test_ctypes_mirrors_have_the_c_struct_layouts(tmp_path):
         assert C.sizeof(mirror) == c[(cname, "sizeof")], f"{cname}: ctypes {C.sizeof(mirror)} vs C {c[(cname, 'sizeof')]} bytes"
         for fname, _ in mirror._fields_:
             assert getattr(mirror, fname).offset == c[(cname, fname)], f"{cname}.{fname}"
+
+
+@pytest.mark.parametrize("dims", [(3, 2, 4, 5, 16), (2, 1, 16, 8, 256), (80, 2, 16, 8, 256), (1, 2, 7, 3, 48), (61, 1, 64, 1, 1152)],
+                         ids=lambda d: "nl%d-no%d-nt%d-nh%d-row%d" % d)
+def test_permute_stride_table_spells_every_kv_block_layout(dims):
+    """The whole address arithmetic of kvbm_paged_permute_kernel is one stride table per side (kvbm_kernels.cu,
+    fill_permute_side).  Checked here without a GPU: moving each row with the table's offsets must equal the oracle's
+    dim_order permutation (kv_block_layout.rs:85-95) for every ordered pair of formats."""
+    from dynamo_b200.kernels import KvBlockLayout as KV
+    nl, no, nt, nh, row = dims
+    region = nt * nh * row
+    block = nl * no * region
+
+    def row_offsets(kv):
+        uni, lstep, ostep, hs, ts = K.permute_strides(kv, nl, no, nh, nt, row, block, region)
+        l, o, h, t = np.meshgrid(np.arange(nl), np.arange(no), np.arange(nh), np.arange(nt), indexing="ij")
+        base = (l * lstep + o * ostep) if uni else (l * no + o) * region      # operational blocks: regions in (layer, outer) order
+        return (base + h * hs + t * ts).reshape(-1)
+
+    rng = np.random.default_rng(nl * 7 + nh)
+    src = rng.integers(0, 256, block, dtype=np.uint8)
+    offs = {kv: row_offsets(kv) for kv in (KV.UniversalTP, KV.UniversalPP, KV.OperationalHND, KV.OperationalNHD)}
+    for kv, off in offs.items():                      # a bijection onto the block's rows
+        assert np.array_equal(np.sort(off), np.arange(nl * no * nh * nt) * row), kv
+    col = np.arange(row)
+    for a, oa in offs.items():
+        for b, ob in offs.items():
+            dst = np.zeros_like(src)
+            dst[(ob[:, None] + col).reshape(-1)] = src[(oa[:, None] + col).reshape(-1)]
+            assert np.array_equal(dst, O.kv_layout_permute(src, int(a), int(b), nl, no, nt, nh, row)), (a, b)
+    assert K.permute_strides(KV.Unknown, nl, no, nh, nt, row, block, region) is None
+    assert K.permute_strides(KV.Custom, nl, no, nh, nt, row, block, region) is None
+    assert K.permute_strides(KV.OperationalNHD, nl, no, nh, nt, row, block + 8, region) is None      # strides must be multiples of 16
