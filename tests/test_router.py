@@ -370,3 +370,56 @@ def test_dump_tree_as_events_rebuilds_the_tree_and_current_size_counts_blocks():
     c.apply_stored(0, [100, 200], [1, 2])
     c.apply_stored(0, [200, 100], [2, 1])
     assert 0 < len(c.dump_tree_as_events()) < 64
+
+
+def test_event_publish_is_safe_from_many_threads():
+    """TRT-LLM's executor calls dynamo_kv_event_publish_* from its own threads (lib/bindings/c/src/lib.rs:328-391 goes
+    through a static publisher): concurrent publishers must neither lose nor tear events."""
+    import threading
+    KB, THREADS, PER = 4, 8, 150
+    events = []
+    tree = R.RadixTree()
+    R._ev_lib().dynamo_llm_shutdown()
+    pub = R.KvEventPublisher("ns", "backend", KB, worker_id=7, tree=tree, on_event=events.append)
+    before = R.KvEventPublisher.published_count()
+    errors = []
+
+    def worker(t):
+        try:
+            for i in range(PER):
+                base = (t * PER + i) * 16
+                toks = [base + k for k in range(2 * KB)]
+                if not pub.publish_stored(t * 10000 + i, toks, [KB, KB], [base + 1, base + 2]):
+                    errors.append(("stored", t, i))
+                if i % 3 == 0 and not pub.publish_removed(t * 10000 + 5000 + i, [base + 2]):
+                    errors.append(("removed", t, i))
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    try:
+        ts = [threading.Thread(target=worker, args=(t,)) for t in range(THREADS)]
+        for th in ts:
+            th.start()
+        for th in ts:
+            th.join()
+        assert errors == []
+        n_removed = THREADS * len(range(0, PER, 3))
+        assert R.KvEventPublisher.published_count() - before == THREADS * PER + n_removed == len(events)
+        assert tree.current_size() == 2 * THREADS * PER - n_removed
+        ids = set()
+        for raw in events:                                   # every callback payload is one complete RouterEvent
+            ev = json.loads(raw)
+            assert ev["worker_id"] == 7
+            ids.add(ev["event"]["event_id"])
+        assert len(ids) == len(events)
+        # a replica fed from the emitted JSON (in arrival order) converges to the same index
+        twin = R.RadixTree()
+        for raw in events:
+            twin.apply_event(raw)
+        assert twin.current_size() == tree.current_size()
+        q = R.compute_block_hash_for_seq([16 * 37 + k for k in range(2 * KB)], KB)
+        assert twin.find_matches(q).scores == tree.find_matches(q).scores != {}
+        twin.close()
+    finally:
+        pub.shutdown()
+        tree.close()
