@@ -705,3 +705,43 @@ def test_permute_stride_table_spells_every_kv_block_layout(dims):
     assert K.permute_strides(KV.Unknown, nl, no, nh, nt, row, block, region) is None
     assert K.permute_strides(KV.Custom, nl, no, nh, nt, row, block, region) is None
     assert K.permute_strides(KV.OperationalNHD, nl, no, nh, nt, row, block + 8, region) is None      # strides must be multiples of 16
+
+
+def test_manager_is_reentrant_from_many_threads(mgr):
+    """SURVEY 8(b) threading: the reference is called from arbitrary tokio worker threads.  Concurrent execute_transfer,
+    register / unregister and notification polling on ONE manager must give the bytes a sequential run gives."""
+    import threading
+    nb, threads, rounds = 64, 8, 40
+    cfg = std_cfg(nb)
+    src_t, dst_t, ref_t = (O.Layout(O.FC, nb, 2, 2, 16, 128, 2) for _ in range(3))
+    rng = np.random.default_rng(3)
+    src_t.buffers[0][:] = rng.integers(0, 256, src_t.buffers[0].size, dtype=np.uint8)
+    hs = mgr.register_fully_contiguous(cfg, src_t.buffers[0].ctypes.data, src_t.buffers[0].size, StorageKind.System)
+    hd = mgr.register_fully_contiguous(cfg, dst_t.buffers[0].ctypes.data, dst_t.buffers[0].size, StorageKind.Pinned)
+    per = nb // threads                                      # thread t owns destination blocks [t*per, (t+1)*per)
+    plans = [[(list(map(int, np.random.default_rng(100 * t + r).integers(0, nb, per))),
+               list(map(int, t * per + np.random.default_rng(7 * t + r).permutation(per)))) for r in range(rounds)] for t in range(threads)]
+    errors = []
+
+    def run(t):
+        try:
+            scratch = np.zeros(cfg.required_bytes(), dtype=np.uint8)
+            for sid, did in plans[t]:
+                note = mgr.execute_transfer(hs, sid, hd, did)
+                assert note.is_complete()
+                h = mgr.register_fully_contiguous(cfg, scratch.ctypes.data, scratch.size, StorageKind.System)   # churn the layout table
+                assert mgr.memory_region(h, 1, 1, 1)[1] == cfg.region_size()
+                mgr.unregister(h)
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=run, args=(t,)) for t in range(threads)]
+    for th in ts:
+        th.start()
+    for th in ts:
+        th.join()
+    assert errors == []
+    for t in range(threads):                                 # destinations are disjoint per thread: order across threads is irrelevant
+        for sid, did in plans[t]:
+            O.execute_memcpy_transfer(src_t, ref_t, sid, did)
+    assert np.array_equal(dst_t.buffers[0], ref_t.buffers[0])
