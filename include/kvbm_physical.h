@@ -19,6 +19,8 @@
  *   CollectiveOps::broadcast             lib/kvbm-engine/src/collectives/mod.rs:75-106 (ncclBcast per region)
  *                                        -- replaced by one replicate launch over NVLink peer mappings
  *
+ * Threading: a kvbm_transfer_manager may be used from any number of threads concurrently (the reference is called from
+ * arbitrary tokio workers); checked under ThreadSanitizer by tests/c/race_check.cpp.
  * Error style: every call returns KVBM_OK (0) or an error code; kvbm_last_error() gives the thread's last
  * message (house style of lib/bindings/c/src/lib.rs:74-78: OK=0, ERR!=0).  Nothing aborts or throws.
  */

@@ -40,6 +40,9 @@ size_t kvr_compute_block_hash_for_seq(const uint32_t* tokens, size_t n_tokens, u
 /* compute_seq_hash_for_block */
 void kvr_compute_seq_hash_for_block(const uint64_t* block_hashes, size_t n, uint64_t* out);
 
+/* Threading: a kvr_radix_tree is NOT internally synchronised -- like the reference's RadixTree (Rc<RefCell<..>> nodes owned by
+ * one indexer task, indexer/kv_indexer.rs) it belongs to one thread at a time.  The dynamo_kv_event_* publisher below IS
+ * thread-safe and serialises the events it applies to an attached tree (tests/c/race_check.cpp under ThreadSanitizer). */
 typedef struct kvr_radix_tree kvr_radix_tree;
 
 /* expiration_ms < 0: no frequency tracking (RadixTree::new); else new_with_frequency(Some(duration)) */

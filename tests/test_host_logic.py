@@ -745,3 +745,29 @@ def test_manager_is_reentrant_from_many_threads(mgr):
         for sid, did in plans[t]:
             O.execute_memcpy_transfer(src_t, ref_t, sid, did)
     assert np.array_equal(dst_t.buffers[0], ref_t.buffers[0])
+
+
+def test_host_libraries_are_race_free_under_thread_sanitizer(tmp_path):
+    """SURVEY 5 (race detection): tests/c/race_check.cpp, built from the library SOURCES with -fsanitize=thread, hammers the
+    host-only TransferManager (execute / register / unregister / notifications) and the KV event publisher (RadixTree +
+    JSON sinks) from 8 threads.  A data race makes ThreadSanitizer print a report and the run exit non-zero."""
+    import pyarrow
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = tmp_path / "p.cpp"
+    probe.write_text("int main(){return 0;}\n")
+    if subprocess.run(["g++", "-fsanitize=thread", str(probe), "-o", str(tmp_path / "p")], capture_output=True).returncode != 0:
+        pytest.skip("g++ has no ThreadSanitizer runtime here")
+    xxh = os.path.join(pyarrow.get_include(), "arrow", "vendored", "xxhash")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = tmp_path / "race_check"
+    src = [os.path.join(root, p) for p in ("tests/c/race_check.cpp", "dynamo_b200/csrc/host/transfer_manager.cpp",
+                                           "dynamo_b200/csrc/host/multicast.cpp", "dynamo_b200/csrc/router/radix_tree.cpp",
+                                           "dynamo_b200/csrc/router/kv_events.cpp")]
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-fno-omit-frame-pointer", "-pthread", "-I", os.path.join(root, "include"),
+           "-I", os.path.join(cuda, "include"), "-I", xxh, *src, "-L", os.path.join(root, "dynamo_b200"), "-lkvbm_kernels",
+           "-L", os.path.join(cuda, "lib64"), "-lcudart", "-ldl", f"-Wl,-rpath,{os.path.join(root, 'dynamo_b200')}",
+           f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}", "-o", str(exe)]
+    b = subprocess.run(cmd, capture_output=True, text=True)
+    assert b.returncode == 0, b.stderr[-2000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1"))
+    assert r.returncode == 0 and "race check ok" in r.stdout and "ThreadSanitizer" not in r.stderr, (r.stdout[-500:], r.stderr[-3000:])
