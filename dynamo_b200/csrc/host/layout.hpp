@@ -36,9 +36,25 @@ inline int validate_config(const kvbm_layout_config& c, std::string* why)
   return KVBM_OK;
 }
 
-inline size_t region_size(const kvbm_layout_config& c) { return c.page_size * c.inner_dim * c.dtype_width_bytes; }
-inline size_t bytes_per_block(const kvbm_layout_config& c) { return c.num_layers * c.outer_dim * region_size(c); }
-inline size_t required_bytes(const kvbm_layout_config& c) { return c.num_blocks * bytes_per_block(c); }
+// The reference multiplies with saturating_mul (config.rs:64-82): a config whose sizes do not fit a usize can never be backed
+// by memory.  Configs also arrive inside metadata blobs from other processes, so every product here is overflow-checked.
+inline size_t sat_mul(size_t a, size_t b)
+{
+  size_t r;
+  return __builtin_mul_overflow(a, b, &r) ? static_cast<size_t>(-1) : r;
+}
+inline size_t region_size(const kvbm_layout_config& c) { return sat_mul(sat_mul(c.page_size, c.inner_dim), c.dtype_width_bytes); }
+inline size_t bytes_per_block(const kvbm_layout_config& c) { return sat_mul(sat_mul(c.num_layers, c.outer_dim), region_size(c)); }
+inline size_t required_bytes(const kvbm_layout_config& c) { return sat_mul(c.num_blocks, bytes_per_block(c)); }
+// a layout whose total size saturates cannot exist; neither can one with more layers than bytes
+inline int check_sizes(const kvbm_layout_config& c, std::string* why)
+{
+  if (required_bytes(c) == static_cast<size_t>(-1) || c.num_layers > (static_cast<size_t>(1) << 24)) {
+    if (why) *why = "layout dimensions overflow: num_blocks * num_layers * outer_dim * page_size * inner_dim * dtype_width_bytes does not fit";
+    return KVBM_ERR_CONFIG;
+  }
+  return KVBM_OK;
+}
 
 struct Allocation {
   uintptr_t addr;
@@ -86,6 +102,7 @@ inline int make_fully_contiguous(const kvbm_layout_config& cfg, uintptr_t base, 
 {
   int rc = validate_config(cfg, why);
   if (rc) return rc;
+  if ((rc = check_sizes(cfg, why))) return rc;
   Layout L;
   L.cfg = cfg;
   L.fully_contiguous = true;
@@ -111,6 +128,7 @@ inline int make_layer_separate(const kvbm_layout_config& cfg, const uintptr_t* b
 {
   int rc = validate_config(cfg, why);
   if (rc) return rc;
+  if ((rc = check_sizes(cfg, why))) return rc;
   if (count != cfg.num_layers) {
     if (why) *why = "Memory region count (" + std::to_string(count) + ") must match num_layers (" + std::to_string(cfg.num_layers) + ")";
     return KVBM_ERR_CONFIG;

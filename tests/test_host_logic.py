@@ -771,3 +771,41 @@ def test_host_libraries_are_race_free_under_thread_sanitizer(tmp_path):
     assert b.returncode == 0, b.stderr[-2000:]
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1"))
     assert r.returncode == 0 and "race check ok" in r.stdout and "ThreadSanitizer" not in r.stderr, (r.stdout[-500:], r.stderr[-3000:])
+
+
+def test_metadata_importers_survive_corrupted_input_under_asan_ubsan(tmp_path):
+    """The three importers parse bytes that come from other processes.  tests/c/fuzz_import.cpp mutates valid exports (bit
+    flips, truncation, 0xff runs, inflated JSON numbers ...) 20 000 times per format and imports them into fresh managers,
+    built from the library sources with -fsanitize=address,undefined: an import may only succeed or return an error code.
+    (This harness found a length_error escaping the C ABI through an unchecked num_layers; layout sizes are now
+    overflow-checked like the reference's saturating_mul, config.rs:64-82.)"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = tmp_path / "p.cpp"
+    probe.write_text("int main(){return 0;}\n")
+    if subprocess.run(["g++", "-fsanitize=address,undefined", str(probe), "-o", str(tmp_path / "p")], capture_output=True).returncode != 0:
+        pytest.skip("g++ has no AddressSanitizer runtime here")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = tmp_path / "fuzz_import"
+    src = [os.path.join(root, p) for p in ("tests/c/fuzz_import.cpp", "dynamo_b200/csrc/host/transfer_manager.cpp", "dynamo_b200/csrc/host/multicast.cpp")]
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer", "-pthread",
+           "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"), *src, "-L", os.path.join(root, "dynamo_b200"), "-lkvbm_kernels",
+           "-L", os.path.join(cuda, "lib64"), "-lcudart", "-ldl", f"-Wl,-rpath,{os.path.join(root, 'dynamo_b200')}",
+           f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}", "-o", str(exe)]
+    b = subprocess.run(cmd, capture_output=True, text=True)
+    assert b.returncode == 0, b.stderr[-2000:]
+    r = subprocess.run([str(exe), "20000"], capture_output=True, text=True, timeout=600, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1"))
+    assert r.returncode == 0 and "fuzz ok" in r.stdout, (r.stdout[-500:], r.stderr[-3000:])
+
+
+def test_layout_sizes_are_overflow_checked(mgr):
+    """config.rs:64-82 multiplies with saturating_mul; a config whose byte size does not fit can never be registered."""
+    huge = LayoutConfig(num_blocks=2**40, num_layers=2**20, outer_dim=2, page_size=2**10, inner_dim=2**10, dtype_width_bytes=2)
+    assert huge.required_bytes() == 2**64 - 1
+    buf = np.zeros(64, dtype=np.uint8)
+    with pytest.raises(KvbmError) as e:
+        mgr.register_fully_contiguous(huge, buf.ctypes.data, 2**63, StorageKind.System)
+    assert e.value.code == ErrorCode.CONFIG and "overflow" in e.value.msg
+    many_layers = std_cfg(1, num_layers=2**30)
+    with pytest.raises(KvbmError) as e:
+        mgr.register_fully_contiguous(many_layers, buf.ctypes.data, 2**62, StorageKind.System)
+    assert e.value.code == ErrorCode.CONFIG
