@@ -851,51 +851,88 @@ extern "C" const char* kvbm_last_error(void) { return g_last_error.c_str(); }
 
 extern "C" int kvbm_layout_config_validate(const kvbm_layout_config* cfg)
 {
+  try {
   if (!cfg) return fail(KVBM_ERR, "null config");
   std::string why;
   int rc = validate_config(*cfg, &why);
   return rc ? fail(rc, why) : KVBM_OK;
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 extern "C" size_t kvbm_layout_required_bytes(const kvbm_layout_config* cfg) { return cfg ? required_bytes(*cfg) : 0; }
 extern "C" size_t kvbm_layout_bytes_per_block(const kvbm_layout_config* cfg) { return cfg ? bytes_per_block(*cfg) : 0; }
 
 extern "C" int kvbm_select_direct_strategy(int src_kind, int dst_kind, const kvbm_transfer_capabilities* caps, kvbm_transfer_plan* out)
 {
+  try {
   if (!out) return fail(KVBM_ERR, "null plan");
   return select_direct_strategy(src_kind, dst_kind, caps, out);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" int kvbm_select_direct_strategy_remote(int src_kind, int dst_kind, int dst_is_remote, const kvbm_transfer_capabilities* caps,
                                                   kvbm_transfer_plan* out)
 {
+  try {
   if (!out) return fail(KVBM_ERR, "null plan");
   return select_direct_strategy(src_kind, dst_kind, caps, out, dst_is_remote != 0);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" int kvbm_select_strategy(int src_kind, int src_is_local, int dst_kind, int dst_is_local, const kvbm_transfer_capabilities* caps,
                                     kvbm_transfer_plan* out)
 {
+  try {
   if (!out) return fail(KVBM_ERR, "null plan");
   return select_strategy(src_kind, src_is_local != 0, dst_kind, dst_is_local != 0, caps, out);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" int kvbm_manager_select_strategy(kvbm_transfer_manager* m, kvbm_layout_handle src, kvbm_layout_handle dst, kvbm_transfer_plan* out)
 {
+  try {
   if (!m || !out) return fail(KVBM_ERR, "null argument");
   std::lock_guard<std::mutex> lk(m->mu);
   Layout *S = m->find(src), *D = m->find(dst);
   if (!S || !D) return fail(KVBM_ERR_HANDLE, "invalid layout handle");
   return select_strategy(S->storage, !S->remote, D->storage, !D->remote, &m->caps, out);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" int kvbm_validate_block_transfer(const size_t* src_ids, size_t n_src, const size_t* dst_ids, size_t n_dst,
                                             size_t src_num_blocks, size_t dst_num_blocks, int same_layout)
 {
+  try {
   return validate_block_transfer(src_ids, n_src, dst_ids, n_dst, src_num_blocks, dst_num_blocks, same_layout != 0);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" int kvbm_manager_create(int cuda_device_id, uint64_t worker_id, kvbm_transfer_manager** out)
 {
+  try {
   if (!out) return fail(KVBM_ERR, "null out");
   auto m = std::make_unique<kvbm_transfer_manager>();
   m->device = cuda_device_id;
@@ -915,6 +952,11 @@ extern "C" int kvbm_manager_create(int cuda_device_id, uint64_t worker_id, kvbm_
   }
   *out = m.release();
   return KVBM_OK;
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" void kvbm_manager_destroy(kvbm_transfer_manager* m)
@@ -963,18 +1005,25 @@ static int finish_register(kvbm_transfer_manager* m, Layout&& L, int storage_kin
 extern "C" int kvbm_manager_register_fully_contiguous(kvbm_transfer_manager* m, const kvbm_layout_config* cfg, void* base, size_t size,
                                                       int storage_kind, int device_id, kvbm_layout_handle* out)
 {
+  try {
   if (!m || !cfg || !out) return fail(KVBM_ERR, "null argument");
   Layout L;
   std::string why;
   int rc = make_fully_contiguous(*cfg, reinterpret_cast<uintptr_t>(base), size, &L, &why);
   if (rc) return fail(rc, why);
   return finish_register(m, std::move(L), storage_kind, device_id, out);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" int kvbm_manager_register_layer_separate(kvbm_transfer_manager* m, const kvbm_layout_config* cfg, void* const* layer_bases,
                                                     const size_t* layer_sizes, int block_dim, int storage_kind, int device_id,
                                                     kvbm_layout_handle* out)
 {
+  try {
   if (!m || !cfg || !out || !layer_bases || !layer_sizes) return fail(KVBM_ERR, "null argument");
   std::vector<uintptr_t> bases(cfg->num_layers);
   for (size_t i = 0; i < cfg->num_layers; ++i) bases[i] = reinterpret_cast<uintptr_t>(layer_bases[i]);
@@ -983,10 +1032,16 @@ extern "C" int kvbm_manager_register_layer_separate(kvbm_transfer_manager* m, co
   int rc = make_layer_separate(*cfg, bases.data(), layer_sizes, cfg->num_layers, block_dim, &L, &why);
   if (rc) return fail(rc, why);
   return finish_register(m, std::move(L), storage_kind, device_id, out);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" int kvbm_manager_unregister(kvbm_transfer_manager* m, kvbm_layout_handle h)
 {
+  try {
   if (!m) return fail(KVBM_ERR, "null manager");
   std::lock_guard<std::mutex> lk(m->mu);
   auto it = m->layouts.find(h);
@@ -1002,11 +1057,17 @@ extern "C" int kvbm_manager_unregister(kvbm_transfer_manager* m, kvbm_layout_han
   }
   m->layouts.erase(it);
   return KVBM_OK;
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" int kvbm_layout_memory_region(kvbm_transfer_manager* m, kvbm_layout_handle h, size_t block, size_t layer, size_t outer,
                                          uintptr_t* addr, size_t* size)
 {
+  try {
   if (!m || !addr) return fail(KVBM_ERR, "null argument");
   std::lock_guard<std::mutex> lk(m->mu);
   Layout* L = m->find(h);
@@ -1014,6 +1075,11 @@ extern "C" int kvbm_layout_memory_region(kvbm_transfer_manager* m, kvbm_layout_h
   std::string why;
   int rc = L->memory_region(block, layer, outer, addr, size, &why);
   return rc ? fail(rc, why) : KVBM_OK;
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" int kvbm_layout_is_fully_contiguous(kvbm_transfer_manager* m, kvbm_layout_handle h)
@@ -1026,6 +1092,7 @@ extern "C" int kvbm_layout_is_fully_contiguous(kvbm_transfer_manager* m, kvbm_la
 
 extern "C" int kvbm_manager_enable_peer_access(kvbm_transfer_manager* m, int peer_device)
 {
+  try {
   if (!m || m->device < 0) return fail(KVBM_ERR_CUDA, "manager has no CUDA device");
   if (peer_device == m->device) return KVBM_OK;
   DeviceGuard g(m->device);
@@ -1039,6 +1106,11 @@ extern "C" int kvbm_manager_enable_peer_access(kvbm_transfer_manager* m, int pee
   }
   if (e != cudaSuccess) return fail_cuda(e, "cudaDeviceEnablePeerAccess");
   return KVBM_OK;
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 // base address + size of the cudaMalloc allocation containing p (driver entry point, no -lcuda needed)
@@ -1064,6 +1136,7 @@ static int allocation_range(uintptr_t p, uintptr_t* base, size_t* size)
 
 extern "C" int kvbm_manager_export_metadata(kvbm_transfer_manager* m, kvbm_layout_handle h, void* buf, size_t cap, size_t* len)
 {
+  try {
   if (!m || !len) return fail(KVBM_ERR, "null argument");
   std::lock_guard<std::mutex> lk(m->mu);
   Layout* L = m->find(h);
@@ -1111,6 +1184,11 @@ extern "C" int kvbm_manager_export_metadata(kvbm_transfer_manager* m, kvbm_layou
     p += sizeof(ba);
   }
   return KVBM_OK;
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 static int import_metadata_impl(kvbm_transfer_manager* m, const void* buf, size_t len, const void* const* local_bases, size_t num_local_bases,
@@ -1118,7 +1196,13 @@ static int import_metadata_impl(kvbm_transfer_manager* m, const void* buf, size_
 
 extern "C" int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void* buf, size_t len, kvbm_layout_handle* out)
 {
+  try {
   return import_metadata_impl(m, buf, len, nullptr, 0, out);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 // Host pools of another process that THIS process has mapped itself (POSIX / SysV shared memory, a hugetlbfs file, memory
@@ -1127,8 +1211,14 @@ extern "C" int kvbm_manager_import_metadata(kvbm_transfer_manager* m, const void
 extern "C" int kvbm_manager_import_metadata_mapped(kvbm_transfer_manager* m, const void* buf, size_t len, const void* const* local_bases,
                                                    size_t num_local_bases, kvbm_layout_handle* out)
 {
+  try {
   if (!local_bases || num_local_bases == 0) return fail(KVBM_ERR, "local_bases: one address per allocation of the layout");
   return import_metadata_impl(m, buf, len, local_bases, num_local_bases, out);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 static int import_metadata_impl(kvbm_transfer_manager* m, const void* buf, size_t len, const void* const* local_bases, size_t num_local_bases,
@@ -1211,6 +1301,7 @@ static int import_metadata_impl(kvbm_transfer_manager* m, const void* buf, size_
 // layer_separate.rs:91-101): the format of one block of a registered layout; Unknown until set.
 extern "C" int kvbm_manager_set_kv_block_layout(kvbm_transfer_manager* m, kvbm_layout_handle h, int kv_layout)
 {
+  try {
   if (!m) return fail(KVBM_ERR, "null manager");
   if (kv_layout < KVBM_KV_UNKNOWN || kv_layout > KVBM_KV_OPERATIONAL_NHD) return fail(KVBM_ERR, "unknown KvBlockLayout");
   std::lock_guard<std::mutex> lk(m->mu);
@@ -1226,6 +1317,11 @@ extern "C" int kvbm_manager_set_kv_block_layout(kvbm_transfer_manager* m, kvbm_l
   }
   L->kv_block_layout = kv_layout;
   return KVBM_OK;
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" int kvbm_manager_kv_block_layout(kvbm_transfer_manager* m, kvbm_layout_handle h)
@@ -1250,16 +1346,23 @@ extern "C" int kvbm_manager_set_capabilities(kvbm_transfer_manager* m, const kvb
 extern "C" int kvbm_manager_execute_transfer(kvbm_transfer_manager* m, kvbm_layout_handle src, const size_t* src_ids, kvbm_layout_handle dst,
                                              const size_t* dst_ids, size_t n, const kvbm_transfer_options* opts, kvbm_notification* out)
 {
+  try {
   if (!m) return fail(KVBM_ERR, "null manager");
   const size_t* s[1] = {src_ids};
   const size_t* d[1] = {dst_ids};
   return execute(m, src, 1, &dst, s, d, n, true, opts, out);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" int kvbm_manager_execute_fanout(kvbm_transfer_manager* m, kvbm_layout_handle src, int num_dsts, const kvbm_layout_handle* dsts,
                                            const size_t* const* src_ids, const size_t* const* dst_ids, size_t n, int replicate,
                                            const kvbm_transfer_options* opts, kvbm_notification* out)
 {
+  try {
   if (!m || !dsts) return fail(KVBM_ERR, "null argument");
   bool rep = replicate != 0;
   if (!rep && src_ids) {
@@ -1268,6 +1371,11 @@ extern "C" int kvbm_manager_execute_fanout(kvbm_transfer_manager* m, kvbm_layout
       if (src_ids[d] != src_ids[0]) rep = false;
   }
   return execute(m, src, num_dsts, dsts, src_ids, dst_ids, n, rep, opts, out);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" int kvbm_notification_is_complete(kvbm_transfer_manager* m, kvbm_notification n)
@@ -1287,6 +1395,7 @@ extern "C" int kvbm_notification_is_complete(kvbm_transfer_manager* m, kvbm_noti
 
 extern "C" int kvbm_notification_wait(kvbm_transfer_manager* m, kvbm_notification n, int64_t timeout_us)
 {
+  try {
   if (!m) return fail(KVBM_ERR, "null manager");
   const auto t0 = std::chrono::steady_clock::now();
   unsigned spins = 0;
@@ -1301,6 +1410,11 @@ extern "C" int kvbm_notification_wait(kvbm_transfer_manager* m, kvbm_notificatio
         return fail(KVBM_ERR_TIMEOUT, "transfer did not complete in time");
       sched_yield();
     }
+  }
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
   }
 }
 
@@ -1389,6 +1503,7 @@ static int copy_out(const void* data, size_t need, void* buf, size_t cap, size_t
 
 extern "C" int kvbm_layout_descriptor_json(kvbm_transfer_manager* m, kvbm_layout_handle h, char* buf, size_t cap, size_t* len)
 {
+  try {
   if (!m || !len) return fail(KVBM_ERR, "null argument");
   std::string js;
   {
@@ -1398,10 +1513,16 @@ extern "C" int kvbm_layout_descriptor_json(kvbm_transfer_manager* m, kvbm_layout
     js = kvbm_wire::descriptor_to_json(to_wire(*L, agent_name_of(m->worker_id)));
   }
   return copy_out(js.data(), js.size(), buf, cap, len);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 extern "C" int kvbm_manager_import_descriptor_json(kvbm_transfer_manager* m, const char* json, size_t len, kvbm_layout_handle* out)
 {
+  try {
   if (!m || !json || !out) return fail(KVBM_ERR, "null argument");
   kvbm_wire::Descriptor d;
   std::string why;
@@ -1428,6 +1549,11 @@ extern "C" int kvbm_manager_import_descriptor_json(kvbm_transfer_manager* m, con
                       : d.location == kvbm_wire::kDisk   ? KVBM_STORAGE_DISK
                                                          : KVBM_STORAGE_SYSTEM;
   return finish_register(m, std::move(L), storage, d.location == kvbm_wire::kDevice ? static_cast<int>(d.location_arg) : 0, out);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 // TransferManager::export_metadata (manager/mod.rs:112, registry :519-556): every local host / device layout, one blob.
@@ -1435,6 +1561,7 @@ extern "C" int kvbm_manager_import_descriptor_json(kvbm_transfer_manager* m, con
 // CUDA IPC handle per allocation, so the importing process can map the pools and reach them over NVLink.
 extern "C" int kvbm_manager_export_serialized_layout(kvbm_transfer_manager* m, void* buf, size_t cap, size_t* len)
 {
+  try {
   if (!m || !len) return fail(KVBM_ERR, "null argument");
   std::vector<kvbm_layout_handle> handles;
   kvbm_wire::Bundle b;
@@ -1470,12 +1597,18 @@ extern "C" int kvbm_manager_export_serialized_layout(kvbm_transfer_manager* m, v
   b.nixl_metadata = std::move(t.out);
   const std::vector<uint8_t> bytes = kvbm_wire::encode_bundle(b);
   return copy_out(bytes.data(), bytes.size(), buf, cap, len);
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
 
 // TransferManager::import_metadata (manager/mod.rs:130, registry :572-633)
 extern "C" int kvbm_manager_import_serialized_layout(kvbm_transfer_manager* m, const void* buf, size_t len, kvbm_layout_handle* out, size_t cap,
                                                      size_t* n_out)
 {
+  try {
   if (!m || !buf || !n_out) return fail(KVBM_ERR, "null argument");
   kvbm_wire::Bundle b;
   std::string why;
@@ -1535,4 +1668,9 @@ extern "C" int kvbm_manager_import_serialized_layout(kvbm_transfer_manager* m, c
   std::lock_guard<std::mutex> lk(m->mu);
   m->loaded_remotes.insert(key);
   return KVBM_OK;
+  } catch (const std::exception& e) {
+    return kvbm_host::set_last_error(KVBM_ERR, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return kvbm_host::set_last_error(KVBM_ERR, "internal error");
+  }
 }
