@@ -423,3 +423,22 @@ def test_event_publish_is_safe_from_many_threads():
     finally:
         pub.shutdown()
         tree.close()
+
+
+def test_remove_worker_verifies_hash_removal_and_default_tree():
+    """radix_tree.rs:1035-1141 (test_radix_tree_default, test_remove_worker_verifies_hash_removal): create_store_event(worker,
+    id, [h..]) stores block hashes h*100 under tokens hashes h."""
+    t = R.RadixTree()
+    assert t.lookup_len() == 0 and t.node_info([]) == (0, 0) and t.current_size() == 0      # empty root, empty lookup
+    t.apply_stored(0, [100, 200, 300], [1, 2, 3])
+    t.apply_stored(1, [100, 200, 300], [1, 2, 3])
+    t.apply_stored(2, [100, 400, 500], [1, 4, 5])
+    assert t.lookup_size(0) == 3
+    assert t.node_info([1]) == (3, 2)                      # block 100: all three workers; children: tokens 2 and 4
+    t.remove_worker(0)
+    assert t.lookup_size(0) is None and t.lookup_len() == 2
+    assert t.node_info([1])[0] == 2                        # workers 1 and 2 remain on block 100
+    assert t.node_info([1, 2])[0] == 1                     # block 200: only worker 1
+    assert t.find_matches([1, 2, 3]).scores == {(1, 0): 3, (2, 0): 1}
+    assert t.get_workers() == [1, 2]
+    t.close()
