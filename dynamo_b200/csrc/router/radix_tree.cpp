@@ -30,6 +30,11 @@ using Clock = std::chrono::steady_clock;
 struct Block;  // RadixBlock
 using BlockPtr = std::shared_ptr<Block>;
 struct Block {
+  std::unordered_set<Block*>* registry = nullptr;   // the owning tree's set of live blocks (see ~kvr_radix_tree)
+  ~Block()
+  {
+    if (registry) registry->erase(this);
+  }
   std::unordered_map<uint64_t, BlockPtr> children;  // LocalBlockHash (tokens hash) -> child
   WorkerSet workers;
   bool has_hash = false;
@@ -78,23 +83,27 @@ struct kvr_radix_tree {
   bool track_frequency = false;
   std::chrono::milliseconds expiration{0};
 
-  // children chains can be very deep: tear down iteratively (the reference does the same, radix_tree.rs:104-137)
+  std::unordered_set<Block*> live;  // every block this tree created that is still alive
+
+  // Tear down without recursion (chains are as deep as a sequence has blocks; the reference's Drop is iterative too,
+  // radix_tree.rs:104-137) and without trusting the graph to be a tree: hand-made hashes can link blocks into cycles, also
+  // into cycles no longer reachable from the root.  Every live block is pinned, every edge is cut, then the pins go.
   ~kvr_radix_tree()
   {
-    std::vector<BlockPtr> stack;
-    for (auto& kv : root->children) stack.push_back(std::move(kv.second));
-    root->children.clear();
+    std::vector<BlockPtr> pins;
+    pins.reserve(live.size());
+    auto pin = [&](const BlockPtr& p) { pins.push_back(p); };
+    for (auto& kv : root->children) pin(kv.second);
     for (auto& wl : lookup)
-      for (auto& kv : wl.second) stack.push_back(std::move(kv.second));
+      for (auto& kv : wl.second) pin(kv.second);
+    root->children.clear();
     lookup.clear();
-    while (!stack.empty()) {
-      BlockPtr b = std::move(stack.back());
-      stack.pop_back();
-      if (b.use_count() == 1) {
-        for (auto& kv : b->children) stack.push_back(std::move(kv.second));
-        b->children.clear();
-      }
-    }
+    // blocks only other blocks still own: pin them through their owners' child maps before the maps are cleared
+    std::vector<Block*> todo(live.begin(), live.end());
+    for (Block* b : todo)
+      for (auto& kv : b->children) pin(kv.second);
+    for (Block* b : todo) b->children.clear();
+    for (Block* b : todo) b->registry = nullptr;   // `live` dies with the tree, before or after the last pin
   }
 
   void remove_or_clear(uint64_t worker_id, bool keep_worker)  // radix_tree.rs:456-480
@@ -180,6 +189,8 @@ extern "C" int kvr_tree_apply_stored(kvr_radix_tree* t, uint64_t worker_id, uint
         child = known->second;
       } else {
         child = std::make_shared<Block>();
+        child->registry = &t->live;
+        t->live.insert(child.get());
         child->has_hash = true;
         child->block_hash = block_hashes[i];
       }
