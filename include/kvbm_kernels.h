@@ -198,7 +198,8 @@ typedef struct kvbm_permute_side {
  * agree on num_layers, outer_dim and region_bytes = page_size * num_heads * row_bytes; row_bytes (head_dim * element size)
  * must be a multiple of 16 in 16..65536 (powers of two take the shift-and-mask walk) and every stride a multiple of 16
  * (cudaErrorInvalidValue otherwise).  `done_flag`
- * (nullable, device-visible) receives `epoch` with system scope after the last byte landed.  One launch, stream-ordered. */
+ * (nullable, device-visible) receives `epoch` with system scope after the last byte landed, `completion_flag` likewise
+ * `completion_value` (a one-thread signal launch behind the permuting launch; none when both are NULL).  Stream-ordered. */
 cudaError_t kvbm_kernels_paged_permute(const kvbm_permute_side* src, const kvbm_permute_side* dst, int num_blocks,
                                        int layer_begin, int layer_end, uint32_t num_heads, uint32_t page_size,
                                        uint32_t row_bytes, uint32_t* done_flag, uint32_t epoch, uint32_t* completion_flag,
